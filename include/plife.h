@@ -1,0 +1,185 @@
+/*
+ * plife.h -- C ABI of the B200-native Particle Life physics step.
+ *
+ * Drop-in boundary for the reference's `Physics` object
+ * (src/main/java/com/particle_life/backend/Physics.java, "B/" below; "A/" is
+ * .../particle_life/app/).  Each entry point names the reference interface it
+ * replaces.  A JNI / Java-FFM shim binds exactly these symbols (see
+ * INTEGRATION.md); nothing here exposes torch or C++ types.
+ *
+ * Conventions
+ *   - every function returns an int status (PLIFE_OK == 0, negative = error)
+ *     unless documented otherwise; nothing throws across the ABI;
+ *   - the caller owns host buffers, the library owns device buffers; no host
+ *     pointer is retained after a call returns;
+ *   - a handle is single-owner: one calling thread at a time (the reference
+ *     drives Physics from its single Loop thread, B/Loop.java:102-121).
+ *     plife_request_stop() and plife_last_error() may be called from any thread;
+ *   - particle order is the reference's: after every step the particle array is
+ *     in stable cell-sorted order (B/Physics.java:343-353).
+ *   - there is NO CPU fallback: without a usable CUDA device plife_create()
+ *     fails with PLIFE_ERR_CUDA.
+ */
+#ifndef PLIFE_H
+#define PLIFE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLIFE_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define PLIFE_OK 0
+#define PLIFE_ERR_INVALID (-1) /* bad argument (IllegalArgumentException in the reference) */
+#define PLIFE_ERR_OOM (-2)     /* device or host allocation failed */
+#define PLIFE_ERR_CUDA (-3)    /* CUDA runtime error; sticky errors poison the handle */
+#define PLIFE_ERR_NCCL (-4)    /* reserved for the multi-GPU exchange */
+#define PLIFE_ERR_STATE (-5)   /* call not valid in the handle's current state */
+#define PLIFE_ERR_STOPPED (-6) /* plife_request_stop() interrupted a multi-step call */
+
+/* arithmetic / storage precision of a handle */
+#define PLIFE_F32 0 /* fp32 storage and arithmetic; cell assignment still in fp64 */
+#define PLIFE_F64 1 /* fp64 throughout; bit-exact with the reference's operation order */
+
+/* plife_config.flags */
+#define PLIFE_FLAG_UNSTABLE_SORT 1 /* skip the in-cell stable ordering (faster; order in a cell arbitrary) */
+#define PLIFE_FLAG_NO_GRAPH 2      /* never capture the step into a CUDA graph */
+
+/* Accelerator kinds (B/Accelerator.java:5-17).  Kind 0 is the only accelerator
+ * in the reference snapshot (A/Main.java:275-280); kinds 1..5 are
+ * builder-defined (no reference definition). */
+#define PLIFE_ACC_PARTICLE_LIFE 0    /* params = {beta (default 0.3)} */
+#define PLIFE_ACC_PARTICLE_LIFE_R 1  /* kind 0 force, divided by r once more */
+#define PLIFE_ACC_PARTICLE_LIFE_R2 2 /* kind 0 force, divided by r^2 more */
+#define PLIFE_ACC_ROTATOR_90 3       /* a*(1-d), rotated by 90 degrees */
+#define PLIFE_ACC_ROTATOR_ATTR 4     /* (1-d), rotated by -a*pi */
+#define PLIFE_ACC_PLANETS 5          /* 0.01 / max(d, 0.01)^2 attraction */
+#define PLIFE_ACC_KIND_COUNT 6
+
+typedef struct plife_handle plife_handle;
+
+typedef struct plife_config {
+    int32_t device;    /* CUDA device ordinal */
+    int32_t precision; /* PLIFE_F32 | PLIFE_F64 */
+    int64_t capacity;  /* particle capacity hint (buffers grow on upload) */
+    int32_t flags;     /* PLIFE_FLAG_* */
+    int32_t reserved;
+    void *stream;      /* cudaStream_t to run on, or NULL: the library creates its own */
+} plife_config;
+
+/* B/PhysicsSettings.java:8-37 minus `dt` (per step) and `matrix` (own setter) */
+typedef struct plife_settings {
+    double rmax;     /* :13, 0 < rmax <= 1 (rmax > 1 makes nx = 0: the reference throws, B/Physics.java:362-374) */
+    double friction; /* :27 */
+    double force;    /* :32 */
+    int32_t wrap;    /* :8  */
+    int32_t reserved;
+} plife_settings;
+
+/* counters of the most recent step */
+typedef struct plife_step_stats {
+    int64_t n;          /* particles */
+    int32_t nx, ny;     /* grid, B/Physics.java:82-85 */
+    int64_t pair_evals; /* candidate pairs (i,j), j != i, in the 3x3 cells: B/Physics.java:423-439 */
+    int64_t steps;      /* steps executed by this handle so far */
+} plife_step_stats;
+
+/* slots of plife_kernel_times() */
+#define PLIFE_K_BIN 0     /* cell id + histogram */
+#define PLIFE_K_SCAN 1    /* exclusive scan over cells */
+#define PLIFE_K_SCATTER 2 /* cursor scatter of source indices */
+#define PLIFE_K_GATHER 3  /* stable in-cell rank + reorder */
+#define PLIFE_K_FORCE 4   /* 3x3 force + friction + integrate + wrap */
+#define PLIFE_K_COUNT 5
+
+int plife_version(void);
+const char *plife_status_string(int status);
+
+/* new ExtendedPhysics(...) / Physics ctor (A/Main.java:281-285, B/Physics.java:65-80).
+ * Defaults after create: PhysicsSettings defaults (rmax 0.02, friction 0.85,
+ * force 1.0, wrap on), accelerator kind 0 with beta 0.3, a 1x1 zero matrix and
+ * zero particles; the host-side setters produce the initial state and upload it. */
+int plife_create(const plife_config *cfg, plife_handle **out);
+/* Physics.kill() + GC (B/Physics.java:156-158) */
+int plife_destroy(plife_handle *h);
+
+/* writes to physics.settings.{rmax,friction,force,wrap} (A/Main.java:811,818,827,834) */
+int plife_set_settings(plife_handle *h, const plife_settings *s);
+int plife_get_settings(const plife_handle *h, plife_settings *out);
+
+/* settings.matrix = ... (A/Main.java:714,1330), Physics.setMatrixSize (B/Physics.java:238-258).
+ * row_major[i*m+j] = matrix.get(i,j): i = own type, j = other type (B/Physics.java:435).
+ * 1 <= m <= 256 (A/Main.java:745).  PLIFE_ERR_STATE if a resident particle has
+ * type >= m (the reference's ensureTypes, B/Physics.java:266-272, is host-side:
+ * download, retype, upload). */
+int plife_set_matrix(plife_handle *h, int32_t m, const double *row_major);
+/* settings.matrix.set(i,j,v) (A/Main.java:703) */
+int plife_set_matrix_entry(plife_handle *h, int32_t i, int32_t j, double v);
+int plife_get_matrix(const plife_handle *h, int32_t *m_out, double *row_major_out, int32_t capacity_m);
+
+/* physics.accelerator = ... (B/Physics.java:27,70).  A Java lambda cannot run on
+ * the device, so accelerators are device functors selected by kind. */
+int plife_set_accelerator(plife_handle *h, int32_t kind, const double *params, int32_t nparams);
+
+/* physics.particles = ... / setParticleCount / setPositions / setTypes
+ * (B/Physics.java:15,166,190,509).  Host SoA in fp64: pos_xy and vel_xy are
+ * interleaved (x0,y0,x1,y1,...); z is identically 0 (B/Range.java:43,71,86).
+ * vel_xy may be NULL (zero velocities, B/Physics.java:300-302).  id may be
+ * NULL (ids 0..n-1).  Validates 0 <= x,y <= 1 and 0 <= type < m. */
+int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double *vel_xy,
+                 const int32_t *type, const uint32_t *id);
+/* PhysicsSnapshot.take (A/PhysicsSnapshot.java:24-62).  Any pointer may be NULL.
+ * Order = current particle order (cell-sorted after a step). Synchronises. */
+int plife_download(plife_handle *h, double *pos_xy, double *vel_xy, int32_t *type, uint32_t *id);
+/* float snapshot for rendering: xy + vxy as fp32 (display-time handoff) */
+int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type);
+
+/* Headless generators with the distributions of the reference's default setters
+ * (B/DefaultPositionSetter.java, B/DefaultTypeSetter.java, B/DefaultMatrix.java:25-31)
+ * on a seeded SplitMix64 stream; bit-identical to plife/synth.py. */
+int plife_init_uniform(plife_handle *h, int64_t n, uint64_t seed);
+int plife_random_matrix(plife_handle *h, int32_t m, uint64_t seed);
+
+/* physics.settings.dt = dt; physics.update() (A/Main.java:292-295, B/Physics.java:112),
+ * nsteps times.  Asynchronous on the handle's stream. */
+int plife_step(plife_handle *h, double dt, int32_t nsteps);
+int plife_sync(plife_handle *h);
+
+/* physics.particles.length */
+int64_t plife_count(const plife_handle *h);
+/* ExtendedPhysics.getTypeCount (A/ExtendedPhysics.java:19-26); out has m entries */
+int plife_type_histogram(plife_handle *h, int64_t *out_m);
+
+/* Physics.forceUpdateStop (B/Physics.java:149-151): honoured between steps of a
+ * multi-step plife_step(); thread-safe. */
+int plife_request_stop(plife_handle *h);
+/* message of the last failing call on this handle; owned by the handle */
+const char *plife_last_error(const plife_handle *h);
+
+/* ---- parity / measurement instrumentation ---- */
+
+/* `containers` of the most recent step (B/Physics.java:18): END offset of every
+ * cell, nx*ny int32.  Synchronises. */
+int plife_get_containers(plife_handle *h, int32_t *out, int64_t capacity);
+int plife_get_step_stats(plife_handle *h, plife_step_stats *out);
+/* In-range neighbour set of every particle for the CURRENT state and settings
+ * (re-bins first; does not advance time): count and an order-independent hash
+ * (sum of mix64(id_j)) per particle, in the sorted order.  Synchronises. */
+int plife_debug_neighbors(plife_handle *h, int32_t *count, uint64_t *hash);
+/* Per-kernel device time: enable, run steps, read accumulated milliseconds and
+ * launch counts (PLIFE_K_* slots).  Profiling inserts events between kernels
+ * and disables graph replay. */
+int plife_set_profiling(plife_handle *h, int32_t enabled);
+int plife_kernel_times(plife_handle *h, double *ms_out, int64_t *launches_out);
+/* device pointers of the current state (for CUDA-GL interop or torch views):
+ * F32: pos = float4{x,y,type bits,id bits}[n], vel = float2[n]
+ * F64: pos = double2[n], vel = double2[n], type = int32[n], id = uint32[n] */
+int plife_device_ptrs(plife_handle *h, void **pos, void **vel, void **type, void **id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLIFE_H */

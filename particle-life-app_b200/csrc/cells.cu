@@ -1,0 +1,419 @@
+// Per-step cell-list build: the reference's serial counting sort
+// (Physics.makeContainers, B/Physics.java:309-354) as four data-parallel passes
+//   K_BIN      cell id per particle + per-cell histogram      (:329-332)
+//   K_SCAN     exclusive prefix over the nx*ny cells          (:335-340)
+//   K_SCATTER  cursor scatter of source indices               (:343-348)
+//   K_GATHER   stable in-cell rank + reorder of the SoA state (:343-353)
+// plus the small utility kernels (type histogram, seeded generator, snapshot).
+//
+// Stability: the reference's scatter is stable (array order inside a cell is
+// the previous array order).  The atomic cursor scatter is not, so K_GATHER
+// ranks every slot's source index among the source indices of its cell and
+// writes to start+rank; the result is exactly the reference's permutation.
+#include "plife_internal.h"
+
+namespace plife {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// B/Physics.java:362-375 getContainerIndex: (int)(x / containerSize) in fp64,
+// with the `== nx -> nx-1` clamp for x == 1.0.
+__device__ __forceinline__ int container_index(double x, double y, const Grid &g)
+{
+    int cx = (int)(x / g.cs);
+    int cy = (int)(y / g.cs);
+    if (cx == g.nx) cx = g.nx - 1;
+    if (cy == g.ny) cy = g.ny - 1;
+    return cx + cy * g.nx;
+}
+
+__global__ void __launch_bounds__(kThreads) bin_f32(const float4 *__restrict__ pt, int n, Grid g,
+                                                    int32_t *__restrict__ cell, int32_t *__restrict__ count)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float4 p = __ldg(&pt[i]);
+    int c = container_index((double)p.x, (double)p.y, g);
+    cell[i] = c;
+    atomicAdd(&count[c], 1);
+}
+
+__global__ void __launch_bounds__(kThreads) bin_f64(const double2 *__restrict__ pos, int n, Grid g,
+                                                    int32_t *__restrict__ cell, int32_t *__restrict__ count)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    double2 p = __ldg(&pos[i]);
+    int c = container_index(p.x, p.y, g);
+    cell[i] = c;
+    atomicAdd(&count[c], 1);
+}
+
+// ---- exclusive scan over cells: tile sums -> scan of sums -> apply ----
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems; // 4096 cells per CTA
+
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix and the block total
+__device__ __forceinline__ int block_exclusive_scan(int v, int &total, int *smem /* >= 33 ints */)
+{
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = warp_inclusive_scan(v, lane);
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        int w = lane < nw ? smem[lane] : 0;
+        int winc = warp_inclusive_scan(w, lane);
+        smem[lane] = winc - w;
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    int r = smem[warp] + inc - v;
+    total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *__restrict__ count, int64_t ncell,
+                                                               int32_t *__restrict__ tile_sums)
+{
+    __shared__ int sm[33];
+    int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int s = 0;
+    // vectorised: each thread sums 16 consecutive cells (4 x int4)
+    int64_t first = base + (int64_t)threadIdx.x * kScanItems;
+    if (first + kScanItems <= ncell) {
+        const int4 *p = reinterpret_cast<const int4 *>(count + first);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; k++) {
+            int4 v = __ldg(p + k);
+            s += v.x + v.y + v.z + v.w;
+        }
+    } else {
+        for (int k = 0; k < kScanItems; k++)
+            if (first + k < ncell) s += count[first + k];
+    }
+    int total;
+    block_exclusive_scan(s, total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_sums(int32_t *__restrict__ tile_sums, int ntiles)
+{
+    __shared__ int sm[33];
+    int carry = 0;
+    for (int base = 0; base < ntiles; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < ntiles ? tile_sums[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, total, sm);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+// writes the exclusive prefix (the cursor start of every cell) into cell_end and
+// zeroes count for the next step
+__global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__ count, int64_t ncell,
+                                                           const int32_t *__restrict__ tile_sums,
+                                                           int32_t *__restrict__ cell_end)
+{
+    __shared__ int sm[33];
+    int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int64_t first = base + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+    bool full = first + kScanItems <= ncell;
+    if (full) {
+        int4 *p = reinterpret_cast<int4 *>(count + first);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; k++) {
+            int4 q = p[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            p[k] = make_int4(0, 0, 0, 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            v[k] = 0;
+            if (first + k < ncell) {
+                v[k] = count[first + k];
+                count[first + k] = 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) s += v[k];
+    int total;
+    int ex = block_exclusive_scan(s, total, sm) + tile_sums[blockIdx.x];
+    if (full) {
+        int4 *o = reinterpret_cast<int4 *>(cell_end + first);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; k++) {
+            int4 q;
+            q.x = ex; ex += v[4 * k];
+            q.y = ex; ex += v[4 * k + 1];
+            q.z = ex; ex += v[4 * k + 2];
+            q.w = ex; ex += v[4 * k + 3];
+            o[k] = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if (first + k < ncell) cell_end[first + k] = ex;
+            ex += v[k];
+        }
+    }
+}
+
+// B/Physics.java:343-348: `i = containers[ci]; buffer[i] = p; containers[ci]++`.
+// Afterwards cell_end[ci] is the END offset of cell ci, as in the reference.
+__global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n,
+                                                         int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    int c = __ldg(&cell[i]);
+    int dst = atomicAdd(&cell_end[c], 1);
+    perm[dst] = i;
+}
+
+__device__ __forceinline__ int stable_slot(int d, int src, const int32_t *__restrict__ cell,
+                                           const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm)
+{
+    int c = __ldg(&cell[src]);
+    int s = c == 0 ? 0 : __ldg(&cell_end[c - 1]);
+    int e = __ldg(&cell_end[c]);
+    int rank = 0;
+    for (int k = s; k < e; k++) rank += (__ldg(&perm[k]) < src) ? 1 : 0;
+    return s + rank;
+}
+
+template <bool STABLE>
+__global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, const float2 *__restrict__ vel_in,
+                                                       float4 *__restrict__ pt_out, float2 *__restrict__ vel_out, int n,
+                                                       const int32_t *__restrict__ cell, const int32_t *__restrict__ cell_end,
+                                                       const int32_t *__restrict__ perm)
+{
+    int d = blockIdx.x * kThreads + threadIdx.x;
+    if (d >= n) return;
+    int src = __ldg(&perm[d]);
+    float4 p = __ldg(&pt_in[src]);
+    float2 v = __ldg(&vel_in[src]);
+    int dst = STABLE ? stable_slot(d, src, cell, cell_end, perm) : d;
+    pt_out[dst] = p;
+    vel_out[dst] = v;
+}
+
+template <bool STABLE>
+__global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out, int n, const int32_t *__restrict__ cell,
+                                                       const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm)
+{
+    int d = blockIdx.x * kThreads + threadIdx.x;
+    if (d >= n) return;
+    int src = __ldg(&perm[d]);
+    double2 p = __ldg(&in.pos[src]);
+    double2 v = __ldg(&in.vel[src]);
+    int t = __ldg(&in.type[src]);
+    uint32_t id = __ldg(&in.id[src]);
+    int dst = STABLE ? stable_slot(d, src, cell, cell_end, perm) : d;
+    out.pos[dst] = p;
+    out.vel[dst] = v;
+    out.type[dst] = t;
+    out.id[dst] = id;
+}
+
+__global__ void __launch_bounds__(kThreads) type_hist_f32(const float4 *__restrict__ pt, int n, int m,
+                                                          unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[256];
+    for (int k = threadIdx.x; k < 256; k += kThreads) sh[k] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        int t = __float_as_int(__ldg(&pt[i]).z);
+        if (t >= 0 && t < m) atomicAdd(&sh[t], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += kThreads)
+        if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
+__global__ void __launch_bounds__(kThreads) type_hist_f64(const int32_t *__restrict__ type, int n, int m,
+                                                          unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[256];
+    for (int k = threadIdx.x; k < 256; k += kThreads) sh[k] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        int t = __ldg(&type[i]);
+        if (t >= 0 && t < m) atomicAdd(&sh[t], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += kThreads)
+        if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
+// SplitMix64 counter stream, bit-identical to plife/synth.py
+__device__ __forceinline__ double splitmix_u01(uint64_t seed, uint64_t counter)
+{
+    uint64_t z = seed + (counter + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(kThreads) init_uniform_f32(float4 *pt, float2 *vel, int n, int m, uint64_t seed)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    uint64_t c = 4ull * (uint64_t)i;
+    double x = splitmix_u01(seed, c), y = splitmix_u01(seed, c + 1);
+    int t = min((int)floor(splitmix_u01(seed, c + 2) * m), m - 1);
+    pt[i] = make_float4((float)x, (float)y, __int_as_float(t), __uint_as_float((uint32_t)i));
+    vel[i] = make_float2(0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(kThreads) init_uniform_f64(StateF64 s, int n, int m, uint64_t seed)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    uint64_t c = 4ull * (uint64_t)i;
+    s.pos[i] = make_double2(splitmix_u01(seed, c), splitmix_u01(seed, c + 1));
+    s.vel[i] = make_double2(0.0, 0.0);
+    s.type[i] = min((int)floor(splitmix_u01(seed, c + 2) * m), m - 1);
+    s.id[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kThreads) snapshot_from_f32(const float4 *__restrict__ pt, const float2 *__restrict__ vel,
+                                                              int n, float2 *pos_out, float2 *vel_out, int32_t *type_out)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float4 p = __ldg(&pt[i]);
+    if (pos_out) pos_out[i] = make_float2(p.x, p.y);
+    if (vel_out) vel_out[i] = __ldg(&vel[i]);
+    if (type_out) type_out[i] = __float_as_int(p.z);
+}
+
+__global__ void __launch_bounds__(kThreads) snapshot_from_f64(StateF64 s, int n, float2 *pos_out, float2 *vel_out,
+                                                              int32_t *type_out)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    if (pos_out) {
+        double2 p = s.pos[i];
+        pos_out[i] = make_float2((float)p.x, (float)p.y);
+    }
+    if (vel_out) {
+        double2 v = s.vel[i];
+        vel_out[i] = make_float2((float)v.x, (float)v.y);
+    }
+    if (type_out) type_out[i] = s.type[i];
+}
+
+inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+} // namespace
+
+cudaError_t launch_bin(plife_handle *h, const Grid &g)
+{
+    int n = (int)h->n;
+    if (n == 0) return cudaSuccess;
+    if (h->precision == PLIFE_F32)
+        bin_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, n, g, h->d_cell, h->d_count);
+    else
+        bin_f64<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s64[h->cur].pos, n, g, h->d_cell, h->d_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan(plife_handle *h, const Grid &g)
+{
+    int64_t ncell = (int64_t)g.nx * g.ny;
+    int ntiles = (int)((ncell + kScanTile - 1) / kScanTile);
+    scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, h->d_tile_sums);
+    scan_sums<<<1, 1024, 0, h->stream>>>(h->d_tile_sums, ntiles);
+    scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, h->d_tile_sums, h->d_cell_end);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(plife_handle *h, const Grid &)
+{
+    int n = (int)h->n;
+    if (n == 0) return cudaSuccess;
+    scatter_perm<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, h->d_cell_end, h->d_perm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather(plife_handle *h, const Grid &)
+{
+    int n = (int)h->n;
+    if (n == 0) return cudaSuccess;
+    int a = h->cur, b = h->cur ^ 1;
+    bool stable = !(h->flags & PLIFE_FLAG_UNSTABLE_SORT);
+    int nb = blocks_for(n, kThreads);
+    if (h->precision == PLIFE_F32) {
+        if (stable)
+            gather_f32<true><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n,
+                                                             h->d_cell, h->d_cell_end, h->d_perm);
+        else
+            gather_f32<false><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n,
+                                                              h->d_cell, h->d_cell_end, h->d_perm);
+    } else {
+        if (stable)
+            gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, h->d_cell, h->d_cell_end, h->d_perm);
+        else
+            gather_f64<false><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, h->d_cell, h->d_cell_end, h->d_perm);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_type_histogram(plife_handle *h, unsigned long long *d_hist)
+{
+    int n = (int)h->n;
+    if (n == 0) return cudaSuccess;
+    int nb = blocks_for(n, kThreads);
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (h->precision == PLIFE_F32)
+        type_hist_f32<<<nb, kThreads, 0, h->stream>>>(h->s32[h->cur].pt, n, h->m, d_hist);
+    else
+        type_hist_f64<<<nb, kThreads, 0, h->stream>>>(h->s64[h->cur].type, n, h->m, d_hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init_uniform(plife_handle *h, int64_t n64, uint64_t seed)
+{
+    int n = (int)n64;
+    if (n == 0) return cudaSuccess;
+    if (h->precision == PLIFE_F32)
+        init_uniform_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, n, h->m, seed);
+    else
+        init_uniform_f64<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s64[h->cur], n, h->m, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32_t *type)
+{
+    int n = (int)h->n;
+    if (n == 0) return cudaSuccess;
+    if (h->precision == PLIFE_F32)
+        snapshot_from_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, n, pos, vel, type);
+    else
+        snapshot_from_f64<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s64[h->cur], n, pos, vel, type);
+    return cudaGetLastError();
+}
+
+} // namespace plife

@@ -1,0 +1,486 @@
+// Velocity + position pass of one step (Physics.updateVelocity / updatePosition,
+// B/Physics.java:397-450) as ONE kernel: thread i owns sorted particle i, walks
+// the 3x3 cells around floor(pos/rmax), accumulates the accelerator output,
+// applies friction, integrates and wraps/clamps, and writes the new state into
+// the other buffer (Jacobi: every force uses the old positions, which is what
+// the reference's barrier between its two passes guarantees, :122-131).
+//
+// Included by force_f32.cu (fused multiply-add on) and force_f64.cu
+// (compiled with -fmad=false so every operation rounds exactly like the
+// reference's non-fused JOML arithmetic).
+#pragma once
+
+#include "plife_internal.h"
+
+namespace plife {
+
+constexpr int kForceThreads = 128;
+
+template <typename R>
+struct Cand {
+    R x, y;
+    int type;
+    uint32_t id;
+};
+
+// ---- state access policies -------------------------------------------------
+struct IOF32 {
+    using R = float;
+    const float4 *__restrict__ pt;
+    const float2 *__restrict__ vel;
+    float4 *__restrict__ pt_out;
+    float2 *__restrict__ vel_out;
+    __device__ __forceinline__ Cand<float> cand(int j) const
+    {
+        float4 q = __ldg(pt + j);
+        return Cand<float>{q.x, q.y, __float_as_int(q.z), __float_as_uint(q.w)};
+    }
+    __device__ __forceinline__ void self_vel(int i, float &vx, float &vy) const
+    {
+        float2 v = __ldg(vel + i);
+        vx = v.x;
+        vy = v.y;
+    }
+    __device__ __forceinline__ void store(int i, float x, float y, float vx, float vy, int type, uint32_t id) const
+    {
+        pt_out[i] = make_float4(x, y, __int_as_float(type), __uint_as_float(id));
+        vel_out[i] = make_float2(vx, vy);
+    }
+};
+
+struct IOF64 {
+    using R = double;
+    StateF64 in, out;
+    __device__ __forceinline__ Cand<double> cand(int j) const
+    {
+        double2 p = __ldg(in.pos + j);
+        return Cand<double>{p.x, p.y, __ldg(in.type + j), __ldg(in.id + j)};
+    }
+    __device__ __forceinline__ void self_vel(int i, double &vx, double &vy) const
+    {
+        double2 v = __ldg(in.vel + i);
+        vx = v.x;
+        vy = v.y;
+    }
+    __device__ __forceinline__ void store(int i, double x, double y, double vx, double vy, int type, uint32_t id) const
+    {
+        out.pos[i] = make_double2(x, y);
+        out.vel[i] = make_double2(vx, vy);
+        out.type[i] = type;
+        out.id[i] = id;
+    }
+};
+
+// ---- small helpers -----------------------------------------------------------
+// B/Physics.java:377-395 wrapContainerX/Y: a single +-n, not a modulo
+__device__ __forceinline__ int wrap_container(int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); }
+
+__device__ __forceinline__ float rsqrt_fast(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// B/Range.java:46-57 (wrap): repeated +-1 until in [0,1).  Every intermediate
+// step of that loop is exact except the one crossing zero, so the loop equals a
+// single rounded `v - floor(v)`; like the loop it can return exactly 1.0 for a
+// tiny negative input.
+template <typename R>
+__device__ __forceinline__ R range_wrap(R v)
+{
+    if (v < R(0) || v >= R(1)) v = v - floor(v);
+    return v;
+}
+// B/Range.java:89-96 (clamp)
+template <typename R>
+__device__ __forceinline__ R range_clamp(R v)
+{
+    return v < R(0) ? R(0) : (v > R(1) ? R(1) : v);
+}
+
+// B/Range.java:74-81 wrapConnection on the raw difference b - a.
+// fp64: literal.  fp32: the same decision, but the +-1 is applied to the operand
+// that lies in [0.5, 1] first, where it is exact, so a seam pair
+// is as accurate as an interior pair.
+__device__ __forceinline__ double wrap_connection(double a, double b)
+{
+    double d = b - a;
+    if (d < -0.5) return d + 1;
+    else if (d >= 0.5) return d - 1;
+    return d;
+}
+__device__ __forceinline__ float wrap_connection(float a, float b)
+{
+    float d = b - a;
+    if (d < -0.5f) return b + (1.0f - a);
+    else if (d >= 0.5f) return (b - 1.0f) - a;
+    return d;
+}
+
+// in-range predicate of B/Physics.java:430-432: d2 != 0 && d2 <= rmax*rmax
+__device__ __forceinline__ bool in_range(double dx, double dy, double r2)
+{
+    double d2 = dx * dx + dy * dy;
+    return d2 != 0 && d2 <= r2;
+}
+constexpr float kTiny = 1e-36f; // keeps rsqrt finite for d2 == 0; far below any representable pair distance^2
+__device__ __forceinline__ bool in_range(float dx, float dy, float r2)
+{
+    float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
+    return (dx != 0.f || dy != 0.f) && d2 <= r2;
+}
+
+// ---- 3x3 traversal -------------------------------------------------------------
+// Calls v.pair(j, cand, dx, dy) for the candidates of particle i in the
+// reference's order (B/Physics.java:407-439).  Lanes whose 3x3 block needs no
+// cell wrap ("interior", needs nx >= 4 so that |x_j - x_i| < 2*rmax <= 0.5 and
+// wrapConnection is the identity) merge the three cells of a row into one
+// contiguous index range; the candidate j == i is NOT filtered there (its
+// d2 == 0 fails the in-range test).  All other lanes take the literal path.
+template <typename IO, typename V>
+__device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict__ cell_end, const Grid &g, int wrap,
+                                         int i, typename IO::R xi, typename IO::R yi, V &v)
+{
+    using R = typename IO::R;
+    const int cx0 = (int)floor((double)xi / g.cs); // :404, no ==nx clamp
+    const int cy0 = (int)floor((double)yi / g.cs); // :405
+    const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
+    if (interior) {
+#pragma unroll 1
+        for (int oy = -1; oy <= 1; ++oy) {
+            const int base = (cy0 + oy) * g.nx + cx0;
+            const int s = base >= 2 ? __ldg(cell_end + base - 2) : 0;
+            const int e = __ldg(cell_end + base + 1);
+#pragma unroll 4
+            for (int j = s; j < e; ++j) {
+                Cand<R> q = io.cand(j);
+                v.pair(j, q, q.x - xi, q.y - yi);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < 9; ++k) {
+            const int ox = k % 3 - 1, oy = k / 3 - 1; // order of :88-98
+            int cx = wrap_container(cx0 + ox, g.nx);  // :408
+            int cy = wrap_container(cy0 + oy, g.ny);  // :409
+            if (wrap) {
+                cx = wrap_container(cx, g.nx); // :411
+                cy = wrap_container(cy, g.ny); // :412
+            } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
+                continue; // :414-416
+            }
+            const int ci = cx + cy * g.nx;                        // :418
+            const int s = ci == 0 ? 0 : __ldg(cell_end + ci - 1); // :420
+            const int e = __ldg(cell_end + ci);                   // :421
+            for (int j = s; j < e; ++j) {
+                if (j == i) continue; // :424
+                Cand<R> q = io.cand(j);
+                R dx, dy;
+                if (wrap) { // :464-467
+                    dx = wrap_connection(xi, q.x);
+                    dy = wrap_connection(yi, q.y);
+                } else {
+                    dx = q.x - xi;
+                    dy = q.y - yi;
+                }
+                v.pair(j, q, dx, dy);
+            }
+        }
+    }
+}
+
+// ---- accelerators (B/Accelerator.java:16): (a, pos/rmax) -> acceleration ------
+// Literal forms, used for fp64 (bit-faithful to the reference's operation order)
+// and for the builder-defined kinds in both precisions.
+template <typename R, int KIND>
+__device__ __forceinline__ void accelerate(R a, R px, R py, const R *prm, R &ox, R &oy)
+{
+    R dist = sqrt(px * px + py * py); // JOML length(), z == 0
+    if (KIND == PLIFE_ACC_PARTICLE_LIFE || KIND == PLIFE_ACC_PARTICLE_LIFE_R || KIND == PLIFE_ACC_PARTICLE_LIFE_R2) {
+        const R beta = prm[0];
+        // A/Main.java:276-278
+        R force = dist < beta ? (dist / beta - R(1)) : a * (R(1) - fabs(R(1) + beta - R(2) * dist) / (R(1) - beta));
+        R k;
+        if (KIND == PLIFE_ACC_PARTICLE_LIFE) k = force / dist; // A/Main.java:279
+        else if (KIND == PLIFE_ACC_PARTICLE_LIFE_R) k = force / (dist * dist);
+        else k = force / (dist * dist * dist);
+        ox = px * k;
+        oy = py * k;
+    } else if (KIND == PLIFE_ACC_ROTATOR_90) {
+        R force = a * (R(1) - dist);
+        R k = force / dist;
+        ox = -py * k;
+        oy = px * k;
+    } else if (KIND == PLIFE_ACC_ROTATOR_ATTR) {
+        R force = R(1) - dist;
+        R angle = -a * R(3.14159265358979323846);
+        R c = cos(angle), sn = sin(angle);
+        R k = force / dist;
+        ox = (c * px + sn * py) * k;
+        oy = (-sn * px + c * py) * k;
+    } else { // PLIFE_ACC_PLANETS
+        R r = dist > R(0.01) ? dist : R(0.01);
+        R k = R(0.01) / (r * r * r);
+        ox = px * k;
+        oy = py * k;
+    }
+}
+
+// ---- visitors ---------------------------------------------------------------------
+template <typename R, bool SMEM>
+struct MatrixView { // transposed matrix Mt[other][own]
+    const R *g;     // global copy
+    const R *s;     // shared copy (valid when SMEM), already multiplied by `scale`
+    int m, own;
+    R scale;
+    uint32_t row; // shared-window byte address of Mt[0][own]
+    uint32_t mb;  // bytes per matrix row
+    __device__ __forceinline__ void init()
+    {
+        if (SMEM) {
+            row = (uint32_t)__cvta_generic_to_shared(s + own);
+            mb = (uint32_t)m * (uint32_t)sizeof(R);
+        }
+    }
+    __device__ __forceinline__ R get(int other) const
+    {
+        if (SMEM) return lds(row + (uint32_t)other * mb); // one IMAD + one LDS
+        return __ldg(g + other * m + own) * scale;
+    }
+    static __device__ __forceinline__ float lds_(uint32_t a, float)
+    {
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ double lds_(uint32_t a, double)
+    {
+        double v;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ R lds(uint32_t a) { return lds_(a, R(0)); }
+};
+
+// Literal visitor: accumulates term by term into the running velocity, exactly
+// like `p.velocity.add(deltaV.mul(rmax*force*dt))` (B/Physics.java:437).
+template <typename R, int KIND, bool SMEM>
+struct LiteralForce {
+    R vx, vy;
+    R r2, invr, k2;
+    const R *prm;
+    MatrixView<R, SMEM> M;
+    __device__ __forceinline__ void pair(int, const Cand<R> &q, R dx, R dy)
+    {
+        if (in_range(dx, dy, r2)) {
+            R px = dx * invr, py = dy * invr; // :434 (JOML div = mul by reciprocal)
+            R ox, oy;
+            accelerate<R, KIND>(M.get(q.type), px, py, prm, ox, oy); // :435
+            vx = vx + ox * k2;                                       // :437
+            vy = vy + oy * k2;
+        }
+    }
+    __device__ __forceinline__ void finish(R &ovx, R &ovy) const
+    {
+        ovx = vx;
+        ovy = vy;
+    }
+};
+
+// fp32 fast visitor for kind 0 (A/Main.java:275-280), branch-free, in absolute
+// distance units.  With b = beta*rmax, d0 = (1+beta)*rmax/2, h = (1-beta)*rmax/2
+// the reference force f(d/rmax) equals
+//     f = (1/b) * [ min(d - b, 0) + a' * max(h - |d - d0|, 0) ],  a' = a * 2*beta/(1-beta)
+// exactly: the first term is the repulsion (d < b), the second the triangular lobe
+// on [b, rmax], and both vanish beyond rmax, so the `d2 <= rmax^2` test
+// (B/Physics.java:432) is implied (f is continuous and 0 at the cutoff).  The
+// factor 1/b is folded into the final scale, a' into the shared-memory matrix.
+// Every constant is a direct constant-bank operand: no 3-register FFMA except
+// the three that must be (f and the two accumulators).
+template <bool SMEM>
+struct FastParticleLife32 {
+    float ax, ay;
+    float b, d0, h;
+    MatrixView<float, SMEM> M;
+    __device__ __forceinline__ void pair(int, const Cand<float> &q, float dx, float dy)
+    {
+        float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
+        float rinv = rsqrt_fast(d2);
+        float d = d2 * rinv;
+        float a = M.get(q.type);
+        float rep = fminf(d - b, 0.0f);
+        float att = fmaxf(h - fabsf(d - d0), 0.0f);
+        float g = fmaf(a, att, rep) * rinv; // self / coincident: dx = dy = 0 kills the term
+        ax = fmaf(g, dx, ax);
+        ay = fmaf(g, dy, ay);
+    }
+};
+
+struct NeighborDiag {
+    int count;
+    unsigned long long hash;
+    template <typename R>
+    __device__ __forceinline__ void add(const Cand<R> &q)
+    {
+        unsigned long long z = (unsigned long long)q.id + 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        hash += z ^ (z >> 31);
+        count++;
+    }
+};
+template <typename R>
+struct NeighborVisitor {
+    NeighborDiag d;
+    R r2;
+    __device__ __forceinline__ void pair(int, const Cand<R> &q, R dx, R dy)
+    {
+        if (in_range(dx, dy, r2)) d.add(q);
+    }
+};
+template <typename R>
+struct PairCountVisitor {
+    int self;
+    unsigned long long count;
+    __device__ __forceinline__ void pair(int j, const Cand<R> &, R, R) { count += (j != self) ? 1u : 0u; }
+};
+
+// ---- kernels ---------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void load_matrix_smem(R *sM, const R *__restrict__ gMt, int m, R scale)
+{
+    for (int k = threadIdx.x; k < m * m; k += blockDim.x) sM[k] = gMt[k] * scale;
+    __syncthreads();
+}
+
+template <typename IO, int KIND, bool SMEM, bool FAST>
+__global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32_t *__restrict__ cell_end,
+                                                             ForceParams<typename IO::R> P,
+                                                             const typename IO::R *__restrict__ gMt)
+{
+    using R = typename IO::R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *sM = reinterpret_cast<R *>(smem_raw);
+    const R mscale = FAST ? P.fast_a_scale : R(1);
+    if (SMEM) load_matrix_smem(sM, gMt, P.m, mscale);
+
+    const int i = blockIdx.x * kForceThreads + threadIdx.x;
+    if (i >= P.n) return;
+    const Cand<R> self = io.cand(i);
+    R vx, vy;
+    io.self_vel(i, vx, vy);
+    MatrixView<R, SMEM> M{gMt, sM, P.m, self.type, mscale, 0u, 0u};
+    M.init();
+
+    R nvx, nvy;
+    if constexpr (FAST) {
+        FastParticleLife32<SMEM> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+        nvx = fmaf(P.fast_k, v.ax, vx * P.mu); // friction first (:401-402), then the summed acceleration
+        nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
+    } else {
+        LiteralForce<R, KIND, SMEM> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
+        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+        v.finish(nvx, nvy);
+    }
+    // updatePosition (:443-450): pos = vel*dt + pos, then wrap or clamp (:499-505)
+    R nx_ = nvx * P.dt + self.x;
+    R ny_ = nvy * P.dt + self.y;
+    if (P.wrap) {
+        nx_ = range_wrap(nx_);
+        ny_ = range_wrap(ny_);
+    } else {
+        nx_ = range_clamp(nx_);
+        ny_ = range_clamp(ny_);
+    }
+    io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(kForceThreads) neighbors_kernel(IO io, const int32_t *__restrict__ cell_end,
+                                                                 ForceParams<typename IO::R> P, int32_t *__restrict__ cnt,
+                                                                 unsigned long long *__restrict__ hash)
+{
+    using R = typename IO::R;
+    const int i = blockIdx.x * kForceThreads + threadIdx.x;
+    if (i >= P.n) return;
+    const Cand<R> self = io.cand(i);
+    NeighborVisitor<R> v{{0, 0ull}, P.r2};
+    traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+    cnt[i] = v.d.count;
+    hash[i] = v.d.hash;
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(kForceThreads) pair_count_kernel(IO io, const int32_t *__restrict__ cell_end,
+                                                                  ForceParams<typename IO::R> P,
+                                                                  unsigned long long *__restrict__ total)
+{
+    using R = typename IO::R;
+    __shared__ unsigned long long sh[kForceThreads / 32];
+    const int i = blockIdx.x * kForceThreads + threadIdx.x;
+    unsigned long long c = 0;
+    if (i < P.n) {
+        const Cand<R> self = io.cand(i);
+        PairCountVisitor<R> v{i, 0ull};
+        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+        c = v.count;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int w = 0; w < kForceThreads / 32; w++) s += sh[w];
+        atomicAdd(total, s);
+    }
+}
+
+// dispatch over accelerator kind / matrix placement
+template <typename IO, bool FAST_OK>
+cudaError_t dispatch_force(const IO &io, const int32_t *cell_end, const ForceParams<typename IO::R> &P,
+                           const typename IO::R *gMt, int kind, cudaStream_t stream)
+{
+    using R = typename IO::R;
+    if (P.n == 0) return cudaSuccess;
+    const int nb = (P.n + kForceThreads - 1) / kForceThreads;
+    const bool smem = P.use_smem_matrix != 0;
+    const size_t sbytes = smem ? sizeof(R) * (size_t)P.m * P.m : 0;
+#define PLIFE_LAUNCH(KIND, SM, FAST)                                                                            \
+    do {                                                                                                        \
+        auto kfn = force_kernel<IO, KIND, SM, FAST>;                                                            \
+        if (sbytes > 48 * 1024) {                                                                               \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes); \
+            if (e != cudaSuccess) return e;                                                                     \
+        }                                                                                                       \
+        kfn<<<nb, kForceThreads, sbytes, stream>>>(io, cell_end, P, gMt);                                       \
+    } while (0)
+#define PLIFE_KIND(KIND)                       \
+    do {                                       \
+        if (smem) PLIFE_LAUNCH(KIND, true, false); \
+        else PLIFE_LAUNCH(KIND, false, false);     \
+    } while (0)
+    switch (kind) {
+    case PLIFE_ACC_PARTICLE_LIFE:
+        if (FAST_OK) {
+            if (smem) PLIFE_LAUNCH(PLIFE_ACC_PARTICLE_LIFE, true, FAST_OK);
+            else PLIFE_LAUNCH(PLIFE_ACC_PARTICLE_LIFE, false, FAST_OK);
+        } else {
+            PLIFE_KIND(PLIFE_ACC_PARTICLE_LIFE);
+        }
+        break;
+    case PLIFE_ACC_PARTICLE_LIFE_R: PLIFE_KIND(PLIFE_ACC_PARTICLE_LIFE_R); break;
+    case PLIFE_ACC_PARTICLE_LIFE_R2: PLIFE_KIND(PLIFE_ACC_PARTICLE_LIFE_R2); break;
+    case PLIFE_ACC_ROTATOR_90: PLIFE_KIND(PLIFE_ACC_ROTATOR_90); break;
+    case PLIFE_ACC_ROTATOR_ATTR: PLIFE_KIND(PLIFE_ACC_ROTATOR_ATTR); break;
+    case PLIFE_ACC_PLANETS: PLIFE_KIND(PLIFE_ACC_PLANETS); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef PLIFE_KIND
+#undef PLIFE_LAUNCH
+    return cudaGetLastError();
+}
+
+} // namespace plife

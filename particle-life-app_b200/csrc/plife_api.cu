@@ -1,0 +1,724 @@
+// C ABI of libplife.so (include/plife.h): handle management, settings, host<->device
+// transfer and the per-step kernel sequence.  There is no CPU compute path in
+// this library: every entry point that touches particles runs CUDA kernels and
+// fails with PLIFE_ERR_CUDA when no device is usable.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "plife_internal.h"
+
+using namespace plife;
+
+namespace {
+
+int fail(plife_handle *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->last_error = buf;
+    return code;
+}
+
+int cuda_fail(plife_handle *h, cudaError_t e, const char *what)
+{
+    // sticky errors (illegal address, launch failure, ...) poison the handle
+    if (e != cudaErrorMemoryAllocation && e != cudaErrorInvalidValue && e != cudaErrorNotReady) h->poisoned = true;
+    cudaGetLastError();
+    if (e == cudaErrorMemoryAllocation) return fail(h, PLIFE_ERR_OOM, "%s: %s", what, cudaGetErrorString(e));
+    return fail(h, PLIFE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(h, expr)                                      \
+    do {                                                 \
+        cudaError_t e_ = (expr);                         \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, #expr); \
+    } while (0)
+
+#define CHECK_HANDLE(h)                                                              \
+    do {                                                                             \
+        if (!(h)) return PLIFE_ERR_INVALID;                                          \
+        if ((h)->poisoned) return fail(h, PLIFE_ERR_CUDA, "handle poisoned by an earlier CUDA error"); \
+        cudaError_t e_ = cudaSetDevice((h)->device);                                 \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, "cudaSetDevice");              \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t count)
+{
+    return cudaMalloc((void **)p, sizeof(T) * (count ? count : 1));
+}
+
+void free_state(plife_handle *h)
+{
+    for (int b = 0; b < 2; b++) {
+        cudaFree(h->s32[b].pt);
+        cudaFree(h->s32[b].vel);
+        cudaFree(h->s64[b].pos);
+        cudaFree(h->s64[b].vel);
+        cudaFree(h->s64[b].type);
+        cudaFree(h->s64[b].id);
+        h->s32[b] = StateF32{};
+        h->s64[b] = StateF64{};
+    }
+    cudaFree(h->d_cell);
+    cudaFree(h->d_perm);
+    h->d_cell = h->d_perm = nullptr;
+    h->cap = 0;
+}
+
+// grow particle buffers; contents are NOT preserved
+int ensure_capacity(plife_handle *h, int64_t n)
+{
+    if (n <= h->cap) return PLIFE_OK;
+    if (n > 0x7fffffffLL - 1024) return fail(h, PLIFE_ERR_INVALID, "particle count %lld exceeds int32 indexing", (long long)n);
+    free_state(h);
+    size_t c = (size_t)n;
+    for (int b = 0; b < 2; b++) {
+        if (h->precision == PLIFE_F32) {
+            CU(h, dev_alloc(&h->s32[b].pt, c));
+            CU(h, dev_alloc(&h->s32[b].vel, c));
+        } else {
+            CU(h, dev_alloc(&h->s64[b].pos, c));
+            CU(h, dev_alloc(&h->s64[b].vel, c));
+            CU(h, dev_alloc(&h->s64[b].type, c));
+            CU(h, dev_alloc(&h->s64[b].id, c));
+        }
+    }
+    CU(h, dev_alloc(&h->d_cell, c));
+    CU(h, dev_alloc(&h->d_perm, c));
+    h->cap = n;
+    return PLIFE_OK;
+}
+
+constexpr int64_t kMaxCells = (int64_t)1 << 28;
+constexpr int kScanTile = 4096; // must match cells.cu
+
+int ensure_cells(plife_handle *h, int64_t ncell)
+{
+    if (ncell <= h->cell_cap) return PLIFE_OK;
+    cudaFree(h->d_count);
+    cudaFree(h->d_cell_end);
+    cudaFree(h->d_tile_sums);
+    h->d_count = h->d_cell_end = h->d_tile_sums = nullptr;
+    h->cell_cap = 0;
+    int64_t padded = (ncell + kScanTile - 1) / kScanTile * kScanTile;
+    CU(h, dev_alloc(&h->d_count, (size_t)padded));
+    CU(h, dev_alloc(&h->d_cell_end, (size_t)padded));
+    CU(h, dev_alloc(&h->d_tile_sums, (size_t)(padded / kScanTile)));
+    CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)padded, h->stream));
+    h->cell_cap = padded;
+    return PLIFE_OK;
+}
+
+// B/Physics.java:82-85 with containerSize = rmax (:312)
+int make_grid(plife_handle *h, Grid *g)
+{
+    double rmax = h->settings.rmax;
+    int nx = (int)floor(1 / rmax);
+    if (!(rmax > 0) || nx < 1) return fail(h, PLIFE_ERR_INVALID, "rmax=%g gives nx=%d", rmax, nx);
+    if ((int64_t)nx * nx > kMaxCells) return fail(h, PLIFE_ERR_INVALID, "rmax=%g gives %lld cells (max %lld)", rmax, (long long)nx * nx, (long long)kMaxCells);
+    g->nx = nx;
+    g->ny = nx;
+    g->cs = rmax;
+    return PLIFE_OK;
+}
+
+template <typename R>
+int upload_matrix_t(plife_handle *h)
+{
+    int m = h->m;
+    if (h->d_matrix_cap < m * m) {
+        cudaFree(h->d_matrix_t);
+        h->d_matrix_t = nullptr;
+        h->d_matrix_cap = 0;
+        CU(h, cudaMalloc(&h->d_matrix_t, sizeof(double) * (size_t)m * m));
+        h->d_matrix_cap = m * m;
+    }
+    std::vector<R> t((size_t)m * m);
+    for (int own = 0; own < m; own++)
+        for (int other = 0; other < m; other++) t[(size_t)other * m + own] = (R)h->matrix[(size_t)own * m + other];
+    // pageable source: the copy is staged before the call returns
+    CU(h, cudaMemcpyAsync(h->d_matrix_t, t.data(), sizeof(R) * t.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->matrix_dirty = false;
+    return PLIFE_OK;
+}
+
+int sync_matrix(plife_handle *h)
+{
+    if (!h->matrix_dirty) return PLIFE_OK;
+    return h->precision == PLIFE_F32 ? upload_matrix_t<float>(h) : upload_matrix_t<double>(h);
+}
+
+template <typename R>
+ForceParams<R> make_params(const plife_handle *h, const Grid &g, double dt)
+{
+    const plife_settings &s = h->settings;
+    ForceParams<R> p{};
+    p.n = (int)h->n;
+    p.m = h->m;
+    p.g = g;
+    p.wrap = s.wrap ? 1 : 0;
+    p.use_smem_matrix = h->m <= 64 ? 1 : 0;
+    p.rmax = (R)s.rmax;
+    p.r2 = (R)(s.rmax * s.rmax);              // B/Physics.java:432
+    p.invr = (R)(1.0 / s.rmax);               // JOML div, :434
+    p.mu = (R)pow(s.friction, 60 * dt);       // :401
+    p.k2 = (R)(s.rmax * s.force * dt);        // :437
+    p.dt = (R)dt;
+    for (int k = 0; k < 4; k++) p.accp[k] = (R)h->acc_params[k];
+    const double beta = h->acc_params[0];
+    p.fast_b = (R)(beta * s.rmax);
+    p.fast_d0 = (R)((1.0 + beta) * s.rmax * 0.5);
+    p.fast_h = (R)((1.0 - beta) * s.rmax * 0.5);
+    p.fast_a_scale = (R)(2.0 * beta / (1.0 - beta));
+    p.fast_k = (R)(s.force * dt / beta);
+    return p;
+}
+
+struct StepTimer {
+    plife_handle *h;
+    plife_handle::PendingTiming t{};
+    bool on;
+    explicit StepTimer(plife_handle *h_) : h(h_), on(h_->profiling) {}
+    cudaError_t mark(int k)
+    {
+        if (!on) return cudaSuccess;
+        cudaError_t e = cudaEventCreate(&t.ev[k]);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(t.ev[k], h->stream);
+    }
+};
+
+int resolve_timings(plife_handle *h)
+{
+    if (h->pending.empty()) return PLIFE_OK;
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto &p : h->pending) {
+        for (int k = 0; k < PLIFE_K_COUNT; k++) {
+            float ms = 0.f;
+            CU(h, cudaEventElapsedTime(&ms, p.ev[k], p.ev[k + 1]));
+            h->k_ms[k] += ms;
+        }
+        h->k_launches[PLIFE_K_BIN] += 1;
+        h->k_launches[PLIFE_K_SCAN] += 3;
+        h->k_launches[PLIFE_K_SCATTER] += 1;
+        h->k_launches[PLIFE_K_GATHER] += 1;
+        h->k_launches[PLIFE_K_FORCE] += 1;
+        for (int k = 0; k <= PLIFE_K_COUNT; k++) cudaEventDestroy(p.ev[k]);
+    }
+    h->pending.clear();
+    return PLIFE_OK;
+}
+
+// makeContainers (B/Physics.java:309-354): state buffer cur -> sorted into cur^1
+int sort_current(plife_handle *h, const Grid &g, StepTimer *tm)
+{
+    int rc = ensure_cells(h, (int64_t)g.nx * g.ny);
+    if (rc) return rc;
+    if (tm) CU(h, tm->mark(0));
+    CU(h, launch_bin(h, g));
+    if (tm) CU(h, tm->mark(1));
+    CU(h, launch_scan(h, g));
+    if (tm) CU(h, tm->mark(2));
+    CU(h, launch_scatter(h, g));
+    if (tm) CU(h, tm->mark(3));
+    CU(h, launch_gather(h, g));
+    if (tm) CU(h, tm->mark(4));
+    return PLIFE_OK;
+}
+
+int run_step(plife_handle *h, double dt)
+{
+    Grid g;
+    int rc = make_grid(h, &g);
+    if (rc) return rc;
+    rc = sync_matrix(h);
+    if (rc) return rc;
+    StepTimer tm(h);
+    rc = sort_current(h, g, &tm);
+    if (rc) return rc;
+    if (h->precision == PLIFE_F32) CU(h, launch_force_f32(h, make_params<float>(h, g, dt)));
+    else CU(h, launch_force_f64(h, make_params<double>(h, g, dt)));
+    if (tm.on) {
+        CU(h, tm.mark(PLIFE_K_COUNT));
+        h->pending.push_back(tm.t);
+        if (h->pending.size() >= 256) {
+            rc = resolve_timings(h);
+            if (rc) return rc;
+        }
+    }
+    h->last_grid = g;
+    h->has_sorted = true;
+    h->steps++;
+    return PLIFE_OK;
+}
+
+int valid_settings(plife_handle *h, const plife_settings *s)
+{
+    if (!s) return fail(h, PLIFE_ERR_INVALID, "settings is NULL");
+    if (!(s->rmax > 0) || s->rmax > 1) return fail(h, PLIFE_ERR_INVALID, "rmax=%g outside (0,1]", s->rmax);
+    if (!isfinite(s->friction) || !isfinite(s->force)) return fail(h, PLIFE_ERR_INVALID, "friction/force not finite");
+    int nx = (int)floor(1 / s->rmax);
+    if ((int64_t)nx * nx > kMaxCells) return fail(h, PLIFE_ERR_INVALID, "rmax=%g gives too many cells", s->rmax);
+    return PLIFE_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int plife_version(void) { return PLIFE_VERSION; }
+
+const char *plife_status_string(int status)
+{
+    switch (status) {
+    case PLIFE_OK: return "ok";
+    case PLIFE_ERR_INVALID: return "invalid argument";
+    case PLIFE_ERR_OOM: return "out of memory";
+    case PLIFE_ERR_CUDA: return "CUDA error";
+    case PLIFE_ERR_NCCL: return "NCCL error";
+    case PLIFE_ERR_STATE: return "invalid state";
+    case PLIFE_ERR_STOPPED: return "stopped";
+    default: return "unknown status";
+    }
+}
+
+int plife_create(const plife_config *cfg, plife_handle **out)
+{
+    if (!cfg || !out) return PLIFE_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->precision != PLIFE_F32 && cfg->precision != PLIFE_F64) return PLIFE_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return PLIFE_ERR_CUDA; // no CPU fallback
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return PLIFE_ERR_INVALID;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return PLIFE_ERR_CUDA;
+    plife_handle *h = new (std::nothrow) plife_handle();
+    if (!h) return PLIFE_ERR_OOM;
+    h->device = cfg->device;
+    h->precision = cfg->precision;
+    h->flags = cfg->flags;
+    if (cfg->stream) {
+        h->stream = (cudaStream_t)cfg->stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete h;
+            return PLIFE_ERR_CUDA;
+        }
+        h->own_stream = true;
+    }
+    if (cudaMalloc((void **)&h->d_scalar, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return PLIFE_ERR_OOM;
+    }
+    if (cfg->capacity > 0) {
+        int rc = ensure_capacity(h, cfg->capacity);
+        if (rc) {
+            plife_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return PLIFE_OK;
+}
+
+int plife_destroy(plife_handle *h)
+{
+    if (!h) return PLIFE_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &p : h->pending)
+        for (int k = 0; k <= PLIFE_K_COUNT; k++) cudaEventDestroy(p.ev[k]);
+    free_state(h);
+    cudaFree(h->d_count);
+    cudaFree(h->d_cell_end);
+    cudaFree(h->d_tile_sums);
+    cudaFree(h->d_matrix_t);
+    cudaFree(h->d_snap);
+    cudaFree(h->d_scalar);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return PLIFE_OK;
+}
+
+int plife_set_settings(plife_handle *h, const plife_settings *s)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    int rc = valid_settings(h, s);
+    if (rc) return rc;
+    h->settings = *s;
+    h->settings.wrap = s->wrap ? 1 : 0;
+    return PLIFE_OK;
+}
+
+int plife_get_settings(const plife_handle *h, plife_settings *out)
+{
+    if (!h || !out) return PLIFE_ERR_INVALID;
+    *out = h->settings;
+    return PLIFE_OK;
+}
+
+int plife_set_matrix(plife_handle *h, int32_t m, const double *row_major)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (m < 1 || m > 256 || !row_major) return fail(h, PLIFE_ERR_INVALID, "matrix size %d outside [1,256] or NULL data", m);
+    for (int k = 0; k < m * m; k++)
+        if (!isfinite(row_major[k])) return fail(h, PLIFE_ERR_INVALID, "matrix entry %d not finite", k);
+    if (h->n > 0 && h->max_type >= m)
+        return fail(h, PLIFE_ERR_STATE, "resident particles have type %d >= new matrix size %d (retype on the host first)", h->max_type, m);
+    h->m = m;
+    h->matrix.assign(row_major, row_major + (size_t)m * m);
+    h->matrix_dirty = true;
+    return PLIFE_OK;
+}
+
+int plife_set_matrix_entry(plife_handle *h, int32_t i, int32_t j, double v)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (i < 0 || j < 0 || i >= h->m || j >= h->m || !isfinite(v)) return fail(h, PLIFE_ERR_INVALID, "matrix entry (%d,%d) out of range for size %d", i, j, h->m);
+    h->matrix[(size_t)i * h->m + j] = v;
+    h->matrix_dirty = true;
+    return PLIFE_OK;
+}
+
+int plife_get_matrix(const plife_handle *h, int32_t *m_out, double *row_major_out, int32_t capacity_m)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (m_out) *m_out = h->m;
+    if (row_major_out) {
+        if (capacity_m < h->m) return PLIFE_ERR_INVALID;
+        memcpy(row_major_out, h->matrix.data(), sizeof(double) * (size_t)h->m * h->m);
+    }
+    return PLIFE_OK;
+}
+
+int plife_set_accelerator(plife_handle *h, int32_t kind, const double *params, int32_t nparams)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (kind < 0 || kind >= PLIFE_ACC_KIND_COUNT) return fail(h, PLIFE_ERR_INVALID, "unknown accelerator kind %d", kind);
+    if (nparams < 0 || nparams > 4 || (nparams > 0 && !params)) return fail(h, PLIFE_ERR_INVALID, "bad accelerator params");
+    double p[4] = {0.3, 0, 0, 0};
+    for (int k = 0; k < nparams; k++) p[k] = params[k];
+    if (kind <= PLIFE_ACC_PARTICLE_LIFE_R2 && !(p[0] > 0 && p[0] < 1)) return fail(h, PLIFE_ERR_INVALID, "beta=%g outside (0,1)", p[0]);
+    h->acc_kind = kind;
+    memcpy(h->acc_params, p, sizeof p);
+    return PLIFE_OK;
+}
+
+int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double *vel_xy, const int32_t *type, const uint32_t *id)
+{
+    CHECK_HANDLE(h);
+    if (n < 0 || (n > 0 && (!pos_xy || !type))) return fail(h, PLIFE_ERR_INVALID, "upload: n=%lld with NULL pos/type", (long long)n);
+    int max_type = -1;
+    for (int64_t i = 0; i < n; i++) {
+        double x = pos_xy[2 * i], y = pos_xy[2 * i + 1];
+        if (!(x >= 0 && x <= 1 && y >= 0 && y <= 1)) return fail(h, PLIFE_ERR_INVALID, "upload: particle %lld position (%g,%g) outside [0,1]^2", (long long)i, x, y);
+        int t = type[i];
+        if (t < 0 || t >= h->m) return fail(h, PLIFE_ERR_INVALID, "upload: particle %lld type %d outside [0,%d)", (long long)i, t, h->m);
+        if (t > max_type) max_type = t;
+    }
+    int rc = ensure_capacity(h, n);
+    if (rc) return rc;
+    h->cur = 0;
+    h->has_sorted = false;
+    const int64_t chunk = 1 << 20;
+    if (h->precision == PLIFE_F32) {
+        std::vector<float4> pt((size_t)(n < chunk ? n : chunk));
+        std::vector<float2> vl(pt.size());
+        for (int64_t s = 0; s < n; s += chunk) {
+            int64_t c = n - s < chunk ? n - s : chunk;
+            for (int64_t k = 0; k < c; k++) {
+                int64_t i = s + k;
+                uint32_t pid = id ? id[i] : (uint32_t)i;
+                float4 q;
+                q.x = (float)pos_xy[2 * i];
+                q.y = (float)pos_xy[2 * i + 1];
+                memcpy(&q.z, &type[i], 4);
+                memcpy(&q.w, &pid, 4);
+                pt[k] = q;
+                vl[k] = vel_xy ? make_float2((float)vel_xy[2 * i], (float)vel_xy[2 * i + 1]) : make_float2(0.f, 0.f);
+            }
+            CU(h, cudaMemcpyAsync(h->s32[0].pt + s, pt.data(), sizeof(float4) * c, cudaMemcpyHostToDevice, h->stream));
+            CU(h, cudaMemcpyAsync(h->s32[0].vel + s, vl.data(), sizeof(float2) * c, cudaMemcpyHostToDevice, h->stream));
+            CU(h, cudaStreamSynchronize(h->stream));
+        }
+    } else {
+        if (n > 0) {
+            CU(h, cudaMemcpyAsync(h->s64[0].pos, pos_xy, sizeof(double2) * n, cudaMemcpyHostToDevice, h->stream));
+            if (vel_xy) CU(h, cudaMemcpyAsync(h->s64[0].vel, vel_xy, sizeof(double2) * n, cudaMemcpyHostToDevice, h->stream));
+            else CU(h, cudaMemsetAsync(h->s64[0].vel, 0, sizeof(double2) * n, h->stream));
+            CU(h, cudaMemcpyAsync(h->s64[0].type, type, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+            if (id) {
+                CU(h, cudaMemcpyAsync(h->s64[0].id, id, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream));
+            } else {
+                std::vector<uint32_t> ids((size_t)n);
+                for (int64_t i = 0; i < n; i++) ids[i] = (uint32_t)i;
+                CU(h, cudaMemcpyAsync(h->s64[0].id, ids.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream));
+                CU(h, cudaStreamSynchronize(h->stream));
+            }
+            CU(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    h->n = n;
+    h->max_type = max_type;
+    return PLIFE_OK;
+}
+
+int plife_download(plife_handle *h, double *pos_xy, double *vel_xy, int32_t *type, uint32_t *id)
+{
+    CHECK_HANDLE(h);
+    int64_t n = h->n;
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (n == 0) return PLIFE_OK;
+    if (h->precision == PLIFE_F32) {
+        const int64_t chunk = 1 << 20;
+        std::vector<float4> pt((size_t)(n < chunk ? n : chunk));
+        std::vector<float2> vl(pt.size());
+        for (int64_t s = 0; s < n; s += chunk) {
+            int64_t c = n - s < chunk ? n - s : chunk;
+            CU(h, cudaMemcpy(pt.data(), h->s32[h->cur].pt + s, sizeof(float4) * c, cudaMemcpyDeviceToHost));
+            if (vel_xy) CU(h, cudaMemcpy(vl.data(), h->s32[h->cur].vel + s, sizeof(float2) * c, cudaMemcpyDeviceToHost));
+            for (int64_t k = 0; k < c; k++) {
+                int64_t i = s + k;
+                if (pos_xy) {
+                    pos_xy[2 * i] = pt[k].x;
+                    pos_xy[2 * i + 1] = pt[k].y;
+                }
+                if (vel_xy) {
+                    vel_xy[2 * i] = vl[k].x;
+                    vel_xy[2 * i + 1] = vl[k].y;
+                }
+                if (type) memcpy(&type[i], &pt[k].z, 4);
+                if (id) memcpy(&id[i], &pt[k].w, 4);
+            }
+        }
+    } else {
+        const StateF64 &s = h->s64[h->cur];
+        if (pos_xy) CU(h, cudaMemcpy(pos_xy, s.pos, sizeof(double2) * n, cudaMemcpyDeviceToHost));
+        if (vel_xy) CU(h, cudaMemcpy(vel_xy, s.vel, sizeof(double2) * n, cudaMemcpyDeviceToHost));
+        if (type) CU(h, cudaMemcpy(type, s.type, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        if (id) CU(h, cudaMemcpy(id, s.id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    }
+    return PLIFE_OK;
+}
+
+int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type)
+{
+    CHECK_HANDLE(h);
+    int64_t n = h->n;
+    if (n == 0) return PLIFE_OK;
+    if (h->snap_cap < n) {
+        cudaFree(h->d_snap);
+        h->d_snap = nullptr;
+        h->snap_cap = 0;
+        CU(h, cudaMalloc(&h->d_snap, (size_t)n * 20));
+        h->snap_cap = n;
+    }
+    float2 *dp = (float2 *)h->d_snap;
+    float2 *dv = dp + n;
+    int32_t *dt = (int32_t *)(dv + n);
+    CU(h, launch_snapshot_f32(h, pos_xy ? dp : nullptr, vel_xy ? dv : nullptr, type ? dt : nullptr));
+    if (pos_xy) CU(h, cudaMemcpyAsync(pos_xy, dp, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (vel_xy) CU(h, cudaMemcpyAsync(vel_xy, dv, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (type) CU(h, cudaMemcpyAsync(type, dt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PLIFE_OK;
+}
+
+int plife_init_uniform(plife_handle *h, int64_t n, uint64_t seed)
+{
+    CHECK_HANDLE(h);
+    if (n < 0) return fail(h, PLIFE_ERR_INVALID, "n < 0");
+    int rc = ensure_capacity(h, n);
+    if (rc) return rc;
+    h->cur = 0;
+    h->has_sorted = false;
+    h->n = n;
+    CU(h, launch_init_uniform(h, n, seed));
+    h->max_type = n > 0 ? h->m - 1 : -1;
+    return PLIFE_OK;
+}
+
+int plife_random_matrix(plife_handle *h, int32_t m, uint64_t seed)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (m < 1 || m > 256) return fail(h, PLIFE_ERR_INVALID, "matrix size %d outside [1,256]", m);
+    std::vector<double> v((size_t)m * m);
+    const uint64_t s = seed ^ 0x4D41545249583634ull;
+    for (int k = 0; k < m * m; k++) {
+        uint64_t z = s + ((uint64_t)k + 1ull) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        v[k] = 2.0 * ((double)(z >> 11) * (1.0 / 9007199254740992.0)) - 1.0; // B/DefaultMatrix.java:28
+    }
+    return plife_set_matrix(h, m, v.data());
+}
+
+int plife_step(plife_handle *h, double dt, int32_t nsteps)
+{
+    CHECK_HANDLE(h);
+    if (!isfinite(dt) || nsteps < 0) return fail(h, PLIFE_ERR_INVALID, "step: dt=%g nsteps=%d", dt, nsteps);
+    for (int s = 0; s < nsteps; s++) {
+        if (h->stop_requested.exchange(0)) return fail(h, PLIFE_ERR_STOPPED, "stopped after %d of %d steps", s, nsteps);
+        int rc = run_step(h, dt);
+        if (rc) return rc;
+    }
+    return PLIFE_OK;
+}
+
+int plife_sync(plife_handle *h)
+{
+    CHECK_HANDLE(h);
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PLIFE_OK;
+}
+
+int64_t plife_count(const plife_handle *h) { return h ? h->n : PLIFE_ERR_INVALID; }
+
+int plife_type_histogram(plife_handle *h, int64_t *out_m)
+{
+    CHECK_HANDLE(h);
+    if (!out_m) return fail(h, PLIFE_ERR_INVALID, "out is NULL");
+    unsigned long long *d_hist = nullptr;
+    CU(h, cudaMalloc((void **)&d_hist, sizeof(unsigned long long) * 256));
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256, h->stream);
+    if (e == cudaSuccess) e = launch_type_histogram(h, d_hist);
+    unsigned long long host[256];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_hist, sizeof host, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_hist);
+    if (e != cudaSuccess) return cuda_fail(h, e, "type histogram");
+    for (int k = 0; k < h->m; k++) out_m[k] = (int64_t)host[k];
+    return PLIFE_OK;
+}
+
+int plife_request_stop(plife_handle *h)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    h->stop_requested.store(1);
+    return PLIFE_OK;
+}
+
+const char *plife_last_error(const plife_handle *h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int plife_get_containers(plife_handle *h, int32_t *out, int64_t capacity)
+{
+    CHECK_HANDLE(h);
+    if (!h->has_sorted) return fail(h, PLIFE_ERR_STATE, "no step has run since the last upload");
+    int64_t ncell = (int64_t)h->last_grid.nx * h->last_grid.ny;
+    if (!out || capacity < ncell) return fail(h, PLIFE_ERR_INVALID, "containers: capacity %lld < %lld", (long long)capacity, (long long)ncell);
+    CU(h, cudaMemcpyAsync(out, h->d_cell_end, sizeof(int32_t) * ncell, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PLIFE_OK;
+}
+
+int plife_get_step_stats(plife_handle *h, plife_step_stats *out)
+{
+    CHECK_HANDLE(h);
+    if (!out) return fail(h, PLIFE_ERR_INVALID, "out is NULL");
+    if (!h->has_sorted) return fail(h, PLIFE_ERR_STATE, "no step has run since the last upload");
+    // buffer cur^1 still holds the sorted pre-step state of the last step
+    const Grid g = h->last_grid;
+    CU(h, cudaMemsetAsync(h->d_scalar, 0, sizeof(unsigned long long), h->stream));
+    if (h->precision == PLIFE_F32) CU(h, launch_pair_count_f32(h, make_params<float>(h, g, 0.0), h->d_scalar));
+    else CU(h, launch_pair_count_f64(h, make_params<double>(h, g, 0.0), h->d_scalar));
+    unsigned long long total = 0;
+    CU(h, cudaMemcpyAsync(&total, h->d_scalar, sizeof total, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    out->n = h->n;
+    out->nx = g.nx;
+    out->ny = g.ny;
+    out->pair_evals = (int64_t)total;
+    out->steps = h->steps;
+    return PLIFE_OK;
+}
+
+int plife_debug_neighbors(plife_handle *h, int32_t *count, uint64_t *hash)
+{
+    CHECK_HANDLE(h);
+    if (!count || !hash) return fail(h, PLIFE_ERR_INVALID, "NULL output");
+    int64_t n = h->n;
+    if (n == 0) return PLIFE_OK;
+    Grid g;
+    int rc = make_grid(h, &g);
+    if (rc) return rc;
+    rc = sort_current(h, g, nullptr); // cur -> cur^1 (sorted)
+    if (rc) return rc;
+    int32_t *d_cnt = nullptr;
+    unsigned long long *d_hash = nullptr;
+    CU(h, dev_alloc(&d_cnt, (size_t)n));
+    cudaError_t e = dev_alloc(&d_hash, (size_t)n);
+    if (e == cudaSuccess)
+        e = h->precision == PLIFE_F32 ? launch_neighbors_f32(h, make_params<float>(h, g, 0.0), d_cnt, d_hash)
+                                      : launch_neighbors_f64(h, make_params<double>(h, g, 0.0), d_cnt, d_hash);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(count, d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hash, d_hash, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_cnt);
+    cudaFree(d_hash);
+    if (e != cudaSuccess) return cuda_fail(h, e, "debug neighbors");
+    // like makeContainers, the sort is visible: the sorted copy becomes the current state
+    h->cur ^= 1;
+    h->has_sorted = false;
+    h->last_grid = g;
+    return PLIFE_OK;
+}
+
+int plife_set_profiling(plife_handle *h, int32_t enabled)
+{
+    CHECK_HANDLE(h);
+    int rc = resolve_timings(h);
+    if (rc) return rc;
+    h->profiling = enabled != 0;
+    if (enabled) {
+        for (int k = 0; k < PLIFE_K_COUNT; k++) {
+            h->k_ms[k] = 0;
+            h->k_launches[k] = 0;
+        }
+    }
+    return PLIFE_OK;
+}
+
+int plife_kernel_times(plife_handle *h, double *ms_out, int64_t *launches_out)
+{
+    CHECK_HANDLE(h);
+    int rc = resolve_timings(h);
+    if (rc) return rc;
+    for (int k = 0; k < PLIFE_K_COUNT; k++) {
+        if (ms_out) ms_out[k] = h->k_ms[k];
+        if (launches_out) launches_out[k] = h->k_launches[k];
+    }
+    return PLIFE_OK;
+}
+
+int plife_device_ptrs(plife_handle *h, void **pos, void **vel, void **type, void **id)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (h->precision == PLIFE_F32) {
+        if (pos) *pos = h->s32[h->cur].pt;
+        if (vel) *vel = h->s32[h->cur].vel;
+        if (type) *type = nullptr;
+        if (id) *id = nullptr;
+    } else {
+        if (pos) *pos = h->s64[h->cur].pos;
+        if (vel) *vel = h->s64[h->cur].vel;
+        if (type) *type = h->s64[h->cur].type;
+        if (id) *id = h->s64[h->cur].id;
+    }
+    return PLIFE_OK;
+}
+
+} // extern "C"

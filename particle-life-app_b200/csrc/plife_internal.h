@@ -1,0 +1,135 @@
+// Internal declarations shared by the translation units of libplife.so.
+// Not part of the ABI (see include/plife.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/plife.h"
+
+namespace plife {
+
+// Uniform grid of the reference: cell edge = rmax, nx = ny = floor(1/rmax)
+// (B/Physics.java:82-85, :312-313).  cs stays double: cell assignment is done
+// with IEEE double division in every precision mode.
+struct Grid {
+    int nx, ny;
+    double cs;
+};
+
+// Kernel parameters of the force/integrate pass for one step, in the
+// arithmetic type R of the handle.
+template <typename R>
+struct ForceParams {
+    int n, m;
+    Grid g;
+    int wrap;
+    int use_smem_matrix;
+    R rmax, r2, invr; // rmax, rmax*rmax, 1/rmax
+    R mu;             // pow(friction, 60*dt), B/Physics.java:401
+    R k2;             // (rmax*force)*dt,      B/Physics.java:437
+    R dt;
+    R accp[4];        // accelerator parameters
+    // kind-0 constants in absolute distance units (fp32 fast path, force_impl.cuh)
+    R fast_b, fast_d0, fast_h; // beta*rmax, (1+beta)*rmax/2, (1-beta)*rmax/2
+    R fast_a_scale;            // 2*beta/(1-beta), folded into the matrix
+    R fast_k;                  // k2/(beta*rmax) = force*dt/beta
+};
+
+// Device state of one precision.  F32 packs {x, y, type bits, id bits} into one
+// float4 so that a neighbour candidate is a single 16-byte load.
+struct StateF32 {
+    float4 *pt;
+    float2 *vel;
+};
+struct StateF64 {
+    double2 *pos;
+    double2 *vel;
+    int32_t *type;
+    uint32_t *id;
+};
+
+struct Timer {
+    cudaEvent_t ev[PLIFE_K_COUNT + 1];
+};
+
+} // namespace plife
+
+struct plife_handle {
+    int device = 0;
+    int precision = PLIFE_F32;
+    int flags = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool poisoned = false;
+
+    plife_settings settings{0.02, 0.85, 1.0, 1, 0};
+    int acc_kind = PLIFE_ACC_PARTICLE_LIFE;
+    double acc_params[4] = {0.3, 0, 0, 0};
+
+    int m = 1;
+    std::vector<double> matrix{0.0}; // row-major [own][other]
+    void *d_matrix_t = nullptr;      // transposed [other][own], in R
+    int d_matrix_cap = 0;            // entries
+    bool matrix_dirty = true;
+
+    int64_t n = 0;
+    int64_t cap = 0;
+    int max_type = -1;
+    int cur = 0; // index of the buffer holding the current state
+    plife::StateF32 s32[2]{};
+    plife::StateF64 s64[2]{};
+    int32_t *d_cell = nullptr; // cell of particle i (pre-sort order)
+    int32_t *d_perm = nullptr; // source index of sorted slot d
+    void *d_snap = nullptr;    // snapshot staging (download_f32)
+    int64_t snap_cap = 0;
+
+    int32_t *d_count = nullptr;   // per-cell histogram, zero between steps
+    int32_t *d_cell_end = nullptr; // `containers`: END offset per cell
+    int32_t *d_tile_sums = nullptr;
+    int64_t cell_cap = 0;
+    int64_t tile_cap = 0;
+    unsigned long long *d_scalar = nullptr; // small device scratch (counters)
+
+    plife::Grid last_grid{0, 0, 0.0};
+    bool has_sorted = false; // buffer cur^1 holds the sorted pre-step state of the last step
+    int64_t steps = 0;
+
+    bool profiling = false;
+    cudaEvent_t ev[PLIFE_K_COUNT + 1]{};
+    bool ev_created = false;
+    double k_ms[PLIFE_K_COUNT]{};
+    int64_t k_launches[PLIFE_K_COUNT]{};
+    struct PendingTiming {
+        cudaEvent_t ev[PLIFE_K_COUNT + 1];
+    };
+    std::vector<PendingTiming> pending;
+
+    std::atomic<int> stop_requested{0};
+    std::string last_error;
+};
+
+namespace plife {
+
+// cells.cu
+cudaError_t launch_bin(plife_handle *h, const Grid &g);
+cudaError_t launch_scan(plife_handle *h, const Grid &g);
+cudaError_t launch_scatter(plife_handle *h, const Grid &g);
+cudaError_t launch_gather(plife_handle *h, const Grid &g);
+cudaError_t launch_type_histogram(plife_handle *h, unsigned long long *d_hist);
+cudaError_t launch_init_uniform(plife_handle *h, int64_t n, uint64_t seed);
+cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32_t *type);
+
+// force_f32.cu / force_f64.cu
+cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p);
+cudaError_t launch_force_f64(plife_handle *h, const ForceParams<double> &p);
+cudaError_t launch_neighbors_f32(plife_handle *h, const ForceParams<float> &p, int32_t *cnt, unsigned long long *hash);
+cudaError_t launch_neighbors_f64(plife_handle *h, const ForceParams<double> &p, int32_t *cnt, unsigned long long *hash);
+cudaError_t launch_pair_count_f32(plife_handle *h, const ForceParams<float> &p, unsigned long long *d_total);
+cudaError_t launch_pair_count_f64(plife_handle *h, const ForceParams<double> &p, unsigned long long *d_total);
+
+} // namespace plife

@@ -1,0 +1,374 @@
+"""Host-side mirror of the reference's `Physics` object over the C ABI.
+
+`Physics` keeps the reference's surface (B/Physics.java): an accelerator, the
+position/type/matrix setter plugins, `settings` (wrap, rmax, friction, force,
+dt, matrix) and `update()`; the particle buffers live on the GPU and come back
+only through `particles` / `snapshot()` (display-time handoff,
+A/PhysicsSnapshot.java:24-62).  All compute is in libplife.so (CUDA, sm_100a);
+this module never computes a physics step itself and has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+from . import _native as N
+from . import synth
+from ._native import (ACC_PARTICLE_LIFE, ACC_PARTICLE_LIFE_R, ACC_PARTICLE_LIFE_R2, ACC_PLANETS,
+                      ACC_ROTATOR_90, ACC_ROTATOR_ATTR, F32, F64, FLAG_UNSTABLE_SORT, KERNEL_NAMES,
+                      PlifeError)
+
+__all__ = ["Physics", "PhysicsSettings", "NativePhysics", "Particles", "PlifeError",
+           "DefaultPositionSetter", "DefaultTypeSetter", "DefaultMatrixGenerator", "synth"]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Particles(NamedTuple):
+    position: np.ndarray  # [n, 2] float64
+    velocity: np.ndarray  # [n, 2] float64
+    type: np.ndarray      # [n] int32
+    id: np.ndarray        # [n] uint32
+
+
+class NativePhysics:
+    """Thin object wrapper over the plife_* entry points (one handle)."""
+
+    def __init__(self, device: int = 0, precision: int = F32, capacity: int = 0, flags: int = 0,
+                 stream: Optional[int] = None):
+        self.L = N.lib()
+        cfg = N.Config(device=device, precision=precision, capacity=capacity, flags=flags, reserved=0,
+                       stream=stream)
+        h = C.c_void_p()
+        rc = self.L.plife_create(C.byref(cfg), C.byref(h))
+        if rc != N.OK:
+            raise PlifeError(rc, "plife_create: " + self.L.plife_status_string(rc).decode()
+                             + " (a CUDA device is required; there is no CPU fallback)")
+        self.h = h
+        self.precision = precision
+
+    # -- plumbing --
+    def _check(self, rc):
+        if rc != N.OK:
+            raise PlifeError(rc, (self.L.plife_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.plife_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- settings --
+    def set_settings(self, rmax, friction, force, wrap):
+        s = N.Settings(rmax=rmax, friction=friction, force=force, wrap=1 if wrap else 0, reserved=0)
+        self._check(self.L.plife_set_settings(self.h, C.byref(s)))
+
+    def get_settings(self):
+        s = N.Settings()
+        self._check(self.L.plife_get_settings(self.h, C.byref(s)))
+        return dict(rmax=s.rmax, friction=s.friction, force=s.force, wrap=bool(s.wrap))
+
+    def set_matrix(self, matrix):
+        m = np.ascontiguousarray(matrix, dtype=np.float64)
+        if m.ndim != 2 or m.shape[0] != m.shape[1]:
+            raise ValueError("matrix must be square")
+        self._check(self.L.plife_set_matrix(self.h, m.shape[0], _ptr(m)))
+
+    def set_matrix_entry(self, i, j, v):
+        self._check(self.L.plife_set_matrix_entry(self.h, i, j, v))
+
+    def get_matrix(self):
+        m = C.c_int32()
+        self._check(self.L.plife_get_matrix(self.h, C.byref(m), None, 0))
+        out = np.empty((m.value, m.value), np.float64)
+        self._check(self.L.plife_get_matrix(self.h, C.byref(m), _ptr(out), m.value))
+        return out
+
+    def random_matrix(self, m, seed):
+        self._check(self.L.plife_random_matrix(self.h, m, seed))
+
+    def set_accelerator(self, kind, params=()):
+        p = np.asarray(params, np.float64)
+        self._check(self.L.plife_set_accelerator(self.h, kind, _ptr(p) if p.size else None, p.size))
+
+    # -- particles --
+    def upload(self, pos, vel, types, ids=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        n = pos.shape[0]
+        vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64).reshape(n, 2)
+        types = np.ascontiguousarray(types, dtype=np.int32).reshape(n)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32).reshape(n)
+        self._check(self.L.plife_upload(self.h, n, _ptr(pos), _ptr(vel), _ptr(types), _ptr(ids)))
+
+    def download(self) -> Particles:
+        n = self.count
+        pos = np.empty((n, 2), np.float64)
+        vel = np.empty((n, 2), np.float64)
+        types = np.empty(n, np.int32)
+        ids = np.empty(n, np.uint32)
+        self._check(self.L.plife_download(self.h, _ptr(pos), _ptr(vel), _ptr(types), _ptr(ids)))
+        return Particles(pos, vel, types, ids)
+
+    def download_f32(self, pos=None, vel=None, types=None):
+        """Float snapshot into caller buffers (numpy arrays or raw addresses)."""
+        def addr(x):
+            if x is None or isinstance(x, int):
+                return x
+            return x.ctypes.data
+        self._check(self.L.plife_download_f32(self.h, addr(pos), addr(vel), addr(types)))
+
+    def init_uniform(self, n, seed):
+        self._check(self.L.plife_init_uniform(self.h, n, seed))
+
+    @property
+    def count(self) -> int:
+        return int(self.L.plife_count(self.h))
+
+    def type_histogram(self):
+        m = self.get_matrix().shape[0]
+        out = np.zeros(m, np.int64)
+        self._check(self.L.plife_type_histogram(self.h, _ptr(out)))
+        return out
+
+    # -- stepping --
+    def step(self, dt, nsteps=1):
+        self._check(self.L.plife_step(self.h, dt, nsteps))
+
+    def sync(self):
+        self._check(self.L.plife_sync(self.h))
+
+    def request_stop(self):
+        self.L.plife_request_stop(self.h)
+
+    # -- instrumentation --
+    def containers(self):
+        st = self.step_stats(pairs=False)
+        out = np.empty(st["nx"] * st["ny"], np.int32)
+        self._check(self.L.plife_get_containers(self.h, _ptr(out), out.size))
+        return out
+
+    def step_stats(self, pairs=True):
+        s = N.StepStats()
+        self._check(self.L.plife_get_step_stats(self.h, C.byref(s)))
+        return dict(n=s.n, nx=s.nx, ny=s.ny, pair_evals=s.pair_evals, steps=s.steps)
+
+    def debug_neighbors(self):
+        n = self.count
+        cnt = np.empty(n, np.int32)
+        hsh = np.empty(n, np.uint64)
+        self._check(self.L.plife_debug_neighbors(self.h, _ptr(cnt), _ptr(hsh)))
+        return cnt, hsh
+
+    def set_profiling(self, on):
+        self._check(self.L.plife_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        ms = np.zeros(N.K_COUNT, np.float64)
+        ln = np.zeros(N.K_COUNT, np.int64)
+        self._check(self.L.plife_kernel_times(self.h, _ptr(ms), _ptr(ln)))
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(KERNEL_NAMES)}
+
+
+# ---------------------------------------------------------------------------
+# Setter plugins (host side, vectorised).  Interfaces mirror
+# B/PositionSetter.java:5-7, B/TypeSetter.java:5-15, B/MatrixGenerator.java:3-11.
+# ---------------------------------------------------------------------------
+
+class DefaultPositionSetter:
+    """B/DefaultPositionSetter.java:8-14: x, y ~ U[0,1)."""
+
+    def set(self, types: np.ndarray, n_types: int, rng: np.random.Generator) -> np.ndarray:
+        return rng.random((types.shape[0], 2))
+
+
+class DefaultTypeSetter:
+    """B/DefaultTypeSetter.java:8-10: floor(random * nTypes)."""
+
+    def get_type(self, position, velocity, types, n_types: int, rng: np.random.Generator) -> np.ndarray:
+        return np.floor(rng.random(types.shape[0]) * n_types).astype(np.int32)
+
+
+class DefaultMatrixGenerator:
+    """B/DefaultMatrixGenerator.java:6-10 -> DefaultMatrix.randomize(): 2*random - 1."""
+
+    def make_matrix(self, size: int, rng: np.random.Generator) -> np.ndarray:
+        return 2.0 * rng.random((size, size)) - 1.0
+
+
+@dataclass
+class PhysicsSettings:
+    """B/PhysicsSettings.java:8-38"""
+    wrap: bool = True
+    rmax: float = 0.02
+    friction: float = 0.85
+    force: float = 1.0
+    dt: float = 0.02
+    matrix: np.ndarray = field(default_factory=lambda: np.zeros((6, 6)))
+
+    def deep_copy(self) -> "PhysicsSettings":
+        return PhysicsSettings(self.wrap, self.rmax, self.friction, self.force, self.dt, self.matrix.copy())
+
+
+class Physics:
+    """Drop-in for the reference's `Physics` (B/Physics.java) on one B200.
+
+    Differences forced by the device boundary: the accelerator is a kind id
+    (a Java/Python lambda cannot run on the GPU), and `particles` is a snapshot
+    download rather than a live array; mutate with `set_particles`.
+    """
+
+    def __init__(self, accelerator: int = ACC_PARTICLE_LIFE, position_setter=None, matrix_generator=None,
+                 type_setter=None, *, particle_count: int = 10000, precision: int = F32, device: int = 0,
+                 seed: Optional[int] = None, accelerator_params=(), flags: int = 0, stream=None):
+        self.settings = PhysicsSettings()
+        self.accelerator = accelerator
+        self.accelerator_params = tuple(accelerator_params)
+        self.position_setter = position_setter or DefaultPositionSetter()
+        self.matrix_generator = matrix_generator or DefaultMatrixGenerator()
+        self.type_setter = type_setter or DefaultTypeSetter()
+        self.rng = np.random.default_rng(seed)
+        self.native = NativePhysics(device=device, precision=precision, flags=flags, stream=stream)
+        self._pushed = None
+        self.generate_matrix()                     # B/Physics.java:78
+        self.set_particle_count(particle_count)    # :79
+
+    # -- step --
+    def _push_settings(self):
+        s = self.settings
+        m = np.asarray(s.matrix, np.float64)
+        key = (s.wrap, s.rmax, s.friction, s.force, m.tobytes(), m.shape, self.accelerator, self.accelerator_params)
+        if key != self._pushed:
+            self.native.set_settings(s.rmax, s.friction, s.force, s.wrap)
+            self.native.set_matrix(m)
+            self.native.set_accelerator(self.accelerator, self.accelerator_params)
+            self._pushed = key
+
+    def update(self):
+        """B/Physics.java:112: one simulation step with the current settings."""
+        self._push_settings()
+        self.native.step(self.settings.dt, 1)
+
+    def force_update_stop(self):  # :149-151
+        self.native.request_stop()
+
+    def kill(self):  # :156-158
+        self.native.close()
+
+    # -- particles --
+    @property
+    def particles(self) -> Particles:
+        return self.native.download()
+
+    def snapshot(self) -> Particles:
+        return self.native.download()
+
+    def set_particles(self, position, velocity, types, ids=None):
+        self._push_settings()
+        self.native.upload(position, velocity, types, ids)
+
+    @property
+    def particle_count(self) -> int:
+        return self.native.count
+
+    def _generate(self, n):
+        """generateParticle (:290-295): type first, then position; velocity zero (:300-302)."""
+        n_types = self.settings.matrix.shape[0]
+        zeros = np.zeros((n, 2))
+        types = self.type_setter.get_type(zeros, zeros, np.zeros(n, np.int32), n_types, self.rng).astype(np.int32)
+        pos = self.ensure_position(self.position_setter.set(types, n_types, self.rng))
+        return pos, zeros.copy(), types
+
+    def set_particle_count(self, n: int):
+        """B/Physics.java:190-223."""
+        cur = self.native.count
+        if n == cur and cur > 0:
+            return
+        if cur == 0:
+            pos, vel, types = self._generate(n)
+            self.set_particles(pos, vel, types)
+            return
+        p = self.native.download()
+        if n < cur:  # shuffle first, then keep the first n (:201-210)
+            keep = self.rng.permutation(cur)[:n]
+            self.set_particles(p.position[keep], p.velocity[keep], p.type[keep], p.id[keep])
+        else:
+            pos, vel, types = self._generate(n - cur)
+            ids = np.concatenate([p.id, np.arange(cur, n, dtype=np.uint32)])
+            self.set_particles(np.concatenate([p.position, pos]), np.concatenate([p.velocity, vel]),
+                               np.concatenate([p.type, types]), ids)
+
+    def set_positions(self):
+        """B/Physics.java:166-168."""
+        p = self.native.download()
+        pos = self.ensure_position(self.position_setter.set(p.type, self.settings.matrix.shape[0], self.rng))
+        self.set_particles(pos, np.zeros_like(p.velocity), p.type, p.id)
+
+    def set_types(self):
+        """B/Physics.java:509-511."""
+        p = self.native.download()
+        t = self.type_setter.get_type(p.position, p.velocity, p.type, self.settings.matrix.shape[0], self.rng)
+        self.set_particles(p.position, p.velocity, t.astype(np.int32), p.id)
+
+    def ensure_types(self):
+        """B/Physics.java:266-272."""
+        p = self.native.download()
+        m = self.settings.matrix.shape[0]
+        bad = p.type >= m
+        if bad.any():
+            t = p.type.copy()
+            t[bad] = self.type_setter.get_type(p.position[bad], p.velocity[bad], p.type[bad], m, self.rng)
+            # upload against the OLD (larger) matrix is still valid; push the new matrix afterwards
+            self.native.upload(p.position, p.velocity, t, p.id)
+
+    # -- matrix --
+    def generate_matrix(self):
+        """B/Physics.java:170-176."""
+        size = self.settings.matrix.shape[0]
+        self.settings.matrix = np.asarray(self.matrix_generator.make_matrix(size, self.rng), np.float64)
+
+    def set_matrix_size(self, new_size: int):
+        """B/Physics.java:238-258."""
+        prev = self.settings.matrix
+        if new_size == prev.shape[0]:
+            return
+        m = np.asarray(self.matrix_generator.make_matrix(new_size, self.rng), np.float64)
+        c = min(prev.shape[0], new_size)
+        m[:c, :c] = prev[:c, :c]
+        self.settings.matrix = m
+        if new_size < prev.shape[0]:
+            self.ensure_types()
+
+    def get_type_count(self) -> np.ndarray:
+        """A/ExtendedPhysics.java:19-26."""
+        self._push_settings()
+        return self.native.type_histogram()
+
+    # -- geometry helpers (host, tiny) --
+    def ensure_position(self, pos: np.ndarray) -> np.ndarray:
+        """B/Physics.java:499-505 with B/Range.java:46-57,89-96."""
+        pos = np.asarray(pos, np.float64)
+        if self.settings.wrap:
+            out = np.where((pos < 0) | (pos >= 1), pos - np.floor(pos), pos)
+            return out
+        return np.clip(pos, 0.0, 1.0)
+
+    def connection(self, pos1, pos2) -> np.ndarray:
+        """B/Physics.java:460-470."""
+        d = np.asarray(pos2, np.float64) - np.asarray(pos1, np.float64)
+        if self.settings.wrap:
+            d = np.where(d < -0.5, d + 1.0, np.where(d >= 0.5, d - 1.0, d))
+        return d
+
+    def distance(self, pos1, pos2) -> float:
+        """B/Physics.java:477-479."""
+        return float(np.sqrt((self.connection(pos1, pos2) ** 2).sum()))

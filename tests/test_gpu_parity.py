@@ -1,0 +1,231 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical states.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8d):
+  fp32: ||dv||2/||v_ref||2 <= 1e-5 and max|dv|/rms(v_ref) <= 1e-4 on the velocity change of one step;
+  fp64: bit-exact (the fp64 kernels keep the reference's operation order, -fmad=false).
+Cell assignment, container offsets and particle order are integer-exact in both modes.
+"""
+import numpy as np
+import pytest
+
+import plife
+from helpers import make_state, max_over_rms, oracle_step, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DT = 0.02
+
+
+def gpu_step(native_lib, precision, pos, vel, types, matrix, steps=1, accel=(0, (0.3,)), flags=0, **kw):
+    p = plife.NativePhysics(precision=precision, flags=flags)
+    p.set_settings(kw.get("rmax", 0.02), kw.get("friction", 0.85), kw.get("force", 1.0), kw.get("wrap", True))
+    p.set_matrix(matrix)
+    p.set_accelerator(accel[0], accel[1])
+    p.upload(pos, vel, types)
+    p.step(kw.get("dt", DT), steps)
+    return p
+
+
+CASES = [
+    dict(n=10_000, m=6, rmax=0.04, wrap=True),    # C1
+    dict(n=10_000, m=6, rmax=0.02, wrap=True),    # C1 at the snapshot default rmax
+    dict(n=10_000, m=6, rmax=0.04, wrap=False),
+    dict(n=5_000, m=3, rmax=0.065, wrap=True),    # fat last cell (nx*rmax < 1)
+    dict(n=5_000, m=3, rmax=0.065, wrap=False),
+    dict(n=3_000, m=4, rmax=float(np.float32(0.04)), wrap=True),  # GUI float-widened rmax
+    dict(n=2_000, m=5, rmax=0.3, wrap=True),      # nx = 3: every lane on the literal path
+    dict(n=1_500, m=2, rmax=0.5, wrap=True),      # nx = 2: duplicate cell visits (E4)
+    dict(n=1_000, m=2, rmax=1.0, wrap=True),      # nx = 1
+    dict(n=1_500, m=2, rmax=0.5, wrap=False),
+    dict(n=20_000, m=70, rmax=0.02, wrap=True),   # matrix too large for shared memory
+    dict(n=200_000, m=8, rmax=0.01, wrap=True),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"n{c['n']}_m{c['m']}_r{c['rmax']:.3g}_{'wrap' if c['wrap'] else 'clamp'}")
+@pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
+def test_one_step_matches_oracle(native_lib, case, precision):
+    f32 = precision == plife.F32
+    pos, vel, types, matrix = make_state(case["n"], case["m"], seed=1000 + case["n"], vel_scale=0.05, f32=f32)
+    kw = dict(rmax=case["rmax"], wrap=case["wrap"], dt=DT)
+    o = oracle_step(pos, vel, types, matrix, **kw)
+    opos, ovel, otyp, oid = o.get_particles()
+    g = gpu_step(native_lib, precision, pos, vel, types, matrix, **kw)
+    got = g.download()
+
+    # sort order, types, container offsets: exact
+    assert np.array_equal(got.id, oid)
+    assert np.array_equal(got.type, otyp)
+    assert np.array_equal(g.containers(), o.containers())
+    st = g.step_stats()
+    assert (st["nx"], st["ny"]) == o.grid()
+    assert st["pair_evals"] == o.pair_stats()[0]
+
+    if f32:
+        mu = 0.85 ** (60 * DT)
+        dv_ref = ovel - vel[oid] * mu
+        dv_got = got.velocity - vel[oid] * mu
+        assert rel_l2(dv_got, dv_ref) <= 1e-5
+        assert max_over_rms(dv_got, dv_ref) <= 1e-4
+        assert rel_l2(got.velocity, ovel) <= 1e-5
+        # position: one fp32 rounding of x + v*dt (ulp(1) = 6e-8) on top of the velocity error, modulo the wrap
+        d = np.abs(got.position - opos)
+        d = np.minimum(d, 1.0 - d) if case["wrap"] else d
+        assert d.max() <= 1.3e-7 + DT * np.abs(got.velocity - ovel).max()
+    else:
+        assert np.array_equal(got.velocity, ovel)
+        assert np.array_equal(got.position, opos)
+
+
+@pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("wrap", [True, False], ids=["wrap", "clamp"])
+def test_neighbour_sets_match_oracle(native_lib, precision, wrap):
+    f32 = precision == plife.F32
+    pos, vel, types, matrix = make_state(30_000, 6, seed=77, f32=f32)
+    # put particles on the seams and exactly on 1.0
+    pos[:50, 0] = 1.0
+    pos[50:100, 1] = 1.0
+    pos[100:150, 0] = 0.0
+    rmax = 0.033
+    o = oracle_step(pos, vel, types, matrix, diag=True, rmax=rmax, wrap=wrap)
+    ocnt, ohash, oborder = o.neighbor_diag()
+    _, _, _, oid = o.get_particles()
+    p = plife.NativePhysics(precision=precision)
+    p.set_settings(rmax, 0.85, 1.0, wrap)
+    p.set_matrix(matrix)
+    p.upload(pos, vel, types)
+    cnt, hsh = p.debug_neighbors()
+    assert np.array_equal(p.download().id, oid)
+    if f32:
+        ok = oborder == 0  # pairs within 2e-6 relative of the cutoff may flip in fp32
+        assert (~ok).mean() < 0.01
+        assert np.array_equal(cnt[ok], ocnt[ok])
+        assert np.array_equal(hsh[ok], ohash[ok])
+    else:
+        assert np.array_equal(cnt, ocnt)
+        assert np.array_equal(hsh, ohash)
+
+
+@pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
+def test_multi_step_trajectory(native_lib, precision):
+    """fp64: 20 steps stay bit-identical.  fp32: re-synchronised every step."""
+    f32 = precision == plife.F32
+    pos, vel, types, matrix = make_state(8_000, 6, seed=5, f32=f32)
+    kw = dict(rmax=0.04, wrap=True, dt=DT)
+    if not f32:
+        o = oracle_step(pos, vel, types, matrix, steps=20, **kw)
+        g = gpu_step(native_lib, precision, pos, vel, types, matrix, steps=20, **kw)
+        opos, ovel, otyp, oid = o.get_particles()
+        got = g.download()
+        assert np.array_equal(got.id, oid)
+        assert np.array_equal(got.position, opos)
+        assert np.array_equal(got.velocity, ovel)
+        return
+    ids = np.arange(pos.shape[0], dtype=np.uint32)
+    p = plife.NativePhysics(precision=precision)
+    p.set_settings(kw["rmax"], 0.85, 1.0, True)
+    p.set_matrix(matrix)
+    p.upload(pos, vel, types, ids)
+    for _ in range(10):
+        cur = p.download()  # fp32-representable state, shared with the oracle
+        o = oracle_step(cur.position, cur.velocity, cur.type, matrix, ids=cur.id, **kw)
+        p.step(DT, 1)
+        opos, ovel, _, oid = o.get_particles()
+        got = p.download()
+        assert np.array_equal(got.id, oid)
+        assert rel_l2(got.velocity, ovel) <= 1e-5
+
+
+ACCELS = [(1, (0.3,)), (2, (0.3,)), (3, ()), (4, ()), (5, ()), (0, (0.45,))]
+
+
+@pytest.mark.parametrize("accel", ACCELS, ids=lambda a: f"kind{a[0]}_{len(a[1])}")
+@pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
+def test_alternate_accelerators(native_lib, accel, precision):
+    """Builder-defined accelerators (no reference definition): parity against our own oracle."""
+    f32 = precision == plife.F32
+    pos, vel, types, matrix = make_state(6_000, 5, seed=accel[0] + 40, vel_scale=0.02, f32=f32)
+    kw = dict(rmax=0.05, wrap=True, dt=DT)
+    params = tuple(accel[1]) + (0.0,) * (4 - len(accel[1])) if accel[1] else (0.3, 0, 0, 0)
+    o = oracle_step(pos, vel, types, matrix, accel_kind=accel[0], accel_params=params, **kw)
+    opos, ovel, _, oid = o.get_particles()
+    g = gpu_step(native_lib, precision, pos, vel, types, matrix, accel=accel, **kw)
+    got = g.download()
+    assert np.array_equal(got.id, oid)
+    if f32:
+        # the /r and /r^2 kinds amplify fp32 rounding at small distances: norm-wise only
+        assert rel_l2(got.velocity, ovel) <= (1e-4 if accel[0] in (1, 2) else 1e-5)
+    else:
+        if accel[0] == 4:  # cos/sin differ in the last ulp between libm and CUDA
+            assert rel_l2(got.velocity, ovel) <= 1e-13
+        else:
+            assert np.array_equal(got.velocity, ovel)
+            assert np.array_equal(got.position, opos)
+
+
+def test_edge_cases(native_lib):
+    p = plife.NativePhysics()
+    # empty state steps fine
+    p.set_matrix(np.zeros((2, 2)))
+    p.upload(np.zeros((0, 2)), None, np.zeros(0, np.int32))
+    p.step(DT, 3)
+    assert p.count == 0
+    # invalid inputs are rejected, not crashed on
+    with pytest.raises(plife.PlifeError):
+        p.set_settings(1.5, 0.85, 1.0, True)  # rmax > 1: nx = 0 (B/Physics.java:362-374 throws)
+    with pytest.raises(plife.PlifeError):
+        p.set_settings(0.0, 0.85, 1.0, True)
+    with pytest.raises(plife.PlifeError):
+        p.upload(np.array([[0.5, 1.5]]), None, np.array([0], np.int32))
+    with pytest.raises(plife.PlifeError):
+        p.upload(np.array([[0.5, 0.5]]), None, np.array([2], np.int32))  # type >= m
+    with pytest.raises(plife.PlifeError):
+        p.set_accelerator(99)
+    # single particle, coincident particles (d2 == 0 exerts no force, :432)
+    pos = np.array([[0.5, 0.5], [0.5, 0.5], [0.5, 0.5]])
+    p.set_settings(0.1, 0.85, 1.0, True)
+    p.set_matrix(np.ones((2, 2)))
+    p.upload(pos, None, np.array([0, 1, 0], np.int32))
+    p.step(DT, 1)
+    got = p.download()
+    assert np.array_equal(got.velocity, np.zeros((3, 2)))
+    assert np.array_equal(got.position, pos)
+    # type histogram
+    assert p.type_histogram().tolist() == [2, 1]
+    # matrix shrink below a resident type is a state error
+    with pytest.raises(plife.PlifeError):
+        p.set_matrix(np.zeros((1, 1)))
+
+
+def test_known_answers_on_gpu(native_lib):
+    """SURVEY.md Appendix C two-particle and seam cases, fp64 path."""
+    p = plife.NativePhysics(precision=plife.F64)
+    p.set_settings(0.04, 0.85, 1.0, True)
+    p.set_matrix(np.ones((1, 1)))
+    pos = np.array([[0.5, 0.5], [0.5 + 0.65 * 0.04, 0.5]])
+    p.upload(pos, None, np.zeros(2, np.int32))
+    p.step(DT, 1)
+    got = p.download()
+    order = np.argsort(got.id)
+    v = got.velocity[order]
+    assert abs(v[0, 0] - 8.0e-4) < 1e-15 and abs(v[1, 0] + 8.0e-4) < 1e-15
+    x = got.position[order]
+    assert abs(x[0, 0] - 0.500016) < 1e-12 and abs(x[1, 0] - 0.525984) < 1e-12
+    # seam: p pulled across the border with wrap, nothing without
+    for wrap, expect in ((True, 0.5714285714285714 * 0.04 * 0.02), (False, 0.0)):
+        p.set_settings(0.04, 0.85, 1.0, wrap)
+        p.upload(np.array([[0.99, 0.5], [0.01, 0.5]]), None, np.zeros(2, np.int32))
+        p.step(DT, 1)
+        got = p.download()
+        v = got.velocity[np.argsort(got.id)]
+        assert abs(v[0, 0] - expect) < 1e-15 and abs(v[1, 0] + expect) < 1e-15
+
+
+def test_unstable_sort_flag_same_sets(native_lib):
+    pos, vel, types, matrix = make_state(20_000, 4, seed=9, f32=True)
+    kw = dict(rmax=0.03, wrap=True)
+    a = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, **kw).download()
+    b = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, flags=plife.FLAG_UNSTABLE_SORT, **kw).download()
+    ia, ib = np.argsort(a.id), np.argsort(b.id)
+    assert np.array_equal(a.type[ia], b.type[ib])
+    assert rel_l2(b.velocity[ib], a.velocity[ia]) <= 1e-5
