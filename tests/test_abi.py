@@ -1,0 +1,79 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/plife.h declares, validates arguments on the host and refuses to compute without CUDA."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "plife.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(plife_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_surface():
+    syms = declared_symbols()
+    for must in ("plife_create", "plife_destroy", "plife_step", "plife_set_settings", "plife_set_matrix",
+                 "plife_set_accelerator", "plife_upload", "plife_download", "plife_request_stop", "plife_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    for s in declared_symbols():
+        assert hasattr(native_lib, s), f"libplife.so does not export {s}"
+    assert native_lib.plife_version() == 100
+
+
+def test_product_library_does_not_link_the_oracle(native_lib):
+    from plife import _native
+    import subprocess
+    out = subprocess.run(["nm", "-D", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle_" not in out
+    src_dir = os.path.join(ROOT, "particle-life-app_b200")
+    for dirpath, _, files in os.walk(src_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "plife_oracle" not in text, f
+
+
+def test_no_gpu_means_loud_failure(native_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: the no-device path cannot be observed")
+    import plife
+    from plife import _native as N
+    with pytest.raises(plife.PlifeError) as e:
+        plife.NativePhysics()
+    assert e.value.status == N.ERR_CUDA
+    h = C.c_void_p()
+    assert native_lib.plife_create(None, C.byref(h)) == N.ERR_INVALID
+    assert native_lib.plife_status_string(N.ERR_CUDA).decode() == "CUDA error"
+    assert native_lib.plife_set_settings(None, None) == N.ERR_INVALID
+    assert native_lib.plife_count(None) == N.ERR_INVALID
+
+
+def test_struct_layouts_match_header():
+    from plife import _native as N
+    assert C.sizeof(N.Settings) == 32 and C.sizeof(N.Config) == 32 and C.sizeof(N.StepStats) == 32
+
+
+def test_synth_generators_are_deterministic_and_in_range():
+    from plife import synth
+    p1, v1, t1 = synth.uniform_state(5000, 7, 42)
+    p2, _, t2 = synth.uniform_state(5000, 7, 42, chunk=1000)
+    assert np.array_equal(p1, p2) and np.array_equal(t1, t2)
+    assert p1.min() >= 0 and p1.max() < 1 and t1.min() >= 0 and t1.max() <= 6 and not v1.any()
+    M = synth.random_matrix(7, 42)
+    assert M.shape == (7, 7) and M.min() >= -1 and M.max() < 1
+    # SplitMix64 reference value: first output for seed 0 is 0xE220A8397B1DCDAF
+    assert int(synth.draw(0, np.array([0], np.uint64))[0]) == 0xE220A8397B1DCDAF
+    for c in synth.CONFIGS.values():
+        nx = int(np.floor(1.0 / c["rmax"]))
+        assert nx >= 25
+    assert int(np.floor(1.0 / synth.CONFIGS["C4"]["rmax"])) == 2800
