@@ -18,16 +18,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// B/Physics.java:362-375 getContainerIndex: (int)(x / containerSize) in fp64,
-// with the `== nx -> nx-1` clamp for x == 1.0.
-__device__ __forceinline__ int container_index(double x, double y, const Grid &g)
-{
-    int cx = (int)(x / g.cs);
-    int cy = (int)(y / g.cs);
-    if (cx == g.nx) cx = g.nx - 1;
-    if (cy == g.ny) cy = g.ny - 1;
-    return cx + cy * g.nx;
-}
 
 __global__ void __launch_bounds__(kThreads) bin_f32(const float4 *__restrict__ pt, int n, Grid g,
                                                     int32_t *__restrict__ cell, int32_t *__restrict__ count)
@@ -35,9 +25,9 @@ __global__ void __launch_bounds__(kThreads) bin_f32(const float4 *__restrict__ p
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     float4 p = __ldg(&pt[i]);
-    int c = container_index((double)p.x, (double)p.y, g);
-    cell[i] = c;
-    atomicAdd(&count[c], 1);
+    int cxy = cell_coords((double)p.x, (double)p.y, g);
+    cell[i] = cxy;
+    atomicAdd(&count[container_of(cxy, g)], 1);
 }
 
 __global__ void __launch_bounds__(kThreads) bin_f64(const double2 *__restrict__ pos, int n, Grid g,
@@ -46,9 +36,9 @@ __global__ void __launch_bounds__(kThreads) bin_f64(const double2 *__restrict__ 
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     double2 p = __ldg(&pos[i]);
-    int c = container_index(p.x, p.y, g);
-    cell[i] = c;
-    atomicAdd(&count[c], 1);
+    int cxy = cell_coords(p.x, p.y, g);
+    cell[i] = cxy;
+    atomicAdd(&count[container_of(cxy, g)], 1);
 }
 
 // ---- exclusive scan over cells: tile sums -> scan of sums -> apply ----
@@ -181,20 +171,19 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
 
 // B/Physics.java:343-348: `i = containers[ci]; buffer[i] = p; containers[ci]++`.
 // Afterwards cell_end[ci] is the END offset of cell ci, as in the reference.
-__global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n,
+__global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n, Grid g,
                                                          int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
 {
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
-    int c = __ldg(&cell[i]);
+    int c = container_of(__ldg(&cell[i]), g);
     int dst = atomicAdd(&cell_end[c], 1);
     perm[dst] = i;
 }
 
-__device__ __forceinline__ int stable_slot(int d, int src, const int32_t *__restrict__ cell,
-                                           const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm)
+__device__ __forceinline__ int stable_slot(int src, int c, const int32_t *__restrict__ cell_end,
+                                           const int32_t *__restrict__ perm)
 {
-    int c = __ldg(&cell[src]);
     int s = c == 0 ? 0 : __ldg(&cell_end[c - 1]);
     int e = __ldg(&cell_end[c]);
     int rank = 0;
@@ -204,23 +193,26 @@ __device__ __forceinline__ int stable_slot(int d, int src, const int32_t *__rest
 
 template <bool STABLE>
 __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, const float2 *__restrict__ vel_in,
-                                                       float4 *__restrict__ pt_out, float2 *__restrict__ vel_out, int n,
-                                                       const int32_t *__restrict__ cell, const int32_t *__restrict__ cell_end,
-                                                       const int32_t *__restrict__ perm)
+                                                       float4 *__restrict__ pt_out, float2 *__restrict__ vel_out, int n, Grid g,
+                                                       const int32_t *__restrict__ cell, int32_t *__restrict__ cell_sorted,
+                                                       const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm)
 {
     int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= n) return;
     int src = __ldg(&perm[d]);
     float4 p = __ldg(&pt_in[src]);
     float2 v = __ldg(&vel_in[src]);
-    int dst = STABLE ? stable_slot(d, src, cell, cell_end, perm) : d;
+    int cxy = __ldg(&cell[src]);
+    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm) : d;
     pt_out[dst] = p;
     vel_out[dst] = v;
+    cell_sorted[dst] = cxy;
 }
 
 template <bool STABLE>
-__global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out, int n, const int32_t *__restrict__ cell,
-                                                       const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm)
+__global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out, int n, Grid g, const int32_t *__restrict__ cell,
+                                                       int32_t *__restrict__ cell_sorted, const int32_t *__restrict__ cell_end,
+                                                       const int32_t *__restrict__ perm)
 {
     int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= n) return;
@@ -229,7 +221,9 @@ __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out
     double2 v = __ldg(&in.vel[src]);
     int t = __ldg(&in.type[src]);
     uint32_t id = __ldg(&in.id[src]);
-    int dst = STABLE ? stable_slot(d, src, cell, cell_end, perm) : d;
+    int cxy = __ldg(&cell[src]);
+    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm) : d;
+    cell_sorted[dst] = cxy;
     out.pos[dst] = p;
     out.vel[dst] = v;
     out.type[dst] = t;
@@ -350,15 +344,15 @@ cudaError_t launch_scan(plife_handle *h, const Grid &g)
     return cudaGetLastError();
 }
 
-cudaError_t launch_scatter(plife_handle *h, const Grid &)
+cudaError_t launch_scatter(plife_handle *h, const Grid &g)
 {
     int n = (int)h->n;
     if (n == 0) return cudaSuccess;
-    scatter_perm<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, h->d_cell_end, h->d_perm);
+    scatter_perm<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, h->d_cell_end, h->d_perm);
     return cudaGetLastError();
 }
 
-cudaError_t launch_gather(plife_handle *h, const Grid &)
+cudaError_t launch_gather(plife_handle *h, const Grid &g)
 {
     int n = (int)h->n;
     if (n == 0) return cudaSuccess;
@@ -367,16 +361,16 @@ cudaError_t launch_gather(plife_handle *h, const Grid &)
     int nb = blocks_for(n, kThreads);
     if (h->precision == PLIFE_F32) {
         if (stable)
-            gather_f32<true><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n,
-                                                             h->d_cell, h->d_cell_end, h->d_perm);
+            gather_f32<true><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
+                                                             h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
         else
-            gather_f32<false><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n,
-                                                              h->d_cell, h->d_cell_end, h->d_perm);
+            gather_f32<false><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
+                                                              h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
     } else {
         if (stable)
-            gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, h->d_cell, h->d_cell_end, h->d_perm);
+            gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
         else
-            gather_f64<false><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, h->d_cell, h->d_cell_end, h->d_perm);
+            gather_f64<false><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
     }
     return cudaGetLastError();
 }

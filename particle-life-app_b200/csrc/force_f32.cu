@@ -9,16 +9,33 @@ static IOF32 make_io(plife_handle *h)
     return IOF32{h->s32[src].pt, h->s32[src].vel, h->s32[dst].pt, h->s32[dst].vel};
 }
 
+static NextBin next_bin(plife_handle *h)
+{
+    if (h->flags & PLIFE_FLAG_NO_FUSED_BIN) return NextBin{nullptr, nullptr};
+    return NextBin{h->d_cell, h->d_count};
+}
+
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
 {
-    return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, p, (const float *)h->d_matrix_t, h->acc_kind, h->stream);
+    const float *mt = (const float *)h->d_matrix_t;
+    const float *mrow = mt + (size_t)p.m * p.m; // row-major copy follows the transposed one
+    // v2 staged kernel whenever the per-lane matrix table fits; v1 (global-memory walk) otherwise
+    if (p.m <= kTabMaxM && !(h->flags & PLIFE_FLAG_FORCE_V1)) {
+        // capacity of one staged row range: 128 targets + the cells hanging over both ends + margin
+        const double rho = (double)p.n / ((double)p.g.nx * p.g.ny);
+        int cap = (int)(kForceThreads + 4.0 * rho + 8.0 * sqrt(rho + 1.0) + 32.0);
+        cap = (cap + 31) / 32 * 32;
+        if (cap > 1536) cap = 1536;
+        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, mrow, h->acc_kind, cap, next_bin(h), h->stream);
+    }
+    return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, mt, h->acc_kind, next_bin(h), h->stream);
 }
 
 cudaError_t launch_neighbors_f32(plife_handle *h, const ForceParams<float> &p, int32_t *cnt, unsigned long long *hash)
 {
     if (p.n == 0) return cudaSuccess;
     const int nb = (p.n + kForceThreads - 1) / kForceThreads;
-    neighbors_kernel<IOF32><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, p, cnt, hash);
+    neighbors_kernel<IOF32><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, cnt, hash);
     return cudaGetLastError();
 }
 
@@ -26,7 +43,7 @@ cudaError_t launch_pair_count_f32(plife_handle *h, const ForceParams<float> &p, 
 {
     if (p.n == 0) return cudaSuccess;
     const int nb = (p.n + kForceThreads - 1) / kForceThreads;
-    pair_count_kernel<IOF32><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, p, d_total);
+    pair_count_kernel<IOF32><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, d_total);
     return cudaGetLastError();
 }
 

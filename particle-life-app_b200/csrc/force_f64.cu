@@ -13,14 +13,16 @@ static IOF64 make_io(plife_handle *h)
 
 cudaError_t launch_force_f64(plife_handle *h, const ForceParams<double> &p)
 {
-    return dispatch_force<IOF64, false>(make_io(h), h->d_cell_end, p, (const double *)h->d_matrix_t, h->acc_kind, h->stream);
+    NextBin nb{nullptr, nullptr};
+    if (!(h->flags & PLIFE_FLAG_NO_FUSED_BIN)) nb = NextBin{h->d_cell, h->d_count};
+    return dispatch_force<IOF64, false>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, (const double *)h->d_matrix_t, h->acc_kind, nb, h->stream);
 }
 
 cudaError_t launch_neighbors_f64(plife_handle *h, const ForceParams<double> &p, int32_t *cnt, unsigned long long *hash)
 {
     if (p.n == 0) return cudaSuccess;
     const int nb = (p.n + kForceThreads - 1) / kForceThreads;
-    neighbors_kernel<IOF64><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, p, cnt, hash);
+    neighbors_kernel<IOF64><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, cnt, hash);
     return cudaGetLastError();
 }
 
@@ -28,7 +30,7 @@ cudaError_t launch_pair_count_f64(plife_handle *h, const ForceParams<double> &p,
 {
     if (p.n == 0) return cudaSuccess;
     const int nb = (p.n + kForceThreads - 1) / kForceThreads;
-    pair_count_kernel<IOF64><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, p, d_total);
+    pair_count_kernel<IOF64><<<nb, kForceThreads, 0, h->stream>>>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, d_total);
     return cudaGetLastError();
 }
 

@@ -140,11 +140,12 @@ __device__ __forceinline__ bool in_range(float dx, float dy, float r2)
 // d2 == 0 fails the in-range test).  All other lanes take the literal path.
 template <typename IO, typename V>
 __device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict__ cell_end, const Grid &g, int wrap,
-                                         int i, typename IO::R xi, typename IO::R yi, V &v)
+                                         int i, typename IO::R xi, typename IO::R yi, int cxy, V &v)
 {
     using R = typename IO::R;
-    const int cx0 = (int)floor((double)xi / g.cs); // :404, no ==nx clamp
-    const int cy0 = (int)floor((double)yi / g.cs); // :405
+    // :404-405 floor(x / containerSize) without the ==nx clamp: cached by the binning pass (cell_coords)
+    const int cx0 = cxy & 0xffff;
+    const int cy0 = cxy >> 16;
     const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
     if (interior) {
 #pragma unroll 1
@@ -228,25 +229,34 @@ __device__ __forceinline__ void accelerate(R a, R px, R py, const R *prm, R &ox,
 }
 
 // ---- visitors ---------------------------------------------------------------------
-template <typename R, bool SMEM>
+constexpr int kMatGlobal = 0; // Mt in global memory (any m)
+constexpr int kMatShared = 1; // Mt copied to shared memory (m <= 64)
+constexpr int kMatLaneTab = 2; // per-lane copy of the lane's own matrix row (staged kernel, m <= 32)
+constexpr int kTabShift = 9;  // lane-table key = type << 9 = byte offset of row `type` (kForceThreads * 4 bytes per row)
+
+template <typename R, int MODE>
 struct MatrixView { // transposed matrix Mt[other][own]
     const R *g;     // global copy
-    const R *s;     // shared copy (valid when SMEM), already multiplied by `scale`
+    const R *s;     // shared copy (MODE 1: Mt, MODE 2: tab[other][thread]), already multiplied by `scale`
     int m, own;
     R scale;
-    uint32_t row; // shared-window byte address of Mt[0][own]
+    uint32_t row; // shared-window byte address of this lane's column
     uint32_t mb;  // bytes per matrix row
     __device__ __forceinline__ void init()
     {
-        if (SMEM) {
+        if (MODE == kMatShared) {
             row = (uint32_t)__cvta_generic_to_shared(s + own);
             mb = (uint32_t)m * (uint32_t)sizeof(R);
+        } else if (MODE == kMatLaneTab) {
+            row = (uint32_t)__cvta_generic_to_shared(s + threadIdx.x);
         }
     }
-    __device__ __forceinline__ R get(int other) const
+    // `key` is the candidate's type (MODE 0/1) or type << kTabShift (MODE 2)
+    __device__ __forceinline__ R get(int key) const
     {
-        if (SMEM) return lds(row + (uint32_t)other * mb); // one IMAD + one LDS
-        return __ldg(g + other * m + own) * scale;
+        if (MODE == kMatShared) return lds(row + (uint32_t)key * mb); // one IMAD + one LDS
+        if (MODE == kMatLaneTab) return lds(row + (uint32_t)key);     // one IADD + one conflict-free LDS
+        return __ldg(g + key * m + own) * scale;
     }
     static __device__ __forceinline__ float lds_(uint32_t a, float)
     {
@@ -265,12 +275,12 @@ struct MatrixView { // transposed matrix Mt[other][own]
 
 // Literal visitor: accumulates term by term into the running velocity, exactly
 // like `p.velocity.add(deltaV.mul(rmax*force*dt))` (B/Physics.java:437).
-template <typename R, int KIND, bool SMEM>
+template <typename R, int KIND, int MODE>
 struct LiteralForce {
     R vx, vy;
     R r2, invr, k2;
     const R *prm;
-    MatrixView<R, SMEM> M;
+    MatrixView<R, MODE> M;
     __device__ __forceinline__ void pair(int, const Cand<R> &q, R dx, R dy)
     {
         if (in_range(dx, dy, r2)) {
@@ -298,11 +308,11 @@ struct LiteralForce {
 // factor 1/b is folded into the final scale, a' into the shared-memory matrix.
 // Every constant is a direct constant-bank operand: no 3-register FFMA except
 // the three that must be (f and the two accumulators).
-template <bool SMEM>
+template <int MODE>
 struct FastParticleLife32 {
     float ax, ay;
     float b, d0, h;
-    MatrixView<float, SMEM> M;
+    MatrixView<float, MODE> M;
     __device__ __forceinline__ void pair(int, const Cand<float> &q, float dx, float dy)
     {
         float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
@@ -346,6 +356,22 @@ struct PairCountVisitor {
     __device__ __forceinline__ void pair(int j, const Cand<R> &, R, R) { count += (j != self) ? 1u : 0u; }
 };
 
+// Fused K_BIN of the NEXT step: the integrate epilogue knows the new position, so it bins it
+// (B/Physics.java:329-332 of the next update()) and saves a pass over the particle array.
+struct NextBin {
+    int32_t *cell;  // packed cell coords per particle, or nullptr: do not bin
+    int32_t *count; // per-cell histogram (zeroed by K_SCAN of this step)
+    template <typename R>
+    __device__ __forceinline__ void add(int i, R x, R y, const Grid &g) const
+    {
+        if (cell) {
+            const int cxy = cell_coords((double)x, (double)y, g);
+            cell[i] = cxy;
+            atomicAdd(count + container_of(cxy, g), 1);
+        }
+    }
+};
+
 // ---- kernels ---------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ void load_matrix_smem(R *sM, const R *__restrict__ gMt, int m, R scale)
@@ -356,8 +382,9 @@ __device__ __forceinline__ void load_matrix_smem(R *sM, const R *__restrict__ gM
 
 template <typename IO, int KIND, bool SMEM, bool FAST>
 __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32_t *__restrict__ cell_end,
+                                                             const int32_t *__restrict__ cell_sorted,
                                                              ForceParams<typename IO::R> P,
-                                                             const typename IO::R *__restrict__ gMt)
+                                                             const typename IO::R *__restrict__ gMt, NextBin nb)
 {
     using R = typename IO::R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -368,20 +395,22 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
     const int i = blockIdx.x * kForceThreads + threadIdx.x;
     if (i >= P.n) return;
     const Cand<R> self = io.cand(i);
+    const int cxy = __ldg(cell_sorted + i);
     R vx, vy;
     io.self_vel(i, vx, vy);
-    MatrixView<R, SMEM> M{gMt, sM, P.m, self.type, mscale, 0u, 0u};
+    constexpr int MODE = SMEM ? kMatShared : kMatGlobal;
+    MatrixView<R, MODE> M{gMt, sM, P.m, self.type, mscale, 0u, 0u};
     M.init();
 
     R nvx, nvy;
     if constexpr (FAST) {
-        FastParticleLife32<SMEM> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
-        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+        FastParticleLife32<MODE> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, cxy, v);
         nvx = fmaf(P.fast_k, v.ax, vx * P.mu); // friction first (:401-402), then the summed acceleration
         nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
     } else {
-        LiteralForce<R, KIND, SMEM> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
-        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+        LiteralForce<R, KIND, MODE> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
+        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, cxy, v);
         v.finish(nvx, nvy);
     }
     // updatePosition (:443-450): pos = vel*dt + pos, then wrap or clamp (:499-505)
@@ -395,10 +424,230 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
         ny_ = range_clamp(ny_);
     }
     io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
+    nb.add(i, nx_, ny_, P.g);
+}
+
+// ---- v2: shared-memory staged candidates (fp32) ------------------------------------------
+// The per-lane `LDG.128` of the kernel above costs 4 L1 data-pipe cycles per warp whatever the
+// address pattern, and the shared matrix lookup bank-conflicts between lanes of different cells
+// (profiles/r1_force_kernel.md); together they saturate L1TEX before the FP32 pipes.  Here each
+// CTA (128 consecutive sorted particles, about 8 cells) first copies the three index ranges that
+// cover the rows above / of / below its cells into shared memory - linear cell ids are
+// row-major, so [cellA + dy*nx - 1, cellB + dy*nx + 1] is ONE contiguous index range per dy -
+// and every lane copies its own matrix row into a [type][thread] table.  The inner loop then
+// issues one `LDS.128` (2.5 cycles with the 2-3 distinct addresses of a warp) and one
+// conflict-free `LDS.32` (bank = lane) per candidate.
+//
+// Trip counts are rounded up to a multiple of 4 (no remainder loops): the extra candidates are
+// the first particles of cell cx0+2 or beyond, whose |dx| exceeds rmax for an interior lane, so
+// they contribute exactly zero; each staged range is followed by 3 far-away sentinels for the
+// case where the range itself ends.  Lanes on the domain seam, and CTAs whose ranges exceed
+// the staging capacity (dense clusters), walk global memory with the literal 9-cell loop.
+constexpr int kTabMaxM = 32;
+constexpr int kStagePad = 3; // sentinels after each staged range
+
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+template <typename V>
+__device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g,
+                                                int wrap, int i, float xi, float yi, int cxy, bool staged_ok,
+                                                uint32_t stage_addr, int cap, const int *s_start, V &v)
+{
+    const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
+    const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
+    if (interior && staged_ok) {
+        const int base0 = (cy0 - 1) * g.nx + cx0;
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+            const int base = base0 + r * g.nx;
+            const int s = base >= 2 ? __ldg(cell_end + base - 2) : 0;
+            const int e = __ldg(cell_end + base + 1);
+            uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s - s_start[r]) * 16u;
+            const uint32_t a1 = a + (uint32_t)(e - s) * 16u;
+            for (; a < a1; a += 64u) { // 4 candidates per trip, padded (see above)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 q = lds128(a + 16u * u);
+                    v.pair(-1, Cand<float>{q.x, q.y, __float_as_int(q.z), 0u}, q.x - xi, q.y - yi);
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < 9; ++k) {
+            const int ox = k % 3 - 1, oy = k / 3 - 1;
+            int cx = wrap_container(cx0 + ox, g.nx);
+            int cy = wrap_container(cy0 + oy, g.ny);
+            if (wrap) {
+                cx = wrap_container(cx, g.nx);
+                cy = wrap_container(cy, g.ny);
+            } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
+                continue;
+            }
+            const int ci = cx + cy * g.nx;
+            const int s = ci == 0 ? 0 : __ldg(cell_end + ci - 1);
+            const int e = __ldg(cell_end + ci);
+            for (int j = s; j < e; ++j) {
+                if (j == i) continue;
+                Cand<float> q = io.cand(j);
+                q.type <<= kTabShift;
+                float dx, dy;
+                if (wrap) {
+                    dx = wrap_connection(xi, q.x);
+                    dy = wrap_connection(yi, q.y);
+                } else {
+                    dx = q.x - xi;
+                    dy = q.y - yi;
+                }
+                v.pair(j, q, dx, dy);
+            }
+        }
+    }
+}
+
+// gM: row-major matrix [own][other] (for the vectorised row copy), gMt: transposed
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kForceThreads) force_kernel_staged(IOF32 io, const int32_t *__restrict__ cell_end,
+                                                                    const int32_t *__restrict__ cell_sorted,
+                                                                    ForceParams<float> P, const float *__restrict__ gM,
+                                                                    int cap, NextBin nb)
+{
+    static_assert(kForceThreads * 4 == (1 << kTabShift), "lane-table row stride");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                                      // [3][cap + kStagePad]
+    float *tab = reinterpret_cast<float *>(smem_raw + (size_t)3 * (cap + kStagePad) * 16);      // [m][kForceThreads]
+    __shared__ int s_cell[2], s_start[3], s_len[3];
+
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * kForceThreads + tid;
+    const bool valid = i < P.n;
+    const Grid g = P.g;
+    Cand<float> self{0.f, 0.f, 0, 0u};
+    int cxy = 0;
+    if (valid) {
+        self = io.cand(i);
+        cxy = __ldg(cell_sorted + i);
+        if (tid == 0) s_cell[0] = container_of(cxy, g);
+        if (tid == kForceThreads - 1 || i == P.n - 1) s_cell[1] = container_of(cxy, g);
+    }
+    // this lane's matrix row -> tab[other][tid] (bank = lane: conflict-free lookups)
+    {
+        const float mscale = FAST ? P.fast_a_scale : 1.0f;
+        const float *rowp = gM + self.type * P.m;
+        if ((P.m & 3) == 0) {
+            for (int t = 0; t < P.m; t += 4) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rowp + t));
+                tab[(t + 0) * kForceThreads + tid] = r4.x * mscale;
+                tab[(t + 1) * kForceThreads + tid] = r4.y * mscale;
+                tab[(t + 2) * kForceThreads + tid] = r4.z * mscale;
+                tab[(t + 3) * kForceThreads + tid] = r4.w * mscale;
+            }
+        } else {
+            for (int t = 0; t < P.m; ++t) tab[t * kForceThreads + tid] = __ldg(rowp + t) * mscale;
+        }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        const int ncell = g.nx * g.ny;
+        int lo = s_cell[0] + (tid - 1) * g.nx - 1;
+        int hi = s_cell[1] + (tid - 1) * g.nx + 1;
+        lo = max(lo, 0);
+        hi = min(hi, ncell - 1);
+        int start = 0, len = 0;
+        if (lo <= hi) {
+            start = lo > 0 ? __ldg(cell_end + lo - 1) : 0;
+            len = __ldg(cell_end + hi) - start;
+        }
+        s_start[tid] = start;
+        s_len[tid] = len;
+    }
+    __syncthreads();
+    const bool staged_ok = s_len[0] <= cap && s_len[1] <= cap && s_len[2] <= cap;
+    if (staged_ok) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int len = s_len[r];
+            const float4 *src = io.pt + s_start[r];
+            float4 *dst = stage + r * (cap + kStagePad);
+            for (int k = tid; k < len + kStagePad; k += kForceThreads) {
+                float4 q = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f); // sentinel: far away, matrix key 0
+                if (k < len) {
+                    q = __ldg(src + k);
+                    q.z = __int_as_float(__float_as_int(q.z) << kTabShift); // matrix key = byte offset of row `type`
+                }
+                dst[k] = q;
+            }
+        }
+    }
+    __syncthreads();
+    if (!valid) return;
+
+    float vx, vy;
+    io.self_vel(i, vx, vy);
+    MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, self.type, 1.0f, 0u, 0u};
+    M.init();
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+    float nvx, nvy;
+    if constexpr (FAST) {
+        FastParticleLife32<kMatLaneTab> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        traverse_staged(io, cell_end, g, P.wrap, i, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
+        nvx = fmaf(P.fast_k, v.ax, vx * P.mu);
+        nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
+    } else {
+        LiteralForce<float, KIND, kMatLaneTab> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
+        traverse_staged(io, cell_end, g, P.wrap, i, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
+        v.finish(nvx, nvy);
+    }
+    float nx_ = fmaf(nvx, P.dt, self.x);
+    float ny_ = fmaf(nvy, P.dt, self.y);
+    if (P.wrap) {
+        nx_ = range_wrap(nx_);
+        ny_ = range_wrap(ny_);
+    } else {
+        nx_ = range_clamp(nx_);
+        ny_ = range_clamp(ny_);
+    }
+    io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
+    nb.add(i, nx_, ny_, g);
+}
+
+inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted,
+                                         const ForceParams<float> &P, const float *gM, int kind, int cap, NextBin nbin,
+                                         cudaStream_t stream)
+{
+    if (P.n == 0) return cudaSuccess;
+    const int nb = (P.n + kForceThreads - 1) / kForceThreads;
+    const size_t sbytes = (size_t)3 * (cap + kStagePad) * 16 + (size_t)P.m * kForceThreads * 4;
+#define PLIFE_LAUNCH_STAGED(KIND, FAST)                                                                          \
+    do {                                                                                                         \
+        auto kfn = force_kernel_staged<KIND, FAST>;                                                              \
+        if (sbytes > 48 * 1024) {                                                                                \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);  \
+            if (e != cudaSuccess) return e;                                                                      \
+        }                                                                                                        \
+        kfn<<<nb, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, P, gM, cap, nbin);                 \
+    } while (0)
+    switch (kind) {
+    case PLIFE_ACC_PARTICLE_LIFE: PLIFE_LAUNCH_STAGED(PLIFE_ACC_PARTICLE_LIFE, true); break;
+    case PLIFE_ACC_PARTICLE_LIFE_R: PLIFE_LAUNCH_STAGED(PLIFE_ACC_PARTICLE_LIFE_R, false); break;
+    case PLIFE_ACC_PARTICLE_LIFE_R2: PLIFE_LAUNCH_STAGED(PLIFE_ACC_PARTICLE_LIFE_R2, false); break;
+    case PLIFE_ACC_ROTATOR_90: PLIFE_LAUNCH_STAGED(PLIFE_ACC_ROTATOR_90, false); break;
+    case PLIFE_ACC_ROTATOR_ATTR: PLIFE_LAUNCH_STAGED(PLIFE_ACC_ROTATOR_ATTR, false); break;
+    case PLIFE_ACC_PLANETS: PLIFE_LAUNCH_STAGED(PLIFE_ACC_PLANETS, false); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef PLIFE_LAUNCH_STAGED
+    return cudaGetLastError();
 }
 
 template <typename IO>
 __global__ void __launch_bounds__(kForceThreads) neighbors_kernel(IO io, const int32_t *__restrict__ cell_end,
+                                                                 const int32_t *__restrict__ cell_sorted,
                                                                  ForceParams<typename IO::R> P, int32_t *__restrict__ cnt,
                                                                  unsigned long long *__restrict__ hash)
 {
@@ -407,13 +656,14 @@ __global__ void __launch_bounds__(kForceThreads) neighbors_kernel(IO io, const i
     if (i >= P.n) return;
     const Cand<R> self = io.cand(i);
     NeighborVisitor<R> v{{0, 0ull}, P.r2};
-    traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+    traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, __ldg(cell_sorted + i), v);
     cnt[i] = v.d.count;
     hash[i] = v.d.hash;
 }
 
 template <typename IO>
 __global__ void __launch_bounds__(kForceThreads) pair_count_kernel(IO io, const int32_t *__restrict__ cell_end,
+                                                                  const int32_t *__restrict__ cell_sorted,
                                                                   ForceParams<typename IO::R> P,
                                                                   unsigned long long *__restrict__ total)
 {
@@ -424,7 +674,7 @@ __global__ void __launch_bounds__(kForceThreads) pair_count_kernel(IO io, const 
     if (i < P.n) {
         const Cand<R> self = io.cand(i);
         PairCountVisitor<R> v{i, 0ull};
-        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, v);
+        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, __ldg(cell_sorted + i), v);
         c = v.count;
     }
 #pragma unroll
@@ -440,8 +690,9 @@ __global__ void __launch_bounds__(kForceThreads) pair_count_kernel(IO io, const 
 
 // dispatch over accelerator kind / matrix placement
 template <typename IO, bool FAST_OK>
-cudaError_t dispatch_force(const IO &io, const int32_t *cell_end, const ForceParams<typename IO::R> &P,
-                           const typename IO::R *gMt, int kind, cudaStream_t stream)
+cudaError_t dispatch_force(const IO &io, const int32_t *cell_end, const int32_t *cell_sorted,
+                           const ForceParams<typename IO::R> &P, const typename IO::R *gMt, int kind, NextBin nbin,
+                           cudaStream_t stream)
 {
     using R = typename IO::R;
     if (P.n == 0) return cudaSuccess;
@@ -455,7 +706,7 @@ cudaError_t dispatch_force(const IO &io, const int32_t *cell_end, const ForcePar
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes); \
             if (e != cudaSuccess) return e;                                                                     \
         }                                                                                                       \
-        kfn<<<nb, kForceThreads, sbytes, stream>>>(io, cell_end, P, gMt);                                       \
+        kfn<<<nb, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, P, gMt, nbin);                    \
     } while (0)
 #define PLIFE_KIND(KIND)                       \
     do {                                       \

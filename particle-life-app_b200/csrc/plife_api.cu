@@ -68,9 +68,11 @@ void free_state(plife_handle *h)
         h->s64[b] = StateF64{};
     }
     cudaFree(h->d_cell);
+    cudaFree(h->d_cell_sorted);
     cudaFree(h->d_perm);
-    h->d_cell = h->d_perm = nullptr;
+    h->d_cell = h->d_cell_sorted = h->d_perm = nullptr;
     h->cap = 0;
+    h->prebinned = false;
 }
 
 // grow particle buffers; contents are NOT preserved
@@ -92,6 +94,7 @@ int ensure_capacity(plife_handle *h, int64_t n)
         }
     }
     CU(h, dev_alloc(&h->d_cell, c));
+    CU(h, dev_alloc(&h->d_cell_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
     h->cap = n;
     return PLIFE_OK;
@@ -114,6 +117,8 @@ int ensure_cells(plife_handle *h, int64_t ncell)
     CU(h, dev_alloc(&h->d_tile_sums, (size_t)(padded / kScanTile)));
     CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)padded, h->stream));
     h->cell_cap = padded;
+    h->count_dirty = false;
+    h->prebinned = false;
     return PLIFE_OK;
 }
 
@@ -138,12 +143,16 @@ int upload_matrix_t(plife_handle *h)
         cudaFree(h->d_matrix_t);
         h->d_matrix_t = nullptr;
         h->d_matrix_cap = 0;
-        CU(h, cudaMalloc(&h->d_matrix_t, sizeof(double) * (size_t)m * m));
+        CU(h, cudaMalloc(&h->d_matrix_t, 2 * sizeof(double) * (size_t)m * m));
         h->d_matrix_cap = m * m;
     }
-    std::vector<R> t((size_t)m * m);
+    // device layout: transposed copy Mt[other][own], then the row-major copy M[own][other]
+    std::vector<R> t((size_t)2 * m * m);
     for (int own = 0; own < m; own++)
-        for (int other = 0; other < m; other++) t[(size_t)other * m + own] = (R)h->matrix[(size_t)own * m + other];
+        for (int other = 0; other < m; other++) {
+            t[(size_t)other * m + own] = (R)h->matrix[(size_t)own * m + other];
+            t[(size_t)m * m + (size_t)own * m + other] = (R)h->matrix[(size_t)own * m + other];
+        }
     // pageable source: the copy is staged before the call returns
     CU(h, cudaMemcpyAsync(h->d_matrix_t, t.data(), sizeof(R) * t.size(), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -224,7 +233,14 @@ int sort_current(plife_handle *h, const Grid &g, StepTimer *tm)
     int rc = ensure_cells(h, (int64_t)g.nx * g.ny);
     if (rc) return rc;
     if (tm) CU(h, tm->mark(0));
-    CU(h, launch_bin(h, g));
+    // the previous force pass already binned its output for this grid: skip K_BIN
+    const bool reuse = h->prebinned && h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs;
+    if (!reuse) {
+        if (h->count_dirty) CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)h->cell_cap, h->stream));
+        CU(h, launch_bin(h, g));
+    }
+    h->prebinned = false;
+    h->count_dirty = false; // K_SCAN zeroes the histogram after reading it
     if (tm) CU(h, tm->mark(1));
     CU(h, launch_scan(h, g));
     if (tm) CU(h, tm->mark(2));
@@ -247,6 +263,10 @@ int run_step(plife_handle *h, double dt)
     if (rc) return rc;
     if (h->precision == PLIFE_F32) CU(h, launch_force_f32(h, make_params<float>(h, g, dt)));
     else CU(h, launch_force_f64(h, make_params<double>(h, g, dt)));
+    // the force pass binned the new positions into d_cell / d_count for the same grid
+    h->prebinned = !(h->flags & PLIFE_FLAG_NO_FUSED_BIN);
+    h->prebinned_grid = g;
+    h->count_dirty = h->prebinned;
     if (tm.on) {
         CU(h, tm.mark(PLIFE_K_COUNT));
         h->pending.push_back(tm.t);
@@ -433,6 +453,7 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
     if (rc) return rc;
     h->cur = 0;
     h->has_sorted = false;
+    h->prebinned = false;
     const int64_t chunk = 1 << 20;
     if (h->precision == PLIFE_F32) {
         std::vector<float4> pt((size_t)(n < chunk ? n : chunk));
@@ -545,6 +566,7 @@ int plife_init_uniform(plife_handle *h, int64_t n, uint64_t seed)
     if (rc) return rc;
     h->cur = 0;
     h->has_sorted = false;
+    h->prebinned = false;
     h->n = n;
     CU(h, launch_init_uniform(h, n, seed));
     h->max_type = n > 0 ? h->m - 1 : -1;
@@ -673,6 +695,7 @@ int plife_debug_neighbors(plife_handle *h, int32_t *count, uint64_t *hash)
     // like makeContainers, the sort is visible: the sorted copy becomes the current state
     h->cur ^= 1;
     h->has_sorted = false;
+    h->prebinned = false;
     h->last_grid = g;
     return PLIFE_OK;
 }

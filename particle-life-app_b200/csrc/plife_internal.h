@@ -21,6 +21,24 @@ struct Grid {
     double cs;
 };
 
+// Cell coordinates of a position, packed cx | cy << 16.  cx = (int)(x / containerSize) in fp64 is
+// both the un-clamped cx0 of the force pass (B/Physics.java:404, floor == truncation for x >= 0) and,
+// after the `== nx -> nx-1` clamp, the container of the sort (:362-375).  nx <= 16384 (kMaxCells),
+// so cx in [0, nx] fits 15 bits.
+__host__ __device__ inline int cell_coords(double x, double y, const Grid &g)
+{
+    int cx = (int)(x / g.cs);
+    int cy = (int)(y / g.cs);
+    return cx | (cy << 16);
+}
+__host__ __device__ inline int container_of(int cxy, const Grid &g)
+{
+    int cx = cxy & 0xffff, cy = cxy >> 16;
+    if (cx == g.nx) cx = g.nx - 1; // for solid borders, :367-372
+    if (cy == g.ny) cy = g.ny - 1;
+    return cx + cy * g.nx;
+}
+
 // Kernel parameters of the force/integrate pass for one step, in the
 // arithmetic type R of the handle.
 template <typename R>
@@ -83,7 +101,8 @@ struct plife_handle {
     int cur = 0; // index of the buffer holding the current state
     plife::StateF32 s32[2]{};
     plife::StateF64 s64[2]{};
-    int32_t *d_cell = nullptr; // cell of particle i (pre-sort order)
+    int32_t *d_cell = nullptr;        // packed cell coords of particle i (pre-sort order)
+    int32_t *d_cell_sorted = nullptr; // the same, permuted into sorted order
     int32_t *d_perm = nullptr; // source index of sorted slot d
     void *d_snap = nullptr;    // snapshot staging (download_f32)
     int64_t snap_cap = 0;
@@ -96,6 +115,9 @@ struct plife_handle {
     unsigned long long *d_scalar = nullptr; // small device scratch (counters)
 
     plife::Grid last_grid{0, 0, 0.0};
+    bool prebinned = false;   // d_cell / d_count already hold the binning of the current state (fused into the last force pass)
+    plife::Grid prebinned_grid{0, 0, 0.0};
+    bool count_dirty = false; // d_count is not all-zero
     bool has_sorted = false; // buffer cur^1 holds the sorted pre-step state of the last step
     int64_t steps = 0;
 

@@ -24,5 +24,7 @@ if __name__ == "__main__":
     names = sys.argv[1:] or ["C1", "C2", "C3", "C3lo", "C5"]
     for nme in names:
         run(nme)
-    run("C3", precision=plife.F64, steps=5)
-    run("C3", flags=plife.FLAG_UNSTABLE_SORT)
+    if not sys.argv[1:]:
+        run("C3", precision=plife.F64, steps=5)
+        run("C3", flags=plife.FLAG_UNSTABLE_SORT)
+        run("C3", flags=4)
