@@ -1,0 +1,161 @@
+package com.particle_life.backend;
+
+import java.lang.foreign.*;
+import java.lang.invoke.MethodHandle;
+
+import org.joml.Vector3d;
+
+/**
+ * Drop-in replacement for {@link Physics} that runs {@code update()} on a B200 through libplife.so.
+ *
+ * <p>UNBUILT / UNTESTED in the build environment (no JVM there; SURVEY.md F7/F8).  It targets the
+ * Java FFM API (final in JDK 22; on the app's JDK 21 toolchain compile with {@code --enable-preview}
+ * or use the JNI variant sketched in INTEGRATION.md).  It binds exactly the {@code plife_*}
+ * symbols of include/plife.h.
+ *
+ * <p>Usage in {@code Main.createPhysics()} (A/Main.java:281-285): construct this class instead of
+ * {@code ExtendedPhysics}.  {@code Loop} and everything above stay unchanged: they call
+ * {@code update()}, mutate {@code settings}, and read {@code particles} when a snapshot is due.
+ * The particle buffers live on the GPU; {@link #pull()} refreshes the Java-side array for the
+ * display-time handoff (A/PhysicsSnapshot.java:24-62) and {@link #push()} uploads edits.
+ */
+public class NativePhysics extends Physics {
+
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final SymbolLookup LIB = SymbolLookup.libraryLookup("libplife.so", Arena.global());
+
+    private static MethodHandle fn(String name, FunctionDescriptor d) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(), d);
+    }
+
+    private static final ValueLayout.OfInt I32 = ValueLayout.JAVA_INT;
+    private static final ValueLayout.OfLong I64 = ValueLayout.JAVA_LONG;
+    private static final ValueLayout.OfDouble F64 = ValueLayout.JAVA_DOUBLE;
+    private static final AddressLayout PTR = ValueLayout.ADDRESS;
+
+    private static final MethodHandle CREATE = fn("plife_create", FunctionDescriptor.of(I32, PTR, PTR));
+    private static final MethodHandle DESTROY = fn("plife_destroy", FunctionDescriptor.of(I32, PTR));
+    private static final MethodHandle SET_SETTINGS = fn("plife_set_settings", FunctionDescriptor.of(I32, PTR, PTR));
+    private static final MethodHandle SET_MATRIX = fn("plife_set_matrix", FunctionDescriptor.of(I32, PTR, I32, PTR));
+    private static final MethodHandle SET_ACCELERATOR = fn("plife_set_accelerator", FunctionDescriptor.of(I32, PTR, I32, PTR, I32));
+    private static final MethodHandle UPLOAD = fn("plife_upload", FunctionDescriptor.of(I32, PTR, I64, PTR, PTR, PTR, PTR));
+    private static final MethodHandle DOWNLOAD = fn("plife_download", FunctionDescriptor.of(I32, PTR, PTR, PTR, PTR, PTR));
+    private static final MethodHandle STEP = fn("plife_step", FunctionDescriptor.of(I32, PTR, F64, I32));
+    private static final MethodHandle SYNC = fn("plife_sync", FunctionDescriptor.of(I32, PTR));
+    private static final MethodHandle REQUEST_STOP = fn("plife_request_stop", FunctionDescriptor.of(I32, PTR));
+    private static final MethodHandle LAST_ERROR = fn("plife_last_error", FunctionDescriptor.of(PTR, PTR));
+
+    /** struct plife_config { int32 device, precision; int64 capacity; int32 flags, reserved; void* stream; } */
+    private static final MemoryLayout CONFIG = MemoryLayout.structLayout(I32.withName("device"), I32.withName("precision"),
+            I64.withName("capacity"), I32.withName("flags"), I32.withName("reserved"), PTR.withName("stream"));
+    /** struct plife_settings { double rmax, friction, force; int32 wrap, reserved; } */
+    private static final MemoryLayout SETTINGS = MemoryLayout.structLayout(F64.withName("rmax"), F64.withName("friction"),
+            F64.withName("force"), I32.withName("wrap"), I32.withName("reserved"));
+
+    private final Arena arena = Arena.ofShared();
+    private MemorySegment handle;
+    private boolean dirty = true; // Java-side particles changed since the last upload
+
+    public NativePhysics(Accelerator accelerator, PositionSetter positionSetter, MatrixGenerator matrixGenerator,
+                         TypeSetter typeSetter) {
+        super(accelerator, positionSetter, matrixGenerator, typeSetter); // generates matrix + 10000 particles on the host
+        try {
+            MemorySegment cfg = arena.allocate(CONFIG);
+            cfg.set(I32, 0, 0);   // device 0
+            cfg.set(I32, 4, 0);   // PLIFE_F32
+            cfg.set(I64, 8, particles.length);
+            MemorySegment out = arena.allocate(PTR);
+            check((int) CREATE.invoke(cfg, out));
+            handle = out.get(PTR, 0);
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+    }
+
+    /** Physics.update() (B/Physics.java:112): settings -> device, one step on the GPU. */
+    @Override
+    public void update() {
+        try {
+            pushSettings();
+            if (dirty) push();
+            check((int) STEP.invoke(handle, settings.dt, 1));
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+    }
+
+    private void pushSettings() throws Throwable {
+        MemorySegment s = arena.allocate(SETTINGS);
+        s.set(F64, 0, settings.rmax);
+        s.set(F64, 8, settings.friction);
+        s.set(F64, 16, settings.force);
+        s.set(I32, 24, settings.wrap ? 1 : 0);
+        check((int) SET_SETTINGS.invoke(handle, s));
+        int m = settings.matrix.size();
+        MemorySegment mat = arena.allocate(F64, (long) m * m);
+        for (int i = 0; i < m; i++)
+            for (int j = 0; j < m; j++) mat.setAtIndex(F64, (long) i * m + j, settings.matrix.get(i, j));
+        check((int) SET_MATRIX.invoke(handle, m, mat));
+        // a Java lambda cannot run on the device: kind 0 is the accelerator of A/Main.java:275-280
+        check((int) SET_ACCELERATOR.invoke(handle, 0, MemorySegment.NULL, 0));
+    }
+
+    /** Upload the Java-side particle array (after setParticleCount / cursor edits / load). */
+    public void push() throws Throwable {
+        int n = particles.length;
+        MemorySegment pos = arena.allocate(F64, 2L * n), vel = arena.allocate(F64, 2L * n), typ = arena.allocate(I32, n);
+        for (int i = 0; i < n; i++) {
+            Particle p = particles[i];
+            pos.setAtIndex(F64, 2L * i, p.position.x);
+            pos.setAtIndex(F64, 2L * i + 1, p.position.y);
+            vel.setAtIndex(F64, 2L * i, p.velocity.x);
+            vel.setAtIndex(F64, 2L * i + 1, p.velocity.y);
+            typ.setAtIndex(I32, i, p.type);
+        }
+        check((int) UPLOAD.invoke(handle, (long) n, pos, vel, typ, MemorySegment.NULL));
+        dirty = false;
+    }
+
+    /** Display-time handoff: refresh the Java-side particles from the GPU (cell-sorted order, like the reference). */
+    public void pull() throws Throwable {
+        int n = particles.length;
+        MemorySegment pos = arena.allocate(F64, 2L * n), vel = arena.allocate(F64, 2L * n), typ = arena.allocate(I32, n);
+        check((int) DOWNLOAD.invoke(handle, pos, vel, typ, MemorySegment.NULL));
+        for (int i = 0; i < n; i++) {
+            Particle p = particles[i];
+            p.position.set(pos.getAtIndex(F64, 2L * i), pos.getAtIndex(F64, 2L * i + 1), 0);
+            p.velocity.set(vel.getAtIndex(F64, 2L * i), vel.getAtIndex(F64, 2L * i + 1), 0);
+            p.type = typ.getAtIndex(I32, i);
+        }
+    }
+
+    /** Call after any Java-side mutation of {@code particles} (A/Main.java:536-582, :671, :1320). */
+    public void markDirty() {
+        dirty = true;
+    }
+
+    @Override
+    public void forceUpdateStop() {
+        try {
+            REQUEST_STOP.invoke(handle);
+        } catch (Throwable ignored) {
+        }
+    }
+
+    @Override
+    public void kill() {
+        try {
+            if (handle != null) DESTROY.invoke(handle);
+            handle = null;
+        } catch (Throwable ignored) {
+        }
+        super.kill();
+    }
+
+    private void check(int status) throws Throwable {
+        if (status != 0) {
+            MemorySegment msg = ((MemorySegment) LAST_ERROR.invoke(handle)).reinterpret(512);
+            throw new RuntimeException("plife status " + status + ": " + msg.getString(0));
+        }
+    }
+}
