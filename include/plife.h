@@ -181,6 +181,31 @@ int plife_kernel_times(plife_handle *h, double *ms_out, int64_t *launches_out);
  * F64: pos = double2[n], vel = double2[n], type = int32[n], id = uint32[n] */
 int plife_device_ptrs(plife_handle *h, void **pos, void **vel, void **type, void **id);
 
+/* ---- multi-GPU slab decomposition (one process per GPU) ----
+ * Rank g owns grid rows [g*ny/G, (g+1)*ny/G).  The library packs / unpacks the halo and migration
+ * messages; the host exchanges them between the phases (NCCL send/recv, e.g. torch.distributed):
+ *   halo_send[0] -> down neighbour's halo_recv[1],  halo_send[1] -> up neighbour's halo_recv[0]
+ *   mig_send[0]  -> down neighbour's mig_recv[1],   mig_send[1]  -> up neighbour's mig_recv[0]
+ * (down = rank-1, up = rank+1, periodic when wrap is on; no exchange across a closed boundary).
+ * Buffers are device memory owned by the caller, in 16-byte records:
+ * plife_slab_halo_records(nx, halo_cap) / plife_slab_migrate_records(mig_cap) records each.
+ * fp32 handles only.  Upload only particles of the rank's own rows (others are dropped). */
+typedef struct plife_slab_buffers {
+    void *halo_send[2], *halo_recv[2], *mig_send[2], *mig_recv[2];
+} plife_slab_buffers;
+
+#define PLIFE_SLAB_SORT 0   /* cell-list build of the owned particles + pack halo rows */
+#define PLIFE_SLAB_FORCE 1  /* place ghost rows, force + integrate, pack leavers */
+#define PLIFE_SLAB_FINISH 2 /* append arrivals; synchronises; updates plife_count() */
+
+int64_t plife_slab_halo_records(int32_t nx, int64_t halo_cap);
+int64_t plife_slab_migrate_records(int64_t mig_cap);
+int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t halo_cap, int64_t mig_cap,
+                         const plife_slab_buffers *bufs);
+/* rows [row_lo, row_hi) owned by this rank under the current settings, and nx */
+int plife_slab_rows(plife_handle *h, int32_t *row_lo, int32_t *row_hi, int32_t *nx);
+int plife_slab_phase(plife_handle *h, int32_t phase, double dt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,8 +26,9 @@ __global__ void __launch_bounds__(kThreads) bin_f32(const float4 *__restrict__ p
     if (i >= n) return;
     float4 p = __ldg(&pt[i]);
     int cxy = cell_coords((double)p.x, (double)p.y, g);
-    cell[i] = cxy;
-    atomicAdd(&count[container_of(cxy, g)], 1);
+    int c = container_of(cxy, g);
+    cell[i] = c < 0 ? -1 : cxy; // slab mode: uploads hold owned particles only; anything else is dropped
+    if (c >= 0) atomicAdd(&count[c], 1);
 }
 
 __global__ void __launch_bounds__(kThreads) bin_f64(const double2 *__restrict__ pos, int n, Grid g,
@@ -101,10 +102,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *__
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) scan_sums(int32_t *__restrict__ tile_sums, int ntiles)
+__global__ void __launch_bounds__(1024) scan_sums(int32_t *__restrict__ tile_sums, int ntiles, int carry0,
+                                                  int32_t *__restrict__ cell_end)
 {
     __shared__ int sm[33];
-    int carry = 0;
+    int carry = carry0;
+    if (threadIdx.x == 0) cell_end[-1] = carry0; // start of local cell 0
     for (int base = 0; base < ntiles; base += 1024) {
         int i = base + threadIdx.x;
         int v = i < ntiles ? tile_sums[i] : 0;
@@ -171,31 +174,51 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
 
 // B/Physics.java:343-348: `i = containers[ci]; buffer[i] = p; containers[ci]++`.
 // Afterwards cell_end[ci] is the END offset of cell ci, as in the reference.
-__global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n, Grid g,
+__global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n_phys, Grid g, int first,
                                                          int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
 {
     int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n_phys) return;
     int c = container_of(__ldg(&cell[i]), g);
+    if (c < 0) return; // dead slot: the particle migrated to another slab
     int dst = atomicAdd(&cell_end[c], 1);
-    perm[dst] = i;
+    perm[dst - first] = i;
 }
 
+// Logical position of pre-sort slot `src`.  Single GPU: the identity.  Slab mode: the pre-sort array is
+// physically [residents 0..n_old) | arrivals from below (k_below) | arrivals from above]; the key puts the
+// three groups in the order of their previous GLOBAL array index, which is what the reference's stable
+// sort preserves: below < residents < above, except across the periodic seam, where rank 0's arrivals
+// from "below" come from the END of the global array and the last rank's arrivals from "above" from its
+// beginning (launch_gather picks the bases).
+struct StableKey {
+    int n_old, k_below;
+    int base_res, base_below, base_above;
+    __device__ __forceinline__ int operator()(int src) const
+    {
+        if (src < n_old) return src + base_res;
+        src -= n_old;
+        return src < k_below ? src + base_below : src - k_below + base_above;
+    }
+};
+
 __device__ __forceinline__ int stable_slot(int src, int c, const int32_t *__restrict__ cell_end,
-                                           const int32_t *__restrict__ perm)
+                                           const int32_t *__restrict__ perm, int first, StableKey key)
 {
-    int s = c == 0 ? 0 : __ldg(&cell_end[c - 1]);
+    int s = __ldg(&cell_end[c - 1]);
     int e = __ldg(&cell_end[c]);
     int rank = 0;
-    for (int k = s; k < e; k++) rank += (__ldg(&perm[k]) < src) ? 1 : 0;
+    const int ksrc = key(src);
+    for (int k = s; k < e; k++) rank += (key(__ldg(&perm[k - first])) < ksrc) ? 1 : 0;
     return s + rank;
 }
 
 template <bool STABLE>
 __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, const float2 *__restrict__ vel_in,
                                                        float4 *__restrict__ pt_out, float2 *__restrict__ vel_out, int n, Grid g,
-                                                       const int32_t *__restrict__ cell, int32_t *__restrict__ cell_sorted,
-                                                       const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm)
+                                                       int first, StableKey key, const int32_t *__restrict__ cell,
+                                                       int32_t *__restrict__ cell_sorted, const int32_t *__restrict__ cell_end,
+                                                       const int32_t *__restrict__ perm)
 {
     int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= n) return;
@@ -203,10 +226,10 @@ __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict_
     float4 p = __ldg(&pt_in[src]);
     float2 v = __ldg(&vel_in[src]);
     int cxy = __ldg(&cell[src]);
-    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm) : d;
-    pt_out[dst] = p;
-    vel_out[dst] = v;
-    cell_sorted[dst] = cxy;
+    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm, first, key) : d + first;
+    pt_out[dst] = p; // sorted positions carry the ghost-below offset `first`; per-target arrays do not
+    vel_out[dst - first] = v;
+    cell_sorted[dst - first] = cxy;
 }
 
 template <bool STABLE>
@@ -222,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out
     int t = __ldg(&in.type[src]);
     uint32_t id = __ldg(&in.id[src]);
     int cxy = __ldg(&cell[src]);
-    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm) : d;
+    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm, 0, StableKey{0x7fffffff, 0, 0, 0, 0}) : d;
     cell_sorted[dst] = cxy;
     out.pos[dst] = p;
     out.vel[dst] = v;
@@ -281,6 +304,22 @@ __global__ void __launch_bounds__(kThreads) init_uniform_f32(float4 *pt, float2 
     vel[i] = make_float2(0.f, 0.f);
 }
 
+// slab mode: every rank scans the global stream and keeps the particles of its own rows
+__global__ void __launch_bounds__(kThreads) init_uniform_owned_f32(float4 *pt, float2 *vel, long long n_global, int m,
+                                                                   uint64_t seed, Grid g, int cap, int *counter)
+{
+    long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n_global) return;
+    uint64_t c = 4ull * (uint64_t)i;
+    float x = (float)splitmix_u01(seed, c), y = (float)splitmix_u01(seed, c + 1);
+    if (container_of(cell_coords((double)x, (double)y, g), g) < 0) return;
+    int t = min((int)floor(splitmix_u01(seed, c + 2) * m), m - 1);
+    int k = atomicAdd(counter, 1);
+    if (k >= cap) return;
+    pt[k] = make_float4(x, y, __int_as_float(t), __uint_as_float((uint32_t)i));
+    vel[k] = make_float2(0.f, 0.f);
+}
+
 __global__ void __launch_bounds__(kThreads) init_uniform_f64(StateF64 s, int n, int m, uint64_t seed)
 {
     int i = blockIdx.x * kThreads + threadIdx.x;
@@ -320,12 +359,13 @@ __global__ void __launch_bounds__(kThreads) snapshot_from_f64(StateF64 s, int n,
 }
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+inline int first_index(const plife_handle *h) { return h->slab.on ? (int)h->slab.halo_cap : 0; }
 
 } // namespace
 
 cudaError_t launch_bin(plife_handle *h, const Grid &g)
 {
-    int n = (int)h->n;
+    int n = (int)h->n_phys;
     if (n == 0) return cudaSuccess;
     if (h->precision == PLIFE_F32)
         bin_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, n, g, h->d_cell, h->d_count);
@@ -336,19 +376,19 @@ cudaError_t launch_bin(plife_handle *h, const Grid &g)
 
 cudaError_t launch_scan(plife_handle *h, const Grid &g)
 {
-    int64_t ncell = (int64_t)g.nx * g.ny;
+    int64_t ncell = (int64_t)g.nx * g.nly;
     int ntiles = (int)((ncell + kScanTile - 1) / kScanTile);
     scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, h->d_tile_sums);
-    scan_sums<<<1, 1024, 0, h->stream>>>(h->d_tile_sums, ntiles);
+    scan_sums<<<1, 1024, 0, h->stream>>>(h->d_tile_sums, ntiles, first_index(h), h->d_cell_end);
     scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, h->d_tile_sums, h->d_cell_end);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scatter(plife_handle *h, const Grid &g)
 {
-    int n = (int)h->n;
+    int n = (int)h->n_phys; // physical pre-sort length (dead slots included)
     if (n == 0) return cudaSuccess;
-    scatter_perm<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, h->d_cell_end, h->d_perm);
+    scatter_perm<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
     return cudaGetLastError();
 }
 
@@ -359,13 +399,22 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
     int a = h->cur, b = h->cur ^ 1;
     bool stable = !(h->flags & PLIFE_FLAG_UNSTABLE_SORT);
     int nb = blocks_for(n, kThreads);
+    StableKey key{0x7fffffff, 0, 0, 0, 0};
+    if (h->slab.on) {
+        const SlabState &S = h->slab;
+        const int no = (int)S.n_old, kb = (int)S.k_below, ka = (int)S.k_above;
+        const bool wrap = h->settings.wrap != 0 && S.world > 1;
+        if (wrap && S.rank == 0 && S.world > 1 && S.rank != S.world - 1) key = StableKey{no, kb, 0, no + ka, no}; // residents, above, below(seam)
+        else if (wrap && S.rank == S.world - 1) key = StableKey{no, kb, ka + kb, ka, 0};                          // above(seam), below, residents
+        else key = StableKey{no, kb, kb, 0, kb + no};                                                             // below, residents, above
+    }
     if (h->precision == PLIFE_F32) {
         if (stable)
             gather_f32<true><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
-                                                             h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
+                                                             first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
         else
             gather_f32<false><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
-                                                              h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
+                                                              first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
     } else {
         if (stable)
             gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
@@ -396,6 +445,14 @@ cudaError_t launch_init_uniform(plife_handle *h, int64_t n64, uint64_t seed)
         init_uniform_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, n, h->m, seed);
     else
         init_uniform_f64<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s64[h->cur], n, h->m, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init_uniform_owned(plife_handle *h, int64_t n_global, uint64_t seed, const Grid &g, int *d_counter)
+{
+    if (n_global == 0) return cudaSuccess;
+    init_uniform_owned_f32<<<blocks_for(n_global, kThreads), kThreads, 0, h->stream>>>(
+        h->s32[h->cur].pt, h->s32[h->cur].vel, (long long)n_global, h->m, seed, g, (int)h->cap, d_counter);
     return cudaGetLastError();
 }
 

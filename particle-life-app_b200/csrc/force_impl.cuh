@@ -150,8 +150,8 @@ __device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict
     if (interior) {
 #pragma unroll 1
         for (int oy = -1; oy <= 1; ++oy) {
-            const int base = (cy0 + oy) * g.nx + cx0;
-            const int s = base >= 2 ? __ldg(cell_end + base - 2) : 0;
+            const int base = (cy0 + g.ly_shift + oy) * g.nx + cx0; // local cell of (cx0, cy0 + oy)
+            const int s = __ldg(cell_end + base - 2);               // cell_end[-1] is valid
             const int e = __ldg(cell_end + base + 1);
 #pragma unroll 4
             for (int j = s; j < e; ++j) {
@@ -171,9 +171,9 @@ __device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict
             } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
                 continue; // :414-416
             }
-            const int ci = cx + cy * g.nx;                        // :418
-            const int s = ci == 0 ? 0 : __ldg(cell_end + ci - 1); // :420
-            const int e = __ldg(cell_end + ci);                   // :421
+            const int ci = cx + local_row(cy, g) * g.nx; // :418 (local cell index)
+            const int s = __ldg(cell_end + ci - 1);      // :420
+            const int e = __ldg(cell_end + ci);          // :421
             for (int j = s; j < e; ++j) {
                 if (j == i) continue; // :424
                 Cand<R> q = io.cand(j);
@@ -358,16 +358,44 @@ struct PairCountVisitor {
 
 // Fused K_BIN of the NEXT step: the integrate epilogue knows the new position, so it bins it
 // (B/Physics.java:329-332 of the next update()) and saves a pass over the particle array.
+// Slab mode: a particle whose new row belongs to another rank is appended to the migration
+// message of that direction (two 16-byte records: {x,y,type,id}, {vx,vy,source slot,-}) and its
+// slot is marked dead; record 0 of a message is the header {count, far, -, -}.
 struct NextBin {
     int32_t *cell;  // packed cell coords per particle, or nullptr: do not bin
     int32_t *count; // per-cell histogram (zeroed by K_SCAN of this step)
+    float4 *mig[2]; // migration messages [down, up] (slab mode) or nullptr
+    int mig_cap;
     template <typename R>
-    __device__ __forceinline__ void add(int i, R x, R y, const Grid &g) const
+    __device__ __forceinline__ void add(int i, R x, R y, R vx, R vy, int type, uint32_t id, const Grid &g) const
     {
-        if (cell) {
-            const int cxy = cell_coords((double)x, (double)y, g);
+        if (!cell) return;
+        const int cxy = cell_coords((double)x, (double)y, g);
+        const int c = container_of(cxy, g);
+        if (c >= 0) {
             cell[i] = cxy;
-            atomicAdd(count + container_of(cxy, g), 1);
+            atomicAdd(count + c, 1);
+            return;
+        }
+        cell[i] = -1; // leaves this slab
+        if (!mig[0]) return;
+        int cy = cxy >> 16;
+        if (cy == g.ny) cy = g.ny - 1;
+        int du = cy - g.row_hi; // rows above the slab (ring distance)
+        if (du < 0) du += g.ny;
+        int dd = g.row_lo - 1 - cy; // rows below the slab
+        if (dd < 0) dd += g.ny;
+        const int dir = du <= dd ? 1 : 0;
+        const bool far = dir ? du >= g.rows_up : dd >= g.rows_dn;
+        int *hdr = reinterpret_cast<int *>(mig[dir]);
+        if (far) {
+            atomicAdd(hdr + 1, 1); // more than one slab in one step: reported as PLIFE_ERR_STATE
+            return;
+        }
+        const int k = atomicAdd(hdr, 1);
+        if (k < mig_cap) {
+            mig[dir][1 + 2 * k] = make_float4((float)x, (float)y, __int_as_float(type), __uint_as_float(id));
+            mig[dir][2 + 2 * k] = make_float4((float)vx, (float)vy, __int_as_float(i), 0.f);
         }
     }
 };
@@ -394,7 +422,8 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
 
     const int i = blockIdx.x * kForceThreads + threadIdx.x;
     if (i >= P.n) return;
-    const Cand<R> self = io.cand(i);
+    const int si = P.first + i;
+    const Cand<R> self = io.cand(si);
     const int cxy = __ldg(cell_sorted + i);
     R vx, vy;
     io.self_vel(i, vx, vy);
@@ -405,12 +434,12 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
     R nvx, nvy;
     if constexpr (FAST) {
         FastParticleLife32<MODE> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
-        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, cxy, v);
+        traverse(io, cell_end, P.g, P.wrap, si, self.x, self.y, cxy, v);
         nvx = fmaf(P.fast_k, v.ax, vx * P.mu); // friction first (:401-402), then the summed acceleration
         nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
     } else {
         LiteralForce<R, KIND, MODE> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
-        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, cxy, v);
+        traverse(io, cell_end, P.g, P.wrap, si, self.x, self.y, cxy, v);
         v.finish(nvx, nvy);
     }
     // updatePosition (:443-450): pos = vel*dt + pos, then wrap or clamp (:499-505)
@@ -424,7 +453,7 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
         ny_ = range_clamp(ny_);
     }
     io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
-    nb.add(i, nx_, ny_, P.g);
+    nb.add(i, nx_, ny_, nvx, nvy, self.type, self.id, P.g);
 }
 
 // ---- v2: shared-memory staged candidates (fp32) ------------------------------------------
@@ -461,11 +490,11 @@ __device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *
     const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
     const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
     if (interior && staged_ok) {
-        const int base0 = (cy0 - 1) * g.nx + cx0;
+        const int base0 = (cy0 + g.ly_shift - 1) * g.nx + cx0;
 #pragma unroll 1
         for (int r = 0; r < 3; ++r) {
             const int base = base0 + r * g.nx;
-            const int s = base >= 2 ? __ldg(cell_end + base - 2) : 0;
+            const int s = __ldg(cell_end + base - 2);
             const int e = __ldg(cell_end + base + 1);
             uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s - s_start[r]) * 16u;
             const uint32_t a1 = a + (uint32_t)(e - s) * 16u;
@@ -489,8 +518,8 @@ __device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *
             } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
                 continue;
             }
-            const int ci = cx + cy * g.nx;
-            const int s = ci == 0 ? 0 : __ldg(cell_end + ci - 1);
+            const int ci = cx + local_row(cy, g) * g.nx;
+            const int s = __ldg(cell_end + ci - 1);
             const int e = __ldg(cell_end + ci);
             for (int j = s; j < e; ++j) {
                 if (j == i) continue;
@@ -529,8 +558,9 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_staged(IOF32 io, c
     const Grid g = P.g;
     Cand<float> self{0.f, 0.f, 0, 0u};
     int cxy = 0;
+    const int si = P.first + i; // index of this target in the sorted array (ghost rows precede it in slab mode)
     if (valid) {
-        self = io.cand(i);
+        self = io.cand(si);
         cxy = __ldg(cell_sorted + i);
         if (tid == 0) s_cell[0] = container_of(cxy, g);
         if (tid == kForceThreads - 1 || i == P.n - 1) s_cell[1] = container_of(cxy, g);
@@ -553,14 +583,14 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_staged(IOF32 io, c
     }
     __syncthreads();
     if (tid < 3) {
-        const int ncell = g.nx * g.ny;
+        const int ncell = g.nx * g.nly;
         int lo = s_cell[0] + (tid - 1) * g.nx - 1;
         int hi = s_cell[1] + (tid - 1) * g.nx + 1;
         lo = max(lo, 0);
         hi = min(hi, ncell - 1);
         int start = 0, len = 0;
         if (lo <= hi) {
-            start = lo > 0 ? __ldg(cell_end + lo - 1) : 0;
+            start = __ldg(cell_end + lo - 1);
             len = __ldg(cell_end + hi) - start;
         }
         s_start[tid] = start;
@@ -595,12 +625,12 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_staged(IOF32 io, c
     float nvx, nvy;
     if constexpr (FAST) {
         FastParticleLife32<kMatLaneTab> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
-        traverse_staged(io, cell_end, g, P.wrap, i, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
+        traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
         nvx = fmaf(P.fast_k, v.ax, vx * P.mu);
         nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
     } else {
         LiteralForce<float, KIND, kMatLaneTab> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
-        traverse_staged(io, cell_end, g, P.wrap, i, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
+        traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
         v.finish(nvx, nvy);
     }
     float nx_ = fmaf(nvx, P.dt, self.x);
@@ -613,7 +643,7 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_staged(IOF32 io, c
         ny_ = range_clamp(ny_);
     }
     io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
-    nb.add(i, nx_, ny_, g);
+    nb.add(i, nx_, ny_, nvx, nvy, self.type, self.id, g);
 }
 
 inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted,
@@ -654,9 +684,9 @@ __global__ void __launch_bounds__(kForceThreads) neighbors_kernel(IO io, const i
     using R = typename IO::R;
     const int i = blockIdx.x * kForceThreads + threadIdx.x;
     if (i >= P.n) return;
-    const Cand<R> self = io.cand(i);
+    const Cand<R> self = io.cand(P.first + i);
     NeighborVisitor<R> v{{0, 0ull}, P.r2};
-    traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, __ldg(cell_sorted + i), v);
+    traverse(io, cell_end, P.g, P.wrap, P.first + i, self.x, self.y, __ldg(cell_sorted + i), v);
     cnt[i] = v.d.count;
     hash[i] = v.d.hash;
 }
@@ -672,9 +702,9 @@ __global__ void __launch_bounds__(kForceThreads) pair_count_kernel(IO io, const 
     const int i = blockIdx.x * kForceThreads + threadIdx.x;
     unsigned long long c = 0;
     if (i < P.n) {
-        const Cand<R> self = io.cand(i);
-        PairCountVisitor<R> v{i, 0ull};
-        traverse(io, cell_end, P.g, P.wrap, i, self.x, self.y, __ldg(cell_sorted + i), v);
+        const Cand<R> self = io.cand(P.first + i);
+        PairCountVisitor<R> v{P.first + i, 0ull};
+        traverse(io, cell_end, P.g, P.wrap, P.first + i, self.x, self.y, __ldg(cell_sorted + i), v);
         c = v.count;
     }
 #pragma unroll

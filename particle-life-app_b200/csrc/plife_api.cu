@@ -84,7 +84,8 @@ int ensure_capacity(plife_handle *h, int64_t n)
     size_t c = (size_t)n;
     for (int b = 0; b < 2; b++) {
         if (h->precision == PLIFE_F32) {
-            CU(h, dev_alloc(&h->s32[b].pt, c));
+            // slab mode: the sorted array is [ghost row below | owned | ghost row above]
+            CU(h, dev_alloc(&h->s32[b].pt, c + (h->slab.on ? 2 * (size_t)h->slab.halo_cap : 0)));
             CU(h, dev_alloc(&h->s32[b].vel, c));
         } else {
             CU(h, dev_alloc(&h->s64[b].pos, c));
@@ -107,13 +108,17 @@ int ensure_cells(plife_handle *h, int64_t ncell)
 {
     if (ncell <= h->cell_cap) return PLIFE_OK;
     cudaFree(h->d_count);
-    cudaFree(h->d_cell_end);
+    if (h->d_cell_end) cudaFree(h->d_cell_end - 4);
     cudaFree(h->d_tile_sums);
     h->d_count = h->d_cell_end = h->d_tile_sums = nullptr;
     h->cell_cap = 0;
     int64_t padded = (ncell + kScanTile - 1) / kScanTile * kScanTile;
     CU(h, dev_alloc(&h->d_count, (size_t)padded));
-    CU(h, dev_alloc(&h->d_cell_end, (size_t)padded));
+    // 4 leading ints: cell_end[-1] (the start of local cell 0) is a valid entry and int4 stores stay aligned
+    int32_t *raw = nullptr;
+    CU(h, dev_alloc(&raw, (size_t)padded + 4));
+    CU(h, cudaMemsetAsync(raw, 0, 16, h->stream));
+    h->d_cell_end = raw + 4;
     CU(h, dev_alloc(&h->d_tile_sums, (size_t)(padded / kScanTile)));
     CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)padded, h->stream));
     h->cell_cap = padded;
@@ -132,6 +137,23 @@ int make_grid(plife_handle *h, Grid *g)
     g->nx = nx;
     g->ny = nx;
     g->cs = rmax;
+    g->row_lo = 0;
+    g->row_hi = nx;
+    g->ly_shift = 0;
+    g->nly = nx;
+    g->rows_up = g->rows_dn = 0;
+    if (h->slab.on) {
+        const int G = h->slab.world, r = h->slab.rank, ny = g->ny;
+        if (ny < 4 * G) return fail(h, PLIFE_ERR_INVALID, "slab mode needs ny >= 4*world (ny=%d, world=%d)", ny, G);
+        auto lo = [&](int k) { return (int)((int64_t)k * ny / G); };
+        g->row_lo = lo(r);
+        g->row_hi = lo(r + 1);
+        g->ly_shift = 1 - g->row_lo;
+        g->nly = g->row_hi - g->row_lo + 2;
+        const int up = (r + 1) % G, dn = (r + G - 1) % G;
+        g->rows_up = lo(up + 1) - lo(up);
+        g->rows_dn = lo(dn + 1) - lo(dn);
+    }
     return PLIFE_OK;
 }
 
@@ -173,6 +195,7 @@ ForceParams<R> make_params(const plife_handle *h, const Grid &g, double dt)
     ForceParams<R> p{};
     p.n = (int)h->n;
     p.m = h->m;
+    p.first = h->slab.on ? (int)h->slab.halo_cap : 0;
     p.g = g;
     p.wrap = s.wrap ? 1 : 0;
     p.use_smem_matrix = h->m <= 64 ? 1 : 0;
@@ -230,11 +253,12 @@ int resolve_timings(plife_handle *h)
 // makeContainers (B/Physics.java:309-354): state buffer cur -> sorted into cur^1
 int sort_current(plife_handle *h, const Grid &g, StepTimer *tm)
 {
-    int rc = ensure_cells(h, (int64_t)g.nx * g.ny);
+    int rc = ensure_cells(h, (int64_t)g.nx * g.nly);
     if (rc) return rc;
     if (tm) CU(h, tm->mark(0));
     // the previous force pass already binned its output for this grid: skip K_BIN
-    const bool reuse = h->prebinned && h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs;
+    const bool reuse = h->prebinned && h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs &&
+                       h->prebinned_grid.row_lo == g.row_lo && h->prebinned_grid.row_hi == g.row_hi;
     if (!reuse) {
         if (h->count_dirty) CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)h->cell_cap, h->stream));
         CU(h, launch_bin(h, g));
@@ -275,6 +299,7 @@ int run_step(plife_handle *h, double dt)
             if (rc) return rc;
         }
     }
+    h->n_phys = h->n;
     h->last_grid = g;
     h->has_sorted = true;
     h->steps++;
@@ -292,6 +317,27 @@ int valid_settings(plife_handle *h, const plife_settings *s)
 }
 
 } // namespace
+
+namespace plife {
+int slab_make_grid(plife_handle *h, Grid *g) { return make_grid(h, g); }
+int slab_fail(plife_handle *h, int code, const char *msg) { return fail(h, code, "%s", msg); }
+int slab_sort(plife_handle *h, const Grid &g)
+{
+    int rc = sync_matrix(h);
+    if (rc) return rc;
+    return sort_current(h, g, nullptr);
+}
+cudaError_t slab_force(plife_handle *h, const Grid &g, double dt)
+{
+    cudaError_t e = launch_force_f32(h, make_params<float>(h, g, dt));
+    h->prebinned = true; // the epilogue binned the stayers; arrivals are binned by phase FINISH
+    h->prebinned_grid = g;
+    h->count_dirty = true;
+    h->last_grid = g;
+    h->has_sorted = true;
+    return e;
+}
+} // namespace plife
 
 extern "C" {
 
@@ -342,6 +388,8 @@ int plife_create(const plife_config *cfg, plife_handle **out)
         delete h;
         return PLIFE_ERR_OOM;
     }
+    cudaMemset(h->d_scalar, 0, 8 * sizeof(unsigned long long));
+    h->capacity_hint = cfg->capacity;
     if (cfg->capacity > 0) {
         int rc = ensure_capacity(h, cfg->capacity);
         if (rc) {
@@ -362,7 +410,7 @@ int plife_destroy(plife_handle *h)
         for (int k = 0; k <= PLIFE_K_COUNT; k++) cudaEventDestroy(p.ev[k]);
     free_state(h);
     cudaFree(h->d_count);
-    cudaFree(h->d_cell_end);
+    if (h->d_cell_end) cudaFree(h->d_cell_end - 4);
     cudaFree(h->d_tile_sums);
     cudaFree(h->d_matrix_t);
     cudaFree(h->d_snap);
@@ -449,7 +497,7 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
         if (t < 0 || t >= h->m) return fail(h, PLIFE_ERR_INVALID, "upload: particle %lld type %d outside [0,%d)", (long long)i, t, h->m);
         if (t > max_type) max_type = t;
     }
-    int rc = ensure_capacity(h, n);
+    int rc = ensure_capacity(h, h->slab.on && h->capacity_hint > n ? h->capacity_hint : n);
     if (rc) return rc;
     h->cur = 0;
     h->has_sorted = false;
@@ -493,6 +541,9 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
         }
     }
     h->n = n;
+    h->n_phys = n;
+    h->slab.n_old = n;
+    h->slab.k_below = h->slab.k_above = 0;
     h->max_type = max_type;
     return PLIFE_OK;
 }
@@ -500,19 +551,26 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
 int plife_download(plife_handle *h, double *pos_xy, double *vel_xy, int32_t *type, uint32_t *id)
 {
     CHECK_HANDLE(h);
-    int64_t n = h->n;
+    int64_t n = h->n_phys;
     CU(h, cudaStreamSynchronize(h->stream));
     if (n == 0) return PLIFE_OK;
+    if (h->slab.on && h->slab.phase != PLIFE_SLAB_SORT) return fail(h, PLIFE_ERR_STATE, "download between slab phases");
     if (h->precision == PLIFE_F32) {
         const int64_t chunk = 1 << 20;
         std::vector<float4> pt((size_t)(n < chunk ? n : chunk));
         std::vector<float2> vl(pt.size());
+        std::vector<int32_t> live;
+        const bool filter = h->slab.on && h->n_phys != h->n; // dead slots of particles that migrated away
+        if (filter) live.resize(pt.size());
+        int64_t o = 0;
         for (int64_t s = 0; s < n; s += chunk) {
             int64_t c = n - s < chunk ? n - s : chunk;
             CU(h, cudaMemcpy(pt.data(), h->s32[h->cur].pt + s, sizeof(float4) * c, cudaMemcpyDeviceToHost));
             if (vel_xy) CU(h, cudaMemcpy(vl.data(), h->s32[h->cur].vel + s, sizeof(float2) * c, cudaMemcpyDeviceToHost));
+            if (filter) CU(h, cudaMemcpy(live.data(), h->d_cell + s, sizeof(int32_t) * c, cudaMemcpyDeviceToHost));
             for (int64_t k = 0; k < c; k++) {
-                int64_t i = s + k;
+                if (filter && live[k] < 0) continue;
+                int64_t i = o++;
                 if (pos_xy) {
                     pos_xy[2 * i] = pt[k].x;
                     pos_xy[2 * i + 1] = pt[k].y;
@@ -562,12 +620,41 @@ int plife_init_uniform(plife_handle *h, int64_t n, uint64_t seed)
 {
     CHECK_HANDLE(h);
     if (n < 0) return fail(h, PLIFE_ERR_INVALID, "n < 0");
+    if (h->slab.on) {
+        // n is the GLOBAL particle count; this rank keeps the particles of its own rows
+        Grid g;
+        int rc = make_grid(h, &g);
+        if (rc) return rc;
+        const int64_t share = n * (g.row_hi - g.row_lo) / g.ny;
+        int64_t want = h->capacity_hint > 0 ? h->capacity_hint : share + share / 8 + 65536;
+        rc = ensure_capacity(h, want);
+        if (rc) return rc;
+        h->cur = 0;
+        h->has_sorted = false;
+        h->prebinned = false;
+        int *d_counter = reinterpret_cast<int *>(h->d_scalar + 6);
+        CU(h, cudaMemsetAsync(d_counter, 0, sizeof(int), h->stream));
+        CU(h, launch_init_uniform_owned(h, n, seed, g, d_counter));
+        int kept = 0;
+        CU(h, cudaMemcpyAsync(&kept, d_counter, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (kept > h->cap) return fail(h, PLIFE_ERR_OOM, "init_uniform: %d owned particles exceed capacity %lld", kept, (long long)h->cap);
+        h->n = h->n_phys = kept;
+        h->slab.n_old = kept;
+        h->slab.k_below = h->slab.k_above = 0;
+        h->slab.phase = PLIFE_SLAB_SORT;
+        h->max_type = kept > 0 ? h->m - 1 : -1;
+        return PLIFE_OK;
+    }
     int rc = ensure_capacity(h, n);
     if (rc) return rc;
     h->cur = 0;
     h->has_sorted = false;
     h->prebinned = false;
     h->n = n;
+    h->n_phys = n;
+    h->slab.n_old = n;
+    h->slab.k_below = h->slab.k_above = 0;
     CU(h, launch_init_uniform(h, n, seed));
     h->max_type = n > 0 ? h->m - 1 : -1;
     return PLIFE_OK;
@@ -593,6 +680,7 @@ int plife_step(plife_handle *h, double dt, int32_t nsteps)
 {
     CHECK_HANDLE(h);
     if (!isfinite(dt) || nsteps < 0) return fail(h, PLIFE_ERR_INVALID, "step: dt=%g nsteps=%d", dt, nsteps);
+    if (h->slab.on) return fail(h, PLIFE_ERR_STATE, "slab mode: drive the step with plife_slab_phase");
     for (int s = 0; s < nsteps; s++) {
         if (h->stop_requested.exchange(0)) return fail(h, PLIFE_ERR_STOPPED, "stopped after %d of %d steps", s, nsteps);
         int rc = run_step(h, dt);
@@ -640,7 +728,7 @@ int plife_get_containers(plife_handle *h, int32_t *out, int64_t capacity)
 {
     CHECK_HANDLE(h);
     if (!h->has_sorted) return fail(h, PLIFE_ERR_STATE, "no step has run since the last upload");
-    int64_t ncell = (int64_t)h->last_grid.nx * h->last_grid.ny;
+    int64_t ncell = (int64_t)h->last_grid.nx * h->last_grid.nly;
     if (!out || capacity < ncell) return fail(h, PLIFE_ERR_INVALID, "containers: capacity %lld < %lld", (long long)capacity, (long long)ncell);
     CU(h, cudaMemcpyAsync(out, h->d_cell_end, sizeof(int32_t) * ncell, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));

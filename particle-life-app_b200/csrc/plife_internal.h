@@ -17,26 +17,43 @@ namespace plife {
 // (B/Physics.java:82-85, :312-313).  cs stays double: cell assignment is done
 // with IEEE double division in every precision mode.
 struct Grid {
-    int nx, ny;
-    double cs;
+    int nx, ny;  // global grid
+    double cs;   // cell edge = rmax
+    // Slab decomposition over grid rows.  This rank owns global rows [row_lo, row_hi);
+    // its cell arrays are indexed by LOCAL cells lx + ly*nx with ly = cy + ly_shift, where local row 0
+    // and nly-1 are the ghost rows below / above.  Single-GPU: row_lo = 0, row_hi = nly = ny, ly_shift = 0.
+    int row_lo, row_hi;
+    int ly_shift, nly;
+    int rows_up, rows_dn; // rows owned by the ring neighbours (migration reach check)
 };
 
 // Cell coordinates of a position, packed cx | cy << 16.  cx = (int)(x / containerSize) in fp64 is
 // both the un-clamped cx0 of the force pass (B/Physics.java:404, floor == truncation for x >= 0) and,
 // after the `== nx -> nx-1` clamp, the container of the sort (:362-375).  nx <= 16384 (kMaxCells),
-// so cx in [0, nx] fits 15 bits.
+// so cx in [0, nx] fits 15 bits.  A negative value marks a dead slot (a particle that migrated away).
 __host__ __device__ inline int cell_coords(double x, double y, const Grid &g)
 {
     int cx = (int)(x / g.cs);
     int cy = (int)(y / g.cs);
     return cx | (cy << 16);
 }
+// local container index, or -1 if the particle is dead / its row is not owned by this rank
 __host__ __device__ inline int container_of(int cxy, const Grid &g)
 {
+    if (cxy < 0) return -1;
     int cx = cxy & 0xffff, cy = cxy >> 16;
     if (cx == g.nx) cx = g.nx - 1; // for solid borders, :367-372
     if (cy == g.ny) cy = g.ny - 1;
-    return cx + cy * g.nx;
+    if (cy < g.row_lo || cy >= g.row_hi) return -1;
+    return cx + (cy + g.ly_shift) * g.nx;
+}
+// local row of a (wrapped) global row reached from an owned row's 3x3 neighbourhood
+__host__ __device__ inline int local_row(int cy, const Grid &g)
+{
+    int ly = cy + g.ly_shift;
+    if (ly < 0) ly += g.ny;
+    else if (ly >= g.ny) ly -= g.ny;
+    return ly;
 }
 
 // Kernel parameters of the force/integrate pass for one step, in the
@@ -44,6 +61,7 @@ __host__ __device__ inline int container_of(int cxy, const Grid &g)
 template <typename R>
 struct ForceParams {
     int n, m;
+    int first; // sorted-array index of target 0 (ghost-below capacity in slab mode, else 0)
     Grid g;
     int wrap;
     int use_smem_matrix;
@@ -77,6 +95,19 @@ struct Timer {
 
 } // namespace plife
 
+namespace plife {
+// Slab-decomposition state of a handle; see slab.cu.
+struct SlabState {
+    bool on = false;
+    int rank = 0, world = 1;
+    int64_t halo_cap = 0, mig_cap = 0; // particles per halo row message / per migration message
+    // exchange buffers (device pointers handed in by the host, 16-byte records); [0] = down, [1] = up
+    float4 *halo_send[2]{}, *halo_recv[2]{}, *mig_send[2]{}, *mig_recv[2]{};
+    int64_t n_old = 0, k_below = 0, k_above = 0; // layout of the pre-sort array: residents | from below | from above
+    int phase = 0;                  // next phase expected by plife_slab_phase
+};
+} // namespace plife
+
 struct plife_handle {
     int device = 0;
     int precision = PLIFE_F32;
@@ -95,8 +126,11 @@ struct plife_handle {
     int d_matrix_cap = 0;            // entries
     bool matrix_dirty = true;
 
-    int64_t n = 0;
+    int64_t n = 0;      // live particles
+    int64_t n_phys = 0; // physical length of the pre-sort array (== n except in slab mode: dead slots)
     int64_t cap = 0;
+    int64_t capacity_hint = 0;
+    plife::SlabState slab;
     int max_type = -1;
     int cur = 0; // index of the buffer holding the current state
     plife::StateF32 s32[2]{};
@@ -144,6 +178,7 @@ cudaError_t launch_scatter(plife_handle *h, const Grid &g);
 cudaError_t launch_gather(plife_handle *h, const Grid &g);
 cudaError_t launch_type_histogram(plife_handle *h, unsigned long long *d_hist);
 cudaError_t launch_init_uniform(plife_handle *h, int64_t n, uint64_t seed);
+cudaError_t launch_init_uniform_owned(plife_handle *h, int64_t n_global, uint64_t seed, const Grid &g, int *d_counter);
 cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32_t *type);
 
 // force_f32.cu / force_f64.cu

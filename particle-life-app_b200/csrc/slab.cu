@@ -1,0 +1,253 @@
+// Multi-GPU slab decomposition of the physics step: one process per GPU, rank g owns
+// grid rows [g*ny/G, (g+1)*ny/G).  The sorted order is row-major by cell, so a slab is one contiguous
+// index range and its first / last rows are contiguous sub-ranges: packing a halo is a plain copy.
+//
+// Per step (host drives the three phases and exchanges the messages between them, e.g. with
+// torch.distributed / NCCL send-recv; see plife/slab.py):
+//   phase SORT    cell-list build of the owned particles; pack first and last owned row into the halo
+//                 messages {count | per-cell END offsets of the row | 16-byte particle records}
+//   (exchange)    halo_send[0] -> down neighbour's halo_recv[1], halo_send[1] -> up neighbour's halo_recv[0]
+//   phase FORCE   place the ghost rows around the owned block of the sorted array
+//                 [ghost below | owned | ghost above], run the force/integrate kernel over the owned
+//                 particles; its epilogue bins the new positions and appends particles whose new row
+//                 belongs to a neighbour to the migration messages
+//   (exchange)    mig_send[0] -> down neighbour's mig_recv[1], mig_send[1] -> up neighbour's mig_recv[0]
+//   phase FINISH  append the arrivals (binning them), update the particle count
+//
+// Order: arrivals from below logically precede all residents and arrivals from above follow them
+// (StableKey in cells.cu), so the concatenation of the slabs in rank order is exactly the
+// single-GPU particle order.
+#include <math.h>
+#include <stdio.h>
+
+#include "plife_internal.h"
+
+using namespace plife;
+
+namespace plife {
+int slab_make_grid(plife_handle *h, Grid *g);
+int slab_sort(plife_handle *h, const Grid &g);
+int slab_fail(plife_handle *h, int code, const char *msg);
+cudaError_t slab_force(plife_handle *h, const Grid &g, double dt);
+} // namespace plife
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int offsets_records(int nx) { return (nx + 3) >> 2; }
+
+// dir 0: first owned row (local row 1) -> becomes the down neighbour's top ghost row
+// dir 1: last owned row (local row nly-2) -> becomes the up neighbour's bottom ghost row
+__global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__ pt_sorted, const int32_t *__restrict__ cell_end,
+                                                      Grid g, int halo_cap, float4 *__restrict__ msg0, float4 *__restrict__ msg1)
+{
+    const int dir = blockIdx.y;
+    float4 *msg = dir ? msg1 : msg0;
+    const int row = dir ? g.nly - 2 : 1;
+    const int start = __ldg(cell_end + row * g.nx - 1);
+    const int end = __ldg(cell_end + (row + 1) * g.nx - 1);
+    const int count = end - start;
+    const int noff = offsets_records(g.nx);
+    const int t = blockIdx.x * kThreads + threadIdx.x;
+    if (t == 0) {
+        int4 hd = make_int4(count <= halo_cap ? count : -count, g.nx, 0, 0);
+        msg[0] = *reinterpret_cast<float4 *>(&hd);
+    }
+    if (count > halo_cap) return; // overflow: reported by the receiver and by phase FINISH
+    int32_t *off = reinterpret_cast<int32_t *>(msg + 1);
+    for (int c = t; c < g.nx; c += gridDim.x * kThreads) off[c] = __ldg(cell_end + row * g.nx + c) - start;
+    for (int k = t; k < count; k += gridDim.x * kThreads) msg[1 + noff + k] = __ldg(pt_sorted + start + k);
+}
+
+// which 0: ghost row below (local row 0), right-aligned before the owned block at `first`
+// which 1: ghost row above (local row nly-1), placed after the owned block
+__global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_sorted, int32_t *__restrict__ cell_end, Grid g,
+                                                        int first, int n, const float4 *__restrict__ msg0,
+                                                        const float4 *__restrict__ msg1, int *__restrict__ err)
+{
+    const int which = blockIdx.y;
+    const float4 *msg = which ? msg1 : msg0;
+    if (!msg) return;
+    const int4 hd = *reinterpret_cast<const int4 *>(msg);
+    const int t = blockIdx.x * kThreads + threadIdx.x;
+    if (hd.x < 0 || hd.y != g.nx) {
+        if (t == 0) atomicAdd(err, 1);
+        return;
+    }
+    const int count = hd.x;
+    const int noff = offsets_records(g.nx);
+    const int base = which ? first + n : first - count;
+    const int row = which ? g.nly - 1 : 0;
+    const int32_t *off = reinterpret_cast<const int32_t *>(msg + 1);
+    for (int c = t; c < g.nx; c += gridDim.x * kThreads) cell_end[row * g.nx + c] = base + off[c];
+    if (which == 0 && t == 0) cell_end[-1] = base;
+    for (int k = t; k < count; k += gridDim.x * kThreads) pt_sorted[base + k] = __ldg(msg + 1 + noff + k);
+}
+
+// Arrivals: message records {x,y,type,id},{vx,vy,source slot,-}.  Each is placed at
+// base + (rank of its source slot among the arrivals of the same message): the sender appended them
+// with an atomic cursor, the rank restores the sender's array order.
+__global__ void __launch_bounds__(kThreads) append_arrivals(const float4 *__restrict__ msg, int k, int base, Grid g,
+                                                            float4 *__restrict__ pt, float2 *__restrict__ vel,
+                                                            int32_t *__restrict__ cell, int32_t *__restrict__ count,
+                                                            int *__restrict__ err)
+{
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= k) return;
+    const float4 a = __ldg(msg + 1 + 2 * j), b = __ldg(msg + 2 + 2 * j);
+    const int src = __float_as_int(b.z);
+    int rank = 0;
+    for (int q = 0; q < k; ++q) rank += (__float_as_int(__ldg(msg + 2 + 2 * q).z) < src) ? 1 : 0;
+    const int dst = base + rank;
+    pt[dst] = a;
+    vel[dst] = make_float2(b.x, b.y);
+    const int cxy = cell_coords((double)a.x, (double)a.y, g);
+    const int c = container_of(cxy, g);
+    cell[dst] = c < 0 ? -1 : cxy;
+    if (c >= 0) atomicAdd(count + c, 1);
+    else atomicAdd(err, 1); // sender and receiver disagree about ownership
+}
+
+__global__ void zero_headers(float4 *a, float4 *b)
+{
+    if (threadIdx.x == 0) {
+        a[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        b[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+int fail(plife_handle *h, int code, const char *msg) { return slab_fail(h, code, msg); }
+
+#define CUS(h, expr)                                                      \
+    do {                                                                  \
+        cudaError_t e_ = (expr);                                          \
+        if (e_ != cudaSuccess) {                                          \
+            h->poisoned = true;                                           \
+            return fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e_));       \
+        }                                                                 \
+    } while (0)
+
+} // namespace
+
+extern "C" {
+
+int64_t plife_slab_halo_records(int32_t nx, int64_t halo_cap) { return 1 + (nx + 3) / 4 + halo_cap; }
+int64_t plife_slab_migrate_records(int64_t mig_cap) { return 1 + 2 * mig_cap; }
+
+int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t halo_cap, int64_t mig_cap,
+                         const plife_slab_buffers *bufs)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (h->precision != PLIFE_F32) return fail(h, PLIFE_ERR_INVALID, "slab mode is implemented for PLIFE_F32 handles");
+    if (h->flags & PLIFE_FLAG_NO_FUSED_BIN) return fail(h, PLIFE_ERR_INVALID, "slab mode needs the fused binning (migration rides on it)");
+    if (world < 1 || rank < 0 || rank >= world || halo_cap < 1 || mig_cap < 1 || !bufs) return fail(h, PLIFE_ERR_INVALID, "slab_configure: bad arguments");
+    if (h->n > 0) return fail(h, PLIFE_ERR_STATE, "configure the slab before uploading particles");
+    for (int d = 0; d < 2; d++)
+        if (!bufs->halo_send[d] || !bufs->halo_recv[d] || !bufs->mig_send[d] || !bufs->mig_recv[d])
+            return fail(h, PLIFE_ERR_INVALID, "slab_configure: NULL exchange buffer");
+    h->slab.on = true;
+    h->slab.rank = rank;
+    h->slab.world = world;
+    h->slab.halo_cap = halo_cap;
+    h->slab.mig_cap = mig_cap;
+    for (int d = 0; d < 2; d++) {
+        h->slab.halo_send[d] = (float4 *)bufs->halo_send[d];
+        h->slab.halo_recv[d] = (float4 *)bufs->halo_recv[d];
+        h->slab.mig_send[d] = (float4 *)bufs->mig_send[d];
+        h->slab.mig_recv[d] = (float4 *)bufs->mig_recv[d];
+    }
+    h->slab.phase = PLIFE_SLAB_SORT;
+    h->prebinned = false;
+    return PLIFE_OK;
+}
+
+int plife_slab_rows(plife_handle *h, int32_t *row_lo, int32_t *row_hi, int32_t *nx)
+{
+    if (!h || !h->slab.on) return PLIFE_ERR_STATE;
+    Grid g;
+    int rc = slab_make_grid(h, &g);
+    if (rc) return rc;
+    if (row_lo) *row_lo = g.row_lo;
+    if (row_hi) *row_hi = g.row_hi;
+    if (nx) *nx = g.nx;
+    return PLIFE_OK;
+}
+
+int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (h->poisoned) return fail(h, PLIFE_ERR_CUDA, "handle poisoned by an earlier CUDA error");
+    if (!h->slab.on) return fail(h, PLIFE_ERR_STATE, "plife_slab_configure has not been called");
+    if (phase != h->slab.phase) return fail(h, PLIFE_ERR_STATE, "slab phases must run in order SORT, FORCE, FINISH");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, PLIFE_ERR_CUDA, "cudaSetDevice");
+    Grid g;
+    int rc = slab_make_grid(h, &g);
+    if (rc) return rc;
+    SlabState &S = h->slab;
+    const bool wrap = h->settings.wrap != 0;
+    const bool has_dn = S.world > 1 && (wrap || S.rank > 0);
+    const bool has_up = S.world > 1 && (wrap || S.rank < S.world - 1);
+    int *d_err = reinterpret_cast<int *>(h->d_scalar + 4);
+    const int first = (int)S.halo_cap;
+
+    if (phase == PLIFE_SLAB_SORT) {
+        rc = slab_sort(h, g); // bin (if needed), scan, scatter, gather: owned block of the sorted array
+        if (rc) return rc;
+        const int sorted = h->cur ^ 1;
+        dim3 grid(32, 2);
+        pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1]);
+        zero_headers<<<1, 32, 0, h->stream>>>(S.mig_send[0], S.mig_send[1]);
+        CUS(h, cudaGetLastError());
+        S.phase = PLIFE_SLAB_FORCE;
+        return PLIFE_OK;
+    }
+    if (phase == PLIFE_SLAB_FORCE) {
+        const int sorted = h->cur ^ 1;
+        dim3 grid(32, 2);
+        unpack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, first, (int)h->n,
+                                                      has_dn ? S.halo_recv[0] : nullptr, has_up ? S.halo_recv[1] : nullptr, d_err);
+        CUS(h, cudaGetLastError());
+        CUS(h, slab_force(h, g, dt));
+        S.phase = PLIFE_SLAB_FINISH;
+        return PLIFE_OK;
+    }
+    // PLIFE_SLAB_FINISH: headers back to the host (the only synchronisation of the step)
+    int4 hs[4];
+    int err = 0;
+    CUS(h, cudaMemcpyAsync(&hs[0], S.mig_send[0], 16, cudaMemcpyDeviceToHost, h->stream));
+    CUS(h, cudaMemcpyAsync(&hs[1], S.mig_send[1], 16, cudaMemcpyDeviceToHost, h->stream));
+    CUS(h, cudaMemcpyAsync(&hs[2], S.mig_recv[0], 16, cudaMemcpyDeviceToHost, h->stream));
+    CUS(h, cudaMemcpyAsync(&hs[3], S.mig_recv[1], 16, cudaMemcpyDeviceToHost, h->stream));
+    CUS(h, cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUS(h, cudaStreamSynchronize(h->stream));
+    S.phase = PLIFE_SLAB_SORT;
+    const int sent_dn = hs[0].x, sent_up = hs[1].x;
+    const int k_below = has_dn ? hs[2].x : 0, k_above = has_up ? hs[3].x : 0;
+    if (err) return fail(h, PLIFE_ERR_STATE, "slab: halo overflow / grid mismatch between ranks / ownership mismatch (raise halo_cap)");
+    if (hs[0].y || hs[1].y) return fail(h, PLIFE_ERR_STATE, "slab: a particle crossed more than one slab in one step");
+    if ((!has_dn && sent_dn) || (!has_up && sent_up)) return fail(h, PLIFE_ERR_STATE, "slab: particle left through a closed boundary");
+    if (sent_dn > S.mig_cap || sent_up > S.mig_cap || k_below > S.mig_cap || k_above > S.mig_cap)
+        return fail(h, PLIFE_ERR_STATE, "slab: migration message overflow (raise mig_cap)");
+    const int64_t L = h->n; // residents before this step (the force pass wrote slots [0, L))
+    if (L + k_below + k_above > h->cap) return fail(h, PLIFE_ERR_OOM, "slab: particle capacity exceeded by arrivals");
+    const int cur = h->cur;
+    int *d_err2 = d_err; // errors raised from here on are reported by the next FINISH
+    CUS(h, cudaMemsetAsync(d_err, 0, sizeof(int), h->stream));
+    if (k_below > 0)
+        append_arrivals<<<(k_below + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(S.mig_recv[0], k_below, (int)L, g, h->s32[cur].pt,
+                                                                                      h->s32[cur].vel, h->d_cell, h->d_count, d_err2);
+    if (k_above > 0)
+        append_arrivals<<<(k_above + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(S.mig_recv[1], k_above, (int)L + k_below, g,
+                                                                                      h->s32[cur].pt, h->s32[cur].vel, h->d_cell, h->d_count, d_err2);
+    CUS(h, cudaGetLastError());
+    S.n_old = L;
+    S.k_below = k_below;
+    S.k_above = k_above;
+    h->n_phys = L + k_below + k_above;
+    h->n = L - sent_dn - sent_up + k_below + k_above;
+    h->steps++;
+    return PLIFE_OK;
+}
+
+} // extern "C"

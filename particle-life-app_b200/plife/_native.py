@@ -33,6 +33,14 @@ class StepStats(C.Structure):
                 ("steps", C.c_int64)]
 
 
+class SlabBuffers(C.Structure):
+    _fields_ = [("halo_send", C.c_void_p * 2), ("halo_recv", C.c_void_p * 2),
+                ("mig_send", C.c_void_p * 2), ("mig_recv", C.c_void_p * 2)]
+
+
+SLAB_SORT, SLAB_FORCE, SLAB_FINISH = 0, 1, 2
+
+
 class PlifeError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"plife status {status}: {message}")
@@ -80,6 +88,11 @@ def lib() -> C.CDLL:
         "plife_set_profiling": (C.c_int, [vp, i32]),
         "plife_kernel_times": (C.c_int, [vp, vp, vp]),
         "plife_device_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "plife_slab_halo_records": (i64, [i32, i64]),
+        "plife_slab_migrate_records": (i64, [i64]),
+        "plife_slab_configure": (C.c_int, [vp, i32, i32, i64, i64, C.POINTER(SlabBuffers)]),
+        "plife_slab_rows": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "plife_slab_phase": (C.c_int, [vp, i32, dbl]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
