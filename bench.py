@@ -48,6 +48,25 @@ def workload(name):
     return c
 
 
+def scaled_workload(name, world):
+    """Weak scaling: per-GPU particle count fixed, density fixed (rmax shrinks with sqrt(world)).
+    world == 8 on C3 reproduces BASELINE config 4's 128M particles (nx = 2828 instead of 2800)."""
+    import numpy as np
+    c = workload(name)
+    if world > 1:
+        nx1 = int(np.floor(1.0 / c["rmax"]))
+        nx = int(round(nx1 * world ** 0.5))
+        rmax = 1.0 / nx
+        while int(np.floor(1.0 / rmax)) != nx:
+            rmax = float(np.nextafter(rmax, 0.0))
+        c["rmax"] = rmax
+        c["n_per_gpu"] = c["n"]
+        c["n"] = c["n"] * world
+    else:
+        c["n_per_gpu"] = c["n"]
+    return c
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -139,7 +158,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = workload(args.workload)
+    cfg = scaled_workload(args.workload, max(1, args.gpus))
     threads = os.cpu_count() or 1
     sample_n = min(cfg["n"], 1_000_000)
     r = cpu_reference_run(cfg, max(1, args.steps), max(0, args.warmup), threads, sample_n)
@@ -175,16 +194,41 @@ def run_ours(args):
     import plife
     from plife import _native as N
 
-    cfg = workload(args.workload)
-    n, m = cfg["n"], cfg["m"]
+    cfg = scaled_workload(args.workload, world)
+    n, m = cfg["n"], cfg["m"]  # n = GLOBAL particle count
     precision = plife.F64 if args.precision == "f64" else plife.F32
 
     stream = torch.cuda.Stream()
-    p = plife.NativePhysics(device=local_rank, precision=precision, stream=stream.cuda_stream)
-    p.set_settings(cfg["rmax"], 0.85, 1.0, cfg["wrap"])
-    p.random_matrix(m, cfg["seed"])
+    if world == 1:
+        p = plife.NativePhysics(device=local_rank, precision=precision, stream=stream.cuda_stream)
+        p.set_settings(cfg["rmax"], 0.85, 1.0, cfg["wrap"])
+        p.random_matrix(m, cfg["seed"])
+        p.init_uniform(n, cfg["seed"])
+        slab = None
+
+        def run_steps(k):
+            p.step(DT, k)
+    else:
+        from plife.slab import DistExchange, SlabPhysics, grid_rows
+        if precision != plife.F32:
+            raise SystemExit("bench.py: the slab path is fp32")
+        nx = grid_rows(cfg["rmax"])
+        rho = n / nx ** 2
+        share = n // world
+        with torch.cuda.stream(stream):
+            slab = SlabPhysics(rank, world, cfg["rmax"], device=local_rank, capacity=share + share // 8 + 65536,
+                               halo_cap=int(nx * rho * 1.5) + 4096, mig_cap=max(65536, share // 64), wrap=cfg["wrap"],
+                               stream=stream.cuda_stream, exchange=args.exchange)
+            if args.exchange == "peer":
+                slab.connect_dist()
+        p = slab.native
+        p.random_matrix(m, cfg["seed"])
+        p.init_uniform(n, cfg["seed"])  # every rank scans the global stream and keeps its own rows
+        ex = DistExchange(rank, world)
+
+        def run_steps(k):
+            slab.step(DT, ex, k)
     matrix = p.get_matrix()
-    p.init_uniform(n, cfg["seed"] + rank)
 
     def barrier():
         if world > 1:
@@ -193,14 +237,14 @@ def run_ours(args):
 
     # ---- resident-state throughput ----
     with torch.cuda.stream(stream):
-        p.step(DT, max(3, args.warmup))
+        run_steps(max(3, args.warmup))
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        p.step(DT, args.steps)
+        run_steps(args.steps)
         e1.record(stream)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
@@ -209,30 +253,35 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = n * world * args.steps / (ms * 1e-3)
+    value = n * args.steps / (ms * 1e-3)
     stats = p.step_stats()
+    n_local = p.count
 
     # ---- per-kernel device time of the same steps (events between kernels) ----
     with torch.cuda.stream(stream):
-        p.set_profiling(True)
-        p.step(DT, args.steps)
-        kt = p.kernel_times()
-        p.set_profiling(False)
+        if world == 1:
+            p.set_profiling(True)
+            run_steps(args.steps)
+            kt = p.kernel_times()
+            p.set_profiling(False)
+        else:
+            kt = {k: (0.0, 0) for k in N.KERNEL_NAMES}
     force_ms = kt["force"][0] / max(1, kt["force"][1])
     per_kernel = {k: v[0] / args.steps for k, v in kt.items()}
 
     # ---- end to end through the C ABI with host buffers ----
-    pin_pos = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    pin_vel = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    pin_typ = torch.empty((n,), dtype=torch.int32).pin_memory()
-    h2d = matrix.nbytes + 32
+    ncap = n if world == 1 else n_local + n_local // 8 + 65536
+    pin_pos = torch.empty((ncap, 2), dtype=torch.float32).pin_memory()
+    pin_vel = torch.empty((ncap, 2), dtype=torch.float32).pin_memory()
+    pin_typ = torch.empty((ncap,), dtype=torch.int32).pin_memory()
+    h2d = (matrix.nbytes + 32) * world
     d2h = n * 20
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step():
         p.set_settings(cfg["rmax"], 0.85, 1.0, cfg["wrap"])
         p.set_matrix(matrix)
-        p.step(DT, 1)
+        run_steps(1)
         p.download_f32(pin_pos.data_ptr(), pin_vel.data_ptr(), pin_typ.data_ptr())
 
     with torch.cuda.stream(stream):
@@ -247,7 +296,7 @@ def run_ours(args):
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * e2e_steps / float(t.item())
+    e2e_value = n * e2e_steps / float(t.item())
 
     if rank != 0:
         if world > 1:
@@ -255,14 +304,15 @@ def run_ours(args):
         return 0
 
     hbm_peak, peak_src = peaks()
-    force_gbs = ALGO_BYTES_FORCE * n / (force_ms * 1e-3) / 1e9
-    step_gbs = ALGO_BYTES_STEP * n * world / (ms / args.steps * 1e-3) / 1e9
+    force_gbs = ALGO_BYTES_FORCE * n / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
+    step_gbs = ALGO_BYTES_STEP * n / (ms / args.steps * 1e-3) / 1e9
     pair_rate = stats["pair_evals"] * world * args.steps / (ms * 1e-3)
     fp32_peak_tf = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
-    fp32_force_tf = FLOP_PER_PAIR * stats["pair_evals"] / (force_ms * 1e-3) / 1e12
+    fp32_force_tf = FLOP_PER_PAIR * stats["pair_evals"] / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
+    fp32_step_tf = FLOP_PER_PAIR * stats["pair_evals"] * world / (ms / args.steps * 1e-3) / 1e12
 
     cpu = None
-    if world == 1 or rank == 0:
+    if world == 1:
         threads = os.cpu_count() or 1
         sample_n = min(n, 1_000_000)
         r = cpu_reference_run(cfg, 2, 1, threads, sample_n)
@@ -278,23 +328,25 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if precision == plife.F32 else "f64", "data": "synthetic",
-        "config": {"workload": f"{cfg['name']}: {n} particles per GPU, {m} types, rmax={cfg['rmax']} (nx={stats['nx']}, "
+        "config": {"workload": f"{cfg['name']}: {n} particles ({cfg['n_per_gpu']} per GPU), {m} types, rmax={cfg['rmax']:.9g} (nx={stats['nx']}, "
                                f"{n / stats['nx'] ** 2:.1f} particles/cell), wrap={cfg['wrap']}, default accelerator, "
                                f"per-step cell-list rebuild, uniform-random state",
-                   "l2": "state (2 x 24 B x N) exceeds the 126 MB L2; no flush needed" if n * 48 > 126e6 else "state fits in L2: cache-resident",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab exchange: see DESIGN.md)"},
+                   "l2": "per-GPU state (2 x 24 B x N) exceeds the 126 MB L2; no flush needed" if cfg["n_per_gpu"] * 48 > 126e6 else "state fits in L2: cache-resident",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} slabs over grid rows, halo exchange + particle migration every step via " + ("kernel pushes into CUDA-IPC peer memory over NVLink" if args.exchange == "peer" else "NCCL send/recv")},
         "pair_evals_per_sec": pair_rate,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "per step: set_settings + set_matrix from host, plife_step, full fp32 snapshot (xy,vxy,type) into pinned host memory"},
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": (6 if world == 1 else 10) * args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "force_kernel (3x3 force + friction + integrate + wrap)",
-                     "achieved": force_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": force_gbs / hbm_peak, "traffic": None,
+                     "achieved": force_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": force_gbs / hbm_peak if force_gbs else None, "traffic": 54.5 * cfg["n_per_gpu"] / 1e9 if world == 1 else None,
+                     "traffic_note": "GB per launch: dram__bytes_read+write of force_kernel_staged from profiles/r1_force_kernel.md (54.5 B/particle)",
                      "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES_FORCE,
                      "binding": "fp32 issue (9*rho-1 = 143 pair evaluations per particle at 16 particles/cell); HBM fraction is low by construction, see fp32"},
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak * world, "unit": "GB/s", "frac": step_gbs / (hbm_peak * world),
                           "algorithmic_bytes_per_particle_step": ALGO_BYTES_STEP},
-        "fp32": {"achieved": fp32_force_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": fp32_force_tf / fp32_peak_tf,
+        "fp32": {"achieved": fp32_force_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": fp32_force_tf / fp32_peak_tf if fp32_force_tf else None,
+                 "whole_step_achieved": fp32_step_tf, "whole_step_frac": fp32_step_tf / (fp32_peak_tf * world),
                  "flop_per_pair_eval": FLOP_PER_PAIR, "peak_source": "nominal 148 SM x 128 lanes x 2 x max SM clock"},
         "kernel_ms_per_step": per_kernel,
         "cpu_baseline": cpu,
@@ -313,6 +365,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU message transport")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -187,7 +187,7 @@ int plife_device_ptrs(plife_handle *h, void **pos, void **vel, void **type, void
  *   halo_send[0] -> down neighbour's halo_recv[1],  halo_send[1] -> up neighbour's halo_recv[0]
  *   mig_send[0]  -> down neighbour's mig_recv[1],   mig_send[1]  -> up neighbour's mig_recv[0]
  * (down = rank-1, up = rank+1, periodic when wrap is on; no exchange across a closed boundary).
- * Buffers are device memory owned by the caller, in 16-byte records:
+ * External exchange (bufs != NULL): buffers are device memory owned by the caller, in 16-byte records:
  * plife_slab_halo_records(nx, halo_cap) / plife_slab_migrate_records(mig_cap) records each.
  * fp32 handles only.  Upload only particles of the rank's own rows (others are dropped). */
 typedef struct plife_slab_buffers {
@@ -202,6 +202,15 @@ int64_t plife_slab_halo_records(int32_t nx, int64_t halo_cap);
 int64_t plife_slab_migrate_records(int64_t mig_cap);
 int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t halo_cap, int64_t mig_cap,
                          const plife_slab_buffers *bufs);
+/* Peer exchange (bufs == NULL in plife_slab_configure): the library owns the buffers; every rank exports a
+ * 64-byte CUDA IPC handle, the host distributes them (any transport), and each rank maps its neighbours'
+ * receive slots.  The step then needs no host-side exchange: kernels push the messages over NVLink and
+ * signal with flags.  NULL = no neighbour in that direction (closed boundary). */
+int plife_slab_export(plife_handle *h, void *ipc_handle_64_bytes);
+int plife_slab_connect_ipc(plife_handle *h, const void *down_handle, const void *up_handle);
+int plife_slab_connect_local(plife_handle *h, plife_handle *down, plife_handle *up);
+/* SORT, FORCE, FINISH back to back, nsteps times (peer exchange only) */
+int plife_slab_step(plife_handle *h, double dt, int32_t nsteps);
 /* rows [row_lo, row_hi) owned by this rank under the current settings, and nx */
 int plife_slab_rows(plife_handle *h, int32_t *row_lo, int32_t *row_hi, int32_t *nx);
 int plife_slab_phase(plife_handle *h, int32_t phase, double dt);

@@ -1,4 +1,7 @@
 // fp32 instantiations of the force/integrate pass (fused multiply-add allowed).
+#include <stdlib.h>
+
+#define PLIFE_FORCE_F32_TU 1 // the staged fp32 kernels are instantiated here and nowhere else
 #include "force_impl.cuh"
 
 namespace plife {
@@ -12,7 +15,8 @@ static IOF32 make_io(plife_handle *h)
 static NextBin next_bin(plife_handle *h)
 {
     if (h->flags & PLIFE_FLAG_NO_FUSED_BIN) return NextBin{nullptr, nullptr, {nullptr, nullptr}, 0};
-    return NextBin{h->d_cell, h->d_count, {h->slab.on ? h->slab.mig_send[0] : nullptr, h->slab.on ? h->slab.mig_send[1] : nullptr}, (int)h->slab.mig_cap};
+    NextBin nb{h->d_cell, h->d_count, {h->slab.on ? h->slab.mig_send[0] : nullptr, h->slab.on ? h->slab.mig_send[1] : nullptr}, (int)h->slab.mig_cap};
+    return nb;
 }
 
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
@@ -22,7 +26,7 @@ cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
     // v2 staged kernel whenever the per-lane matrix table fits; v1 (global-memory walk) otherwise
     if (p.m <= kTabMaxM && !(h->flags & PLIFE_FLAG_FORCE_V1)) {
         // capacity of one staged row range: 128 targets + the cells hanging over both ends + margin
-        const double rho = (double)p.n / ((double)p.g.nx * p.g.ny);
+        const double rho = (double)p.n / ((double)p.g.nx * (p.g.row_hi - p.g.row_lo)); // particles per owned cell
         int cap = (int)(kForceThreads + 4.0 * rho + 8.0 * sqrt(rho + 1.0) + 32.0);
         cap = (cap + 31) / 32 * 32;
         if (cap > 1536) cap = 1536;

@@ -456,6 +456,11 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
     nb.add(i, nx_, ny_, nvx, nvy, self.type, self.id, P.g);
 }
 
+// The v2 kernels below exist ONLY in the fp32 translation unit.  force_f64.cu is compiled with
+// -fmad=false; if it also instantiated them, the library would hold two device images of the same
+// kernel (fused and unfused arithmetic) and which one a launch binds to is decided at module-load time:
+// results then differ by an ulp from process to process (found the hard way, profiles/r1_multigpu.md).
+#ifdef PLIFE_FORCE_F32_TU
 // ---- v2: shared-memory staged candidates (fp32) ------------------------------------------
 // The per-lane `LDG.128` of the kernel above costs 4 L1 data-pipe cycles per warp whatever the
 // address pattern, and the shared matrix lookup bank-conflicts between lanes of different cells
@@ -674,6 +679,8 @@ inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_en
 #undef PLIFE_LAUNCH_STAGED
     return cudaGetLastError();
 }
+
+#endif // PLIFE_FORCE_F32_TU
 
 template <typename IO>
 __global__ void __launch_bounds__(kForceThreads) neighbors_kernel(IO io, const int32_t *__restrict__ cell_end,

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -408,6 +409,7 @@ int plife_destroy(plife_handle *h)
     cudaStreamSynchronize(h->stream);
     for (auto &p : h->pending)
         for (int k = 0; k <= PLIFE_K_COUNT; k++) cudaEventDestroy(p.ev[k]);
+    slab_destroy(h);
     free_state(h);
     cudaFree(h->d_count);
     if (h->d_cell_end) cudaFree(h->d_cell_end - 4);

@@ -105,8 +105,21 @@ struct SlabState {
     float4 *halo_send[2]{}, *halo_recv[2]{}, *mig_send[2]{}, *mig_recv[2]{};
     int64_t n_old = 0, k_below = 0, k_above = 0; // layout of the pre-sort array: residents | from below | from above
     int phase = 0;                  // next phase expected by plife_slab_phase
+    // peer exchange (library-owned buffers, CUDA IPC)
+    bool peer_mode = false;
+    float4 *xbuf = nullptr;         // flags + receive slots (exported)
+    int64_t xrecords = 0, hrec = 0, mrec = 0;
+    int nx_cfg = 0;
+    unsigned long long seq = 1;     // step sequence number written into the neighbours' flags
+    float4 *peer_base[2]{};         // the neighbours' xbuf mapped into this process / device
+    bool peer_ipc[2]{};
 };
 } // namespace plife
+
+struct plife_handle;
+namespace plife {
+void slab_destroy(plife_handle *h);
+}
 
 struct plife_handle {
     int device = 0;

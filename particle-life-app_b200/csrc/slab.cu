@@ -14,11 +14,21 @@
 //   (exchange)    mig_send[0] -> down neighbour's mig_recv[1], mig_send[1] -> up neighbour's mig_recv[0]
 //   phase FINISH  append the arrivals (binning them), update the particle count
 //
+// Two ways to move the messages:
+//   external  the host exchanges caller-provided buffers between the phases (torch.distributed/NCCL);
+//   peer      (default) the library owns the buffers, ranks map each other's receive slots with CUDA IPC
+//             and the kernels push a message straight into the neighbour's slot over NVLink, then raise a
+//             flag (sequence number) there; the consumer's stream spins on its own flag in a 1-thread
+//             kernel.  Slots are double-buffered by step parity: a rank can only be one message ahead of
+//             its neighbour (it waits for the neighbour's flag of step k before it produces step k+1), so
+//             the slot of step k+1 was consumed by the neighbour before its step-k flag was raised.
+//
 // Order: arrivals from below logically precede all residents and arrivals from above follow them
 // (StableKey in cells.cu), so the concatenation of the slabs in rank order is exactly the
 // single-GPU particle order.
 #include <math.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "plife_internal.h"
 
@@ -56,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__
     }
     if (count > halo_cap) return; // overflow: reported by the receiver and by phase FINISH
     int32_t *off = reinterpret_cast<int32_t *>(msg + 1);
-    for (int c = t; c < g.nx; c += gridDim.x * kThreads) off[c] = __ldg(cell_end + row * g.nx + c) - start;
+    for (int c = t; c < 4 * noff; c += gridDim.x * kThreads) off[c] = c < g.nx ? __ldg(cell_end + row * g.nx + c) - start : 0;
     for (int k = t; k < count; k += gridDim.x * kThreads) msg[1 + noff + k] = __ldg(pt_sorted + start + k);
 }
 
@@ -109,6 +119,45 @@ __global__ void __launch_bounds__(kThreads) append_arrivals(const float4 *__rest
     else atomicAdd(err, 1); // sender and receiver disagree about ownership
 }
 
+// copy a message (its used records only) into the neighbour's receive slot
+__global__ void __launch_bounds__(kThreads) push_msg(const float4 *__restrict__ local, float4 *__restrict__ peer, int is_halo, int nx,
+                                                     int cap)
+{
+    const int count = *reinterpret_cast<const int *>(local);
+    int nrec;
+    if (is_halo) nrec = count < 0 ? 1 : 1 + offsets_records(nx) + count;
+    else nrec = 1 + 2 * min(count, cap);
+    for (int k = blockIdx.x * kThreads + threadIdx.x; k < nrec; k += gridDim.x * kThreads) peer[k] = local[k];
+    __threadfence_system();
+}
+
+__global__ void signal_flags(volatile unsigned long long *f0, volatile unsigned long long *f1, unsigned long long seq)
+{
+    __threadfence_system();
+    if (f0) *f0 = seq;
+    if (f1) *f1 = seq;
+}
+
+// spin until both flags (written by the neighbours) reach seq; bounded so a dead peer cannot hang the GPU
+__global__ void wait_flags(const volatile unsigned long long *f0, const volatile unsigned long long *f1, unsigned long long seq,
+                           int *err)
+{
+    const long long t0 = clock64();
+    const long long limit = 20000000000ll; // ~10 s of SM clocks
+    for (int k = 0; k < 2; ++k) {
+        const volatile unsigned long long *f = k ? f1 : f0;
+        if (!f) continue;
+        while (*f < seq) {
+            if (clock64() - t0 > limit) {
+                atomicAdd(err, 1 << 16); // timeout
+                return;
+            }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
 __global__ void zero_headers(float4 *a, float4 *b)
 {
     if (threadIdx.x == 0) {
@@ -130,6 +179,50 @@ int fail(plife_handle *h, int code, const char *msg) { return slab_fail(h, code,
 
 } // namespace
 
+// ---- peer-mode buffer layout (one allocation per rank, exported through CUDA IPC) ----
+// records (16 B): [0,8) flags: 8 x uint64 (halo from dn, halo from up, mig from dn, mig from up, spare)
+//                 then halo slots [parity][dir][hrec], then migration slots [parity][dir][mrec]
+namespace {
+constexpr int kFlagRecords = 8;
+enum { F_HALO_DN = 0, F_HALO_UP = 1, F_MIG_DN = 2, F_MIG_UP = 3 };
+
+inline float4 *halo_slot(float4 *base, const SlabState &S, int parity, int dir)
+{
+    return base + kFlagRecords + (size_t)(parity * 2 + dir) * S.hrec;
+}
+inline float4 *mig_slot(float4 *base, const SlabState &S, int parity, int dir)
+{
+    return base + kFlagRecords + (size_t)4 * S.hrec + (size_t)(parity * 2 + dir) * S.mrec;
+}
+inline volatile unsigned long long *flag_of(float4 *base, int idx)
+{
+    return base ? reinterpret_cast<volatile unsigned long long *>(base) + idx : nullptr;
+}
+
+void slab_release(plife_handle *h)
+{
+    SlabState &S = h->slab;
+    for (int d = 0; d < 2; d++) {
+        if (S.peer_ipc[d] && S.peer_base[d] && !(d == 1 && S.peer_base[1] == S.peer_base[0] && S.peer_ipc[0]))
+            cudaIpcCloseMemHandle(S.peer_base[d]);
+        S.peer_base[d] = nullptr;
+        S.peer_ipc[d] = false;
+    }
+    if (S.peer_mode) {
+        cudaFree(S.xbuf);
+        for (int d = 0; d < 2; d++) {
+            cudaFree(S.halo_send[d]);
+            cudaFree(S.mig_send[d]);
+        }
+    }
+    S = SlabState{};
+}
+} // namespace
+
+namespace plife {
+void slab_destroy(plife_handle *h) { slab_release(h); }
+} // namespace plife
+
 extern "C" {
 
 int64_t plife_slab_halo_records(int32_t nx, int64_t halo_cap) { return 1 + (nx + 3) / 4 + halo_cap; }
@@ -141,24 +234,110 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
     if (!h) return PLIFE_ERR_INVALID;
     if (h->precision != PLIFE_F32) return fail(h, PLIFE_ERR_INVALID, "slab mode is implemented for PLIFE_F32 handles");
     if (h->flags & PLIFE_FLAG_NO_FUSED_BIN) return fail(h, PLIFE_ERR_INVALID, "slab mode needs the fused binning (migration rides on it)");
-    if (world < 1 || rank < 0 || rank >= world || halo_cap < 1 || mig_cap < 1 || !bufs) return fail(h, PLIFE_ERR_INVALID, "slab_configure: bad arguments");
+    if (world < 1 || rank < 0 || rank >= world || halo_cap < 1 || mig_cap < 1) return fail(h, PLIFE_ERR_INVALID, "slab_configure: bad arguments");
     if (h->n > 0) return fail(h, PLIFE_ERR_STATE, "configure the slab before uploading particles");
-    for (int d = 0; d < 2; d++)
-        if (!bufs->halo_send[d] || !bufs->halo_recv[d] || !bufs->mig_send[d] || !bufs->mig_recv[d])
-            return fail(h, PLIFE_ERR_INVALID, "slab_configure: NULL exchange buffer");
-    h->slab.on = true;
-    h->slab.rank = rank;
-    h->slab.world = world;
-    h->slab.halo_cap = halo_cap;
-    h->slab.mig_cap = mig_cap;
-    for (int d = 0; d < 2; d++) {
-        h->slab.halo_send[d] = (float4 *)bufs->halo_send[d];
-        h->slab.halo_recv[d] = (float4 *)bufs->halo_recv[d];
-        h->slab.mig_send[d] = (float4 *)bufs->mig_send[d];
-        h->slab.mig_recv[d] = (float4 *)bufs->mig_recv[d];
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, PLIFE_ERR_CUDA, "cudaSetDevice");
+    slab_release(h);
+    SlabState &S = h->slab;
+    Grid g;
+    S.on = false;
+    int rc = slab_make_grid(h, &g);
+    if (rc) return rc;
+    S.on = true;
+    S.rank = rank;
+    S.world = world;
+    S.halo_cap = halo_cap;
+    S.mig_cap = mig_cap;
+    S.nx_cfg = g.nx;
+    S.hrec = plife_slab_halo_records(g.nx, halo_cap);
+    S.mrec = plife_slab_migrate_records(mig_cap);
+    S.seq = 1;
+    if (bufs) { // external exchange: the host moves the messages between the phases
+        for (int d = 0; d < 2; d++) {
+            if (!bufs->halo_send[d] || !bufs->halo_recv[d] || !bufs->mig_send[d] || !bufs->mig_recv[d]) {
+                S.on = false;
+                return fail(h, PLIFE_ERR_INVALID, "slab_configure: NULL exchange buffer");
+            }
+            S.halo_send[d] = (float4 *)bufs->halo_send[d];
+            S.halo_recv[d] = (float4 *)bufs->halo_recv[d];
+            S.mig_send[d] = (float4 *)bufs->mig_send[d];
+            S.mig_recv[d] = (float4 *)bufs->mig_recv[d];
+        }
+        S.peer_mode = false;
+    } else { // peer exchange: library-owned buffers, neighbours connect with plife_slab_connect_*
+        S.peer_mode = true;
+        S.xrecords = kFlagRecords + 4 * S.hrec + 4 * S.mrec;
+        cudaError_t e = cudaMalloc((void **)&S.xbuf, (size_t)S.xrecords * 16);
+        for (int d = 0; d < 2 && e == cudaSuccess; d++) {
+            e = cudaMalloc((void **)&S.halo_send[d], (size_t)S.hrec * 16);
+            if (e == cudaSuccess) e = cudaMalloc((void **)&S.mig_send[d], (size_t)S.mrec * 16);
+        }
+        if (e == cudaSuccess) e = cudaMemset(S.xbuf, 0, (size_t)S.xrecords * 16);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            slab_release(h);
+            return fail(h, PLIFE_ERR_OOM, "slab_configure: allocating exchange buffers failed");
+        }
     }
-    h->slab.phase = PLIFE_SLAB_SORT;
+    S.phase = PLIFE_SLAB_SORT;
     h->prebinned = false;
+    return PLIFE_OK;
+}
+
+int plife_slab_export(plife_handle *h, void *ipc_handle_64_bytes)
+{
+    if (!h || !ipc_handle_64_bytes) return PLIFE_ERR_INVALID;
+    if (!h->slab.on || !h->slab.peer_mode) return fail(h, PLIFE_ERR_STATE, "slab_export: not in peer mode");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, PLIFE_ERR_CUDA, "cudaSetDevice");
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, h->slab.xbuf);
+    if (e != cudaSuccess) return fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e));
+    memcpy(ipc_handle_64_bytes, &hd, 64);
+    return PLIFE_OK;
+}
+
+// neighbours in other processes: the 64-byte handles they exported (NULL: no neighbour in that direction)
+int plife_slab_connect_ipc(plife_handle *h, const void *down_handle, const void *up_handle)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    SlabState &S = h->slab;
+    if (!S.on || !S.peer_mode) return fail(h, PLIFE_ERR_STATE, "slab_connect: not in peer mode");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, PLIFE_ERR_CUDA, "cudaSetDevice");
+    const void *hd[2] = {down_handle, up_handle};
+    for (int d = 0; d < 2; d++) {
+        if (!hd[d]) continue;
+        if (d == 1 && hd[0] && memcmp(hd[0], hd[1], 64) == 0) { // two ranks: both neighbours are the same peer
+            S.peer_base[1] = S.peer_base[0];
+            S.peer_ipc[1] = true;
+            continue;
+        }
+        cudaIpcMemHandle_t m;
+        memcpy(&m, hd[d], 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, m, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e));
+        S.peer_base[d] = (float4 *)p;
+        S.peer_ipc[d] = true;
+    }
+    return PLIFE_OK;
+}
+
+// neighbours that are handles of this process (virtual ranks on one device, or one process driving several GPUs
+// with peer access enabled)
+int plife_slab_connect_local(plife_handle *h, plife_handle *down, plife_handle *up)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    SlabState &S = h->slab;
+    if (!S.on || !S.peer_mode) return fail(h, PLIFE_ERR_STATE, "slab_connect: not in peer mode");
+    plife_handle *nb[2] = {down, up};
+    for (int d = 0; d < 2; d++) {
+        if (!nb[d]) continue;
+        if (!nb[d]->slab.on || !nb[d]->slab.peer_mode || nb[d]->slab.hrec != S.hrec || nb[d]->slab.mrec != S.mrec)
+            return fail(h, PLIFE_ERR_INVALID, "slab_connect_local: neighbour not configured identically");
+        S.peer_base[d] = nb[d]->slab.xbuf;
+        S.peer_ipc[d] = false;
+    }
     return PLIFE_OK;
 }
 
@@ -185,11 +364,22 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
     int rc = slab_make_grid(h, &g);
     if (rc) return rc;
     SlabState &S = h->slab;
+    if (g.nx > S.nx_cfg) return fail(h, PLIFE_ERR_STATE, "slab: rmax shrank since plife_slab_configure (halo messages would not fit): reconfigure");
     const bool wrap = h->settings.wrap != 0;
     const bool has_dn = S.world > 1 && (wrap || S.rank > 0);
     const bool has_up = S.world > 1 && (wrap || S.rank < S.world - 1);
+    if (S.peer_mode && ((has_dn && !S.peer_base[0]) || (has_up && !S.peer_base[1])))
+        return fail(h, PLIFE_ERR_STATE, "slab: neighbours not connected (plife_slab_connect_ipc / _local)");
     int *d_err = reinterpret_cast<int *>(h->d_scalar + 4);
     const int first = (int)S.halo_cap;
+    const int parity = (int)(S.seq & 1);
+    float4 *dn = S.peer_base[0], *up = S.peer_base[1];
+    // where this step's messages arrive
+    float4 *halo_in[2], *mig_in[2];
+    for (int d = 0; d < 2; d++) {
+        halo_in[d] = S.peer_mode ? halo_slot(S.xbuf, S, parity, d) : S.halo_recv[d];
+        mig_in[d] = S.peer_mode ? mig_slot(S.xbuf, S, parity, d) : S.mig_recv[d];
+    }
 
     if (phase == PLIFE_SLAB_SORT) {
         rc = slab_sort(h, g); // bin (if needed), scan, scatter, gather: owned block of the sorted array
@@ -198,32 +388,52 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         dim3 grid(32, 2);
         pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1]);
         zero_headers<<<1, 32, 0, h->stream>>>(S.mig_send[0], S.mig_send[1]);
+        if (S.peer_mode) {
+            // my first row is the down neighbour's ghost row ABOVE its slab (its slot dir 1), and vice versa
+            if (has_dn) push_msg<<<32, kThreads, 0, h->stream>>>(S.halo_send[0], halo_slot(dn, S, parity, 1), 1, g.nx, (int)S.halo_cap);
+            if (has_up) push_msg<<<32, kThreads, 0, h->stream>>>(S.halo_send[1], halo_slot(up, S, parity, 0), 1, g.nx, (int)S.halo_cap);
+            if (has_dn || has_up)
+                signal_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(dn, F_HALO_UP) : nullptr, has_up ? flag_of(up, F_HALO_DN) : nullptr, S.seq);
+        }
         CUS(h, cudaGetLastError());
         S.phase = PLIFE_SLAB_FORCE;
         return PLIFE_OK;
     }
     if (phase == PLIFE_SLAB_FORCE) {
         const int sorted = h->cur ^ 1;
+        if (S.peer_mode && (has_dn || has_up))
+            wait_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr, has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq, d_err);
         dim3 grid(32, 2);
         unpack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, first, (int)h->n,
-                                                      has_dn ? S.halo_recv[0] : nullptr, has_up ? S.halo_recv[1] : nullptr, d_err);
+                                                      has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr, d_err);
         CUS(h, cudaGetLastError());
         CUS(h, slab_force(h, g, dt));
+        if (S.peer_mode) {
+            if (has_dn) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[0], mig_slot(dn, S, parity, 1), 0, g.nx, (int)S.mig_cap);
+            if (has_up) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[1], mig_slot(up, S, parity, 0), 0, g.nx, (int)S.mig_cap);
+            if (has_dn || has_up)
+                signal_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(dn, F_MIG_UP) : nullptr, has_up ? flag_of(up, F_MIG_DN) : nullptr, S.seq);
+            CUS(h, cudaGetLastError());
+        }
         S.phase = PLIFE_SLAB_FINISH;
         return PLIFE_OK;
     }
     // PLIFE_SLAB_FINISH: headers back to the host (the only synchronisation of the step)
-    int4 hs[4];
+    if (S.peer_mode && (has_dn || has_up))
+        wait_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr, S.seq, d_err);
+    int4 hs[4] = {};
     int err = 0;
     CUS(h, cudaMemcpyAsync(&hs[0], S.mig_send[0], 16, cudaMemcpyDeviceToHost, h->stream));
     CUS(h, cudaMemcpyAsync(&hs[1], S.mig_send[1], 16, cudaMemcpyDeviceToHost, h->stream));
-    CUS(h, cudaMemcpyAsync(&hs[2], S.mig_recv[0], 16, cudaMemcpyDeviceToHost, h->stream));
-    CUS(h, cudaMemcpyAsync(&hs[3], S.mig_recv[1], 16, cudaMemcpyDeviceToHost, h->stream));
+    if (has_dn) CUS(h, cudaMemcpyAsync(&hs[2], mig_in[0], 16, cudaMemcpyDeviceToHost, h->stream));
+    if (has_up) CUS(h, cudaMemcpyAsync(&hs[3], mig_in[1], 16, cudaMemcpyDeviceToHost, h->stream));
     CUS(h, cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUS(h, cudaStreamSynchronize(h->stream));
     S.phase = PLIFE_SLAB_SORT;
+    S.seq++;
     const int sent_dn = hs[0].x, sent_up = hs[1].x;
     const int k_below = has_dn ? hs[2].x : 0, k_above = has_up ? hs[3].x : 0;
+    if (err >> 16) return fail(h, PLIFE_ERR_STATE, "slab: timed out waiting for a neighbour's message");
     if (err) return fail(h, PLIFE_ERR_STATE, "slab: halo overflow / grid mismatch between ranks / ownership mismatch (raise halo_cap)");
     if (hs[0].y || hs[1].y) return fail(h, PLIFE_ERR_STATE, "slab: a particle crossed more than one slab in one step");
     if ((!has_dn && sent_dn) || (!has_up && sent_up)) return fail(h, PLIFE_ERR_STATE, "slab: particle left through a closed boundary");
@@ -232,14 +442,13 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
     const int64_t L = h->n; // residents before this step (the force pass wrote slots [0, L))
     if (L + k_below + k_above > h->cap) return fail(h, PLIFE_ERR_OOM, "slab: particle capacity exceeded by arrivals");
     const int cur = h->cur;
-    int *d_err2 = d_err; // errors raised from here on are reported by the next FINISH
-    CUS(h, cudaMemsetAsync(d_err, 0, sizeof(int), h->stream));
+    CUS(h, cudaMemsetAsync(d_err, 0, sizeof(int), h->stream)); // errors raised from here on are reported by the next FINISH
     if (k_below > 0)
-        append_arrivals<<<(k_below + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(S.mig_recv[0], k_below, (int)L, g, h->s32[cur].pt,
-                                                                                      h->s32[cur].vel, h->d_cell, h->d_count, d_err2);
+        append_arrivals<<<(k_below + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(mig_in[0], k_below, (int)L, g, h->s32[cur].pt,
+                                                                                      h->s32[cur].vel, h->d_cell, h->d_count, d_err);
     if (k_above > 0)
-        append_arrivals<<<(k_above + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(S.mig_recv[1], k_above, (int)L + k_below, g,
-                                                                                      h->s32[cur].pt, h->s32[cur].vel, h->d_cell, h->d_count, d_err2);
+        append_arrivals<<<(k_above + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(mig_in[1], k_above, (int)L + k_below, g,
+                                                                                      h->s32[cur].pt, h->s32[cur].vel, h->d_cell, h->d_count, d_err);
     CUS(h, cudaGetLastError());
     S.n_old = L;
     S.k_below = k_below;
@@ -247,6 +456,21 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
     h->n_phys = L + k_below + k_above;
     h->n = L - sent_dn - sent_up + k_below + k_above;
     h->steps++;
+    return PLIFE_OK;
+}
+
+// all three phases back to back (peer mode only: nothing for the host to do in between)
+int plife_slab_step(plife_handle *h, double dt, int32_t nsteps)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (!h->slab.on || !h->slab.peer_mode) return fail(h, PLIFE_ERR_STATE, "plife_slab_step needs the peer exchange mode");
+    for (int s = 0; s < nsteps; s++) {
+        if (h->stop_requested.exchange(0)) return fail(h, PLIFE_ERR_STOPPED, "stopped");
+        for (int ph = PLIFE_SLAB_SORT; ph <= PLIFE_SLAB_FINISH; ph++) {
+            int rc = plife_slab_phase(h, ph, dt);
+            if (rc) return rc;
+        }
+    }
     return PLIFE_OK;
 }
 

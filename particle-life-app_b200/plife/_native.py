@@ -93,6 +93,10 @@ def lib() -> C.CDLL:
         "plife_slab_configure": (C.c_int, [vp, i32, i32, i64, i64, C.POINTER(SlabBuffers)]),
         "plife_slab_rows": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "plife_slab_phase": (C.c_int, [vp, i32, dbl]),
+        "plife_slab_step": (C.c_int, [vp, dbl, i32]),
+        "plife_slab_export": (C.c_int, [vp, vp]),
+        "plife_slab_connect_ipc": (C.c_int, [vp, vp, vp]),
+        "plife_slab_connect_local": (C.c_int, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

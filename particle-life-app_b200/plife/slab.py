@@ -71,7 +71,7 @@ class DistExchange:
     def __init__(self, rank: int, world: int, group=None):
         self.rank, self.world, self.group = rank, world, group
 
-    def exchange(self, send: Sequence, recv: Sequence, wrap: bool):
+    def exchange(self, send: Sequence, recv: Sequence, wrap: bool, what: str = ""):
         import torch.distributed as dist
         dn, up = neighbours(self.rank, self.world, wrap)
         ops = []
@@ -108,20 +108,28 @@ class LocalExchange:
 # ---------------------------------------------------------------------------
 
 class SlabPhysics:
-    """One rank of the slab-decomposed simulation: a libplife handle in slab mode plus its
-    exchange buffers (torch tensors: torch is the plumbing for device memory and NCCL)."""
+    """One rank of the slab-decomposed simulation: a libplife handle in slab mode.
+
+    exchange="peer" (default): the library owns the message buffers and pushes halos / migrants straight
+    into the neighbours' buffers over NVLink (CUDA IPC); `connect_dist` distributes the IPC handles once
+    (torch.distributed is only the plumbing for that) and a step is a single C call.
+    exchange="nccl": the messages live in torch tensors and are exchanged with NCCL send/recv between the
+    phases (`DistExchange`)."""
 
     def __init__(self, rank: int, world: int, rmax: float, *, device: int = 0, capacity: int, halo_cap: int,
-                 mig_cap: int, friction=0.85, force=1.0, wrap=True, stream=None, flags: int = 0):
-        import torch
+                 mig_cap: int, friction=0.85, force=1.0, wrap=True, stream=None, flags: int = 0, exchange: str = "peer"):
         from . import NativePhysics
-        self.torch = torch
-        self.rank, self.world, self.wrap = rank, world, wrap
-        self.dev = torch.device("cuda", device)
+        self.rank, self.world, self.wrap, self.exchange_mode = rank, world, wrap, exchange
         self.native = NativePhysics(device=device, precision=N.F32, capacity=capacity, flags=flags, stream=stream)
         self.native.set_settings(rmax, friction, force, wrap)
         self.rmax = rmax
         L = self.native.L
+        if exchange == "peer":
+            self.native._check(L.plife_slab_configure(self.native.h, rank, world, halo_cap, mig_cap, None))
+            return
+        import torch
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
         nx = grid_rows(rmax)
         hrec = int(L.plife_slab_halo_records(nx, halo_cap))
         mrec = int(L.plife_slab_migrate_records(mig_cap))
@@ -139,6 +147,25 @@ class SlabPhysics:
         self._bufs = b
         self.native._check(L.plife_slab_configure(self.native.h, rank, world, halo_cap, mig_cap, C.byref(b)))
 
+    # -- peer exchange wiring --
+    def export_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.native._check(self.native.L.plife_slab_export(self.native.h, buf))
+        return buf.raw
+
+    def connect_ipc(self, down: Optional[bytes], up: Optional[bytes]):
+        self._ipc = (C.create_string_buffer(down, 64) if down else None, C.create_string_buffer(up, 64) if up else None)
+        self.native._check(self.native.L.plife_slab_connect_ipc(self.native.h, self._ipc[0], self._ipc[1]))
+
+    def connect_dist(self, group=None):
+        """All-gather the IPC handles over torch.distributed and map the two ring neighbours."""
+        import torch.distributed as dist
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.export_handle(), group=group)
+        dn, up = neighbours(self.rank, self.world, True)  # map both ring neighbours; closed boundaries just never use them
+        self.connect_ipc(handles[dn] if dn is not None else None, handles[up] if up is not None else None)
+        dist.barrier(group=group)
+
     def rows(self):
         lo, hi, nx = C.c_int32(), C.c_int32(), C.c_int32()
         self.native._check(self.native.L.plife_slab_rows(self.native.h, C.byref(lo), C.byref(hi), C.byref(nx)))
@@ -147,12 +174,15 @@ class SlabPhysics:
     def phase(self, which: int, dt: float):
         self.native._check(self.native.L.plife_slab_phase(self.native.h, which, dt))
 
-    def step(self, dt: float, exchange: DistExchange, nsteps: int = 1):
+    def step(self, dt: float, exchange: Optional[DistExchange] = None, nsteps: int = 1):
+        if self.exchange_mode == "peer":
+            self.native._check(self.native.L.plife_slab_step(self.native.h, dt, nsteps))
+            return
         for _ in range(nsteps):
             self.phase(N.SLAB_SORT, dt)
-            exchange.exchange(self.halo_send, self.halo_recv, self.wrap)
+            exchange.exchange(self.halo_send, self.halo_recv, self.wrap, "halo")
             self.phase(N.SLAB_FORCE, dt)
-            exchange.exchange(self.mig_send, self.mig_recv, self.wrap)
+            exchange.exchange(self.mig_send, self.mig_recv, self.wrap, "mig")
             self.phase(N.SLAB_FINISH, dt)
 
     @property
@@ -164,14 +194,20 @@ class VirtualCluster:
     """`world` slabs driven in lockstep inside one process on one device."""
 
     def __init__(self, world: int, rmax: float, matrix, *, device: int = 0, capacity: int, halo_cap: int, mig_cap: int,
-                 wrap=True, friction=0.85, force=1.0, accelerator=(0, ())):
-        self.world, self.wrap, self.rmax = world, wrap, rmax
+                 wrap=True, friction=0.85, force=1.0, accelerator=(0, ()), exchange: str = "peer"):
+        self.world, self.wrap, self.rmax, self.exchange_mode = world, wrap, rmax, exchange
         self.slabs = [SlabPhysics(r, world, rmax, device=device, capacity=capacity, halo_cap=halo_cap, mig_cap=mig_cap,
-                                  wrap=wrap, friction=friction, force=force) for r in range(world)]
+                                  wrap=wrap, friction=friction, force=force, exchange=exchange) for r in range(world)]
         for s in self.slabs:
             s.native.set_matrix(matrix)
             s.native.set_accelerator(accelerator[0], accelerator[1])
         self.ex = LocalExchange(world)
+        if exchange == "peer":
+            for r, s in enumerate(self.slabs):
+                dn, up = neighbours(r, world, True)
+                s.native._check(s.native.L.plife_slab_connect_local(
+                    s.native.h, self.slabs[dn].native.h if dn is not None else None,
+                    self.slabs[up].native.h if up is not None else None))
 
     def upload(self, pos, vel, types, ids=None):
         pos = np.asarray(pos, np.float64).reshape(-1, 2)
@@ -184,6 +220,14 @@ class VirtualCluster:
             s.native.upload(pos[k], vel[k], np.asarray(types)[k], ids[k])
 
     def step(self, dt: float, nsteps: int = 1):
+        if self.exchange_mode == "peer":
+            # lockstep over the virtual ranks: every phase is enqueued on all handles before the next one,
+            # so a rank spinning on a neighbour's flag always finds the producer already queued
+            for _ in range(nsteps):
+                for ph in (N.SLAB_SORT, N.SLAB_FORCE, N.SLAB_FINISH):
+                    for s in self.slabs:
+                        s.phase(ph, dt)
+            return
         for _ in range(nsteps):
             for s in self.slabs:
                 s.phase(N.SLAB_SORT, dt)
@@ -200,9 +244,10 @@ class VirtualCluster:
 
     def _sync(self):
         # the handles run on their own streams; the copies run on torch's current stream
+        import torch
         for s in self.slabs:
             s.native.sync()
-        self.slabs[0].torch.cuda.synchronize()
+        torch.cuda.synchronize()
 
     def download(self):
         """Concatenation of the slabs in rank order == the single-GPU particle order."""

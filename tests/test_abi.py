@@ -77,3 +77,23 @@ def test_synth_generators_are_deterministic_and_in_range():
         nx = int(np.floor(1.0 / c["rmax"]))
         assert nx >= 25
     assert int(np.floor(1.0 / synth.CONFIGS["C4"]["rmax"])) == 2800
+
+
+def test_every_kernel_lives_in_exactly_one_object():
+    """force_f64.cu is compiled with -fmad=false.  A kernel instantiated in two translation units with
+    different flags yields two device images under one name, and which one a launch binds to varies from
+    process to process (1-ulp irreproducibility).  Guard: no kernel entry point appears in two objects."""
+    import glob
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    objs = sorted(glob.glob(os.path.join(ROOT, "particle-life-app_b200", "csrc", "_obj", "*.o")))
+    if not objs or not os.path.exists(cuobjdump):
+        pytest.skip("objects or cuobjdump not available")
+    seen = {}
+    for o in objs:
+        out = subprocess.run([cuobjdump, "-elf", o], capture_output=True, text=True).stdout
+        for k in set(re.findall(r"\.text\.(_Z\w+)", out)):
+            assert k not in seen, f"kernel {k} is compiled in both {seen[k]} and {os.path.basename(o)}"
+            seen[k] = os.path.basename(o)
+    assert any("force_kernel_staged" in k for k in seen)

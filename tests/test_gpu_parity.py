@@ -235,9 +235,10 @@ def test_unstable_sort_flag_same_sets(native_lib):
 # slab decomposition on ONE GPU: virtual ranks exchanging through device copies
 # ---------------------------------------------------------------------------
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"], ids=["peer", "external"])
 @pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("wrap", [True, False], ids=["wrap", "clamp"])
-def test_virtual_slabs_match_single_gpu(native_lib, world, wrap):
+def test_virtual_slabs_match_single_gpu(native_lib, world, wrap, exchange):
     """G slabs with halo exchange + migration reproduce the single-GPU state: same particles, same order
     (slabs concatenated in rank order), same values; the particles really migrate between slabs."""
     from plife.slab import VirtualCluster
@@ -247,7 +248,7 @@ def test_virtual_slabs_match_single_gpu(native_lib, world, wrap):
     single.set_settings(rmax, 0.85, 1.0, wrap)
     single.set_matrix(matrix)
     single.upload(pos, vel, types)
-    vc = VirtualCluster(world, rmax, matrix, capacity=n, halo_cap=4096, mig_cap=4096, wrap=wrap)
+    vc = VirtualCluster(world, rmax, matrix, capacity=n, halo_cap=4096, mig_cap=4096, wrap=wrap, exchange=exchange)
     vc.upload(pos, vel, types)
     start_counts = vc.counts()
     assert sum(start_counts) == n
