@@ -43,47 +43,53 @@ __global__ void __launch_bounds__(kThreads) bin_f64(const double2 *__restrict__ 
 }
 
 // ---- exclusive scan over cells: tile sums -> scan of sums -> apply ----
+// One pass scans two quantities packed into 64 bits: the particle count of a cell (low word ->
+// cell_end, the reference's `containers`) and its number of target PAIRS ceil(count/2) (high word ->
+// pair_start, used by the two-targets-per-lane force kernel).
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems; // 4096 cells per CTA
+using u64 = unsigned long long;
 
-__device__ __forceinline__ int warp_inclusive_scan(int v, int lane)
+__device__ __forceinline__ u64 pack_count(int c) { return (u64)(unsigned)c | ((u64)(unsigned)((c + 1) >> 1) << 32); }
+
+__device__ __forceinline__ u64 warp_inclusive_scan(u64 v, int lane)
 {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, o);
+        u64 t = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o) v += t;
     }
     return v;
 }
 
-// block-wide exclusive scan of one int per thread; returns the exclusive prefix and the block total
-__device__ __forceinline__ int block_exclusive_scan(int v, int &total, int *smem /* >= 33 ints */)
+// block-wide exclusive scan of one value per thread; returns the exclusive prefix and the block total
+__device__ __forceinline__ u64 block_exclusive_scan(u64 v, u64 &total, u64 *smem /* >= 33 */)
 {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = warp_inclusive_scan(v, lane);
+    u64 inc = warp_inclusive_scan(v, lane);
     if (lane == 31) smem[warp] = inc;
     __syncthreads();
     if (warp == 0) {
         int nw = (blockDim.x + 31) >> 5;
-        int w = lane < nw ? smem[lane] : 0;
-        int winc = warp_inclusive_scan(w, lane);
+        u64 w = lane < nw ? smem[lane] : 0;
+        u64 winc = warp_inclusive_scan(w, lane);
         smem[lane] = winc - w;
         if (lane == 31) smem[32] = winc;
     }
     __syncthreads();
-    int r = smem[warp] + inc - v;
+    u64 r = smem[warp] + inc - v;
     total = smem[32];
     __syncthreads();
     return r;
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *__restrict__ count, int64_t ncell,
-                                                               int32_t *__restrict__ tile_sums)
+                                                               u64 *__restrict__ tile_sums)
 {
-    __shared__ int sm[33];
+    __shared__ u64 sm[33];
     int64_t base = (int64_t)blockIdx.x * kScanTile;
-    int s = 0;
+    u64 s = 0;
     // vectorised: each thread sums 16 consecutive cells (4 x int4)
     int64_t first = base + (int64_t)threadIdx.x * kScanItems;
     if (first + kScanItems <= ncell) {
@@ -91,44 +97,45 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *__
 #pragma unroll
         for (int k = 0; k < kScanItems / 4; k++) {
             int4 v = __ldg(p + k);
-            s += v.x + v.y + v.z + v.w;
+            s += pack_count(v.x) + pack_count(v.y) + pack_count(v.z) + pack_count(v.w);
         }
     } else {
         for (int k = 0; k < kScanItems; k++)
-            if (first + k < ncell) s += count[first + k];
+            if (first + k < ncell) s += pack_count(count[first + k]);
     }
-    int total;
+    u64 total;
     block_exclusive_scan(s, total, sm);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) scan_sums(int32_t *__restrict__ tile_sums, int ntiles, int carry0,
-                                                  int32_t *__restrict__ cell_end)
+__global__ void __launch_bounds__(1024) scan_sums(u64 *__restrict__ tile_sums, int ntiles, int carry0,
+                                                  int32_t *__restrict__ cell_end, int32_t *__restrict__ npairs)
 {
-    __shared__ int sm[33];
-    int carry = carry0;
+    __shared__ u64 sm[33];
+    u64 carry = (u64)(unsigned)carry0; // particle offsets start after the ghost-below capacity; pairs at 0
     if (threadIdx.x == 0) cell_end[-1] = carry0; // start of local cell 0
     for (int base = 0; base < ntiles; base += 1024) {
         int i = base + threadIdx.x;
-        int v = i < ntiles ? tile_sums[i] : 0;
-        int total;
-        int ex = block_exclusive_scan(v, total, sm);
+        u64 v = i < ntiles ? tile_sums[i] : 0;
+        u64 total;
+        u64 ex = block_exclusive_scan(v, total, sm);
         if (i < ntiles) tile_sums[i] = carry + ex;
         carry += total;
     }
+    if (threadIdx.x == 0) *npairs = (int32_t)(carry >> 32);
 }
 
-// writes the exclusive prefix (the cursor start of every cell) into cell_end and
+// writes the exclusive prefixes (the cursor start of every cell, the first pair of every cell) and
 // zeroes count for the next step
 __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__ count, int64_t ncell,
-                                                           const int32_t *__restrict__ tile_sums,
-                                                           int32_t *__restrict__ cell_end)
+                                                           const u64 *__restrict__ tile_sums,
+                                                           int32_t *__restrict__ cell_end, int32_t *__restrict__ pair_start)
 {
-    __shared__ int sm[33];
+    __shared__ u64 sm[33];
     int64_t base = (int64_t)blockIdx.x * kScanTile;
     int64_t first = base + (int64_t)threadIdx.x * kScanItems;
     int v[kScanItems];
-    int s = 0;
+    u64 s = 0;
     bool full = first + kScanItems <= ncell;
     if (full) {
         int4 *p = reinterpret_cast<int4 *>(count + first);
@@ -149,25 +156,30 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
         }
     }
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) s += v[k];
-    int total;
-    int ex = block_exclusive_scan(s, total, sm) + tile_sums[blockIdx.x];
+    for (int k = 0; k < kScanItems; k++) s += pack_count(v[k]);
+    u64 total;
+    u64 ex = block_exclusive_scan(s, total, sm) + tile_sums[blockIdx.x];
     if (full) {
         int4 *o = reinterpret_cast<int4 *>(cell_end + first);
+        int4 *po = reinterpret_cast<int4 *>(pair_start + first);
 #pragma unroll
         for (int k = 0; k < kScanItems / 4; k++) {
-            int4 q;
-            q.x = ex; ex += v[4 * k];
-            q.y = ex; ex += v[4 * k + 1];
-            q.z = ex; ex += v[4 * k + 2];
-            q.w = ex; ex += v[4 * k + 3];
+            int4 q, r;
+            q.x = (int)ex; r.x = (int)(ex >> 32); ex += pack_count(v[4 * k]);
+            q.y = (int)ex; r.y = (int)(ex >> 32); ex += pack_count(v[4 * k + 1]);
+            q.z = (int)ex; r.z = (int)(ex >> 32); ex += pack_count(v[4 * k + 2]);
+            q.w = (int)ex; r.w = (int)(ex >> 32); ex += pack_count(v[4 * k + 3]);
             o[k] = q;
+            po[k] = r;
         }
     } else {
 #pragma unroll
         for (int k = 0; k < kScanItems; k++) {
-            if (first + k < ncell) cell_end[first + k] = ex;
-            ex += v[k];
+            if (first + k < ncell) {
+                cell_end[first + k] = (int)ex;
+                pair_start[first + k] = (int)(ex >> 32);
+            }
+            ex += pack_count(v[k]);
         }
     }
 }
@@ -202,14 +214,23 @@ struct StableKey {
     }
 };
 
-__device__ __forceinline__ int stable_slot(int src, int c, const int32_t *__restrict__ cell_end,
-                                           const int32_t *__restrict__ perm, int first, StableKey key)
+// slot of `src` in the sorted array; also registers the leader (even rank) of every target pair of the cell
+template <bool STABLE>
+__device__ __forceinline__ int sorted_slot(int d, int src, int c, const int32_t *__restrict__ cell_end,
+                                           const int32_t *__restrict__ perm, int first, StableKey key,
+                                           const int32_t *__restrict__ pair_start, int32_t *__restrict__ pair_first)
 {
-    int s = __ldg(&cell_end[c - 1]);
-    int e = __ldg(&cell_end[c]);
-    int rank = 0;
-    const int ksrc = key(src);
-    for (int k = s; k < e; k++) rank += (key(__ldg(&perm[k - first])) < ksrc) ? 1 : 0;
+    const int s = __ldg(&cell_end[c - 1]);
+    int rank;
+    if (STABLE) {
+        const int e = __ldg(&cell_end[c]);
+        rank = 0;
+        const int ksrc = key(src);
+        for (int k = s; k < e; k++) rank += (key(__ldg(&perm[k - first])) < ksrc) ? 1 : 0;
+    } else {
+        rank = d + first - s;
+    }
+    if (pair_first && (rank & 1) == 0) pair_first[__ldg(&pair_start[c]) + (rank >> 1)] = s + rank - first;
     return s + rank;
 }
 
@@ -218,7 +239,8 @@ __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict_
                                                        float4 *__restrict__ pt_out, float2 *__restrict__ vel_out, int n, Grid g,
                                                        int first, StableKey key, const int32_t *__restrict__ cell,
                                                        int32_t *__restrict__ cell_sorted, const int32_t *__restrict__ cell_end,
-                                                       const int32_t *__restrict__ perm)
+                                                       const int32_t *__restrict__ perm, const int32_t *__restrict__ pair_start,
+                                                       int32_t *__restrict__ pair_first)
 {
     int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= n) return;
@@ -226,7 +248,7 @@ __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict_
     float4 p = __ldg(&pt_in[src]);
     float2 v = __ldg(&vel_in[src]);
     int cxy = __ldg(&cell[src]);
-    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm, first, key) : d + first;
+    int dst = sorted_slot<STABLE>(d, src, container_of(cxy, g), cell_end, perm, first, key, pair_start, pair_first);
     pt_out[dst] = p; // sorted positions carry the ghost-below offset `first`; per-target arrays do not
     vel_out[dst - first] = v;
     cell_sorted[dst - first] = cxy;
@@ -235,7 +257,8 @@ __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict_
 template <bool STABLE>
 __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out, int n, Grid g, const int32_t *__restrict__ cell,
                                                        int32_t *__restrict__ cell_sorted, const int32_t *__restrict__ cell_end,
-                                                       const int32_t *__restrict__ perm)
+                                                       const int32_t *__restrict__ perm, const int32_t *__restrict__ pair_start,
+                                                       int32_t *__restrict__ pair_first)
 {
     int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= n) return;
@@ -245,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out
     int t = __ldg(&in.type[src]);
     uint32_t id = __ldg(&in.id[src]);
     int cxy = __ldg(&cell[src]);
-    int dst = STABLE ? stable_slot(src, container_of(cxy, g), cell_end, perm, 0, StableKey{0x7fffffff, 0, 0, 0, 0}) : d;
+    int dst = sorted_slot<STABLE>(d, src, container_of(cxy, g), cell_end, perm, 0, StableKey{0x7fffffff, 0, 0, 0, 0}, pair_start, pair_first);
     cell_sorted[dst] = cxy;
     out.pos[dst] = p;
     out.vel[dst] = v;
@@ -360,6 +383,7 @@ __global__ void __launch_bounds__(kThreads) snapshot_from_f64(StateF64 s, int n,
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 inline int first_index(const plife_handle *h) { return h->slab.on ? (int)h->slab.halo_cap : 0; }
+inline int32_t *npairs_ptr(plife_handle *h) { return reinterpret_cast<int32_t *>(h->d_scalar + 7); }
 
 } // namespace
 
@@ -378,9 +402,10 @@ cudaError_t launch_scan(plife_handle *h, const Grid &g)
 {
     int64_t ncell = (int64_t)g.nx * g.nly;
     int ntiles = (int)((ncell + kScanTile - 1) / kScanTile);
-    scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, h->d_tile_sums);
-    scan_sums<<<1, 1024, 0, h->stream>>>(h->d_tile_sums, ntiles, first_index(h), h->d_cell_end);
-    scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, h->d_tile_sums, h->d_cell_end);
+    u64 *ts = reinterpret_cast<u64 *>(h->d_tile_sums);
+    scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts);
+    scan_sums<<<1, 1024, 0, h->stream>>>(ts, ntiles, first_index(h), h->d_cell_end, npairs_ptr(h));
+    scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts, h->d_cell_end, h->d_pair_start);
     return cudaGetLastError();
 }
 
@@ -399,6 +424,7 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
     int a = h->cur, b = h->cur ^ 1;
     bool stable = !(h->flags & PLIFE_FLAG_UNSTABLE_SORT);
     int nb = blocks_for(n, kThreads);
+    int32_t *pf = (h->flags & PLIFE_FLAG_PAIRS) ? h->d_pair_first : nullptr; // only the opt-in pairs kernel needs it
     StableKey key{0x7fffffff, 0, 0, 0, 0};
     if (h->slab.on) {
         const SlabState &S = h->slab;
@@ -411,15 +437,15 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
     if (h->precision == PLIFE_F32) {
         if (stable)
             gather_f32<true><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
-                                                             first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
+                                                             first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, pf);
         else
             gather_f32<false><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
-                                                              first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
+                                                              first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, pf);
     } else {
         if (stable)
-            gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
+            gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, nullptr);
         else
-            gather_f64<false><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
+            gather_f64<false><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, nullptr);
     }
     return cudaGetLastError();
 }

@@ -23,10 +23,22 @@ cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
 {
     const float *mt = (const float *)h->d_matrix_t;
     const float *mrow = mt + (size_t)p.m * p.m; // row-major copy follows the transposed one
+    const double rho = (double)p.n / ((double)p.g.nx * (p.g.row_hi - p.g.row_lo)); // particles per owned cell
+    // v3: two targets per lane.  Opt-in: on B200 it executes 6 % fewer instructions than v2 but its 36 KB of
+    // shared memory per CTA caps occupancy at 24 warps/SM and it ends up 3 % slower (profiles/r1_force_kernel.md).
+    if ((h->flags & PLIFE_FLAG_PAIRS) && h->acc_kind == PLIFE_ACC_PARTICLE_LIFE && p.m <= 16 && rho >= 2.0) {
+        int cap = (int)(2 * kForceThreads + 4.0 * rho + 10.0 * sqrt(rho + 1.0) + 32.0);
+        cap = (cap + 31) / 32 * 32;
+        if (cap <= 1280) {
+            const int64_t ncell = (int64_t)p.g.nx * (p.g.row_hi - p.g.row_lo);
+            const int max_pairs = (int)((p.n + (p.n < ncell ? p.n : ncell)) / 2 + 1);
+            return launch_force_pairs(make_io(h), h->d_cell_end, h->d_cell_sorted, h->d_pair_first,
+                                      reinterpret_cast<const int32_t *>(h->d_scalar + 7), max_pairs, p, mrow, cap, next_bin(h), h->stream);
+        }
+    }
     // v2 staged kernel whenever the per-lane matrix table fits; v1 (global-memory walk) otherwise
     if (p.m <= kTabMaxM && !(h->flags & PLIFE_FLAG_FORCE_V1)) {
         // capacity of one staged row range: 128 targets + the cells hanging over both ends + margin
-        const double rho = (double)p.n / ((double)p.g.nx * (p.g.row_hi - p.g.row_lo)); // particles per owned cell
         int cap = (int)(kForceThreads + 4.0 * rho + 8.0 * sqrt(rho + 1.0) + 32.0);
         cap = (cap + 31) / 32 * 32;
         if (cap > 1536) cap = 1536;

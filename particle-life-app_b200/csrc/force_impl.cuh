@@ -487,7 +487,7 @@ __device__ __forceinline__ float4 lds128(uint32_t a)
     return v;
 }
 
-template <typename V>
+template <int KEYSHIFT = kTabShift, typename V>
 __device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g,
                                                 int wrap, int i, float xi, float yi, int cxy, bool staged_ok,
                                                 uint32_t stage_addr, int cap, const int *s_start, V &v)
@@ -529,7 +529,7 @@ __device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *
             for (int j = s; j < e; ++j) {
                 if (j == i) continue;
                 Cand<float> q = io.cand(j);
-                q.type <<= kTabShift;
+                q.type <<= KEYSHIFT;
                 float dx, dy;
                 if (wrap) {
                     dx = wrap_connection(xi, q.x);
@@ -677,6 +677,190 @@ inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_en
     default: return cudaErrorInvalidValue;
     }
 #undef PLIFE_LAUNCH_STAGED
+    return cudaGetLastError();
+}
+
+// ---- v3: two targets per lane (fp32, accelerator kind 0) -----------------------------------
+// The v2 inner loop is limited by issue slots AND the L1 data pipe (LDS.128 + LDS.32 per pair
+// evaluation, profiles/r1_force_kernel.md).  Targets of one cell share their candidate list, so a
+// lane that owns TWO targets of the same cell amortises the candidate load, the address arithmetic
+// and the loop control over two pair evaluations, and fetches both matrix coefficients with one
+// conflict-free LDS.64 from a [type][thread] table of float2.  Pairs never straddle cells: the scan
+// produces pair_start[cell] = prefix of ceil(count/2) and the gather registers the even-ranked particle
+// of every pair (pair_first); an odd cell leaves the second slot of its last lane idle.
+constexpr int kPairShift = 10; // lane-table row stride: kForceThreads * sizeof(float2)
+
+__device__ __forceinline__ float2 lds64(uint32_t a)
+{
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+
+struct FastPair32 {
+    float ax0, ay0, ax1, ay1;
+    float x0, y0, x1, y1;
+    float b, d0, h;
+    uint32_t row; // shared address of tab2[0][thread]
+    __device__ __forceinline__ void one(float a, float dx, float dy, float &ax, float &ay) const
+    {
+        float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
+        float rinv = rsqrt_fast(d2);
+        float d = d2 * rinv;
+        float rep = fminf(d - b, 0.0f);
+        float att = fmaxf(h - fabsf(d - d0), 0.0f);
+        float g = fmaf(a, att, rep) * rinv;
+        ax = fmaf(g, dx, ax);
+        ay = fmaf(g, dy, ay);
+    }
+    __device__ __forceinline__ void cand(const float4 &q)
+    {
+        const float2 a = lds64(row + (uint32_t)__float_as_int(q.z));
+        one(a.x, q.x - x0, q.y - y0, ax0, ay0);
+        one(a.y, q.x - x1, q.y - y1, ax1, ay1);
+    }
+};
+
+__global__ void __launch_bounds__(kForceThreads) force_kernel_pairs(IOF32 io, const int32_t *__restrict__ cell_end,
+                                                                   const int32_t *__restrict__ cell_sorted,
+                                                                   const int32_t *__restrict__ pair_first,
+                                                                   const int32_t *__restrict__ npairs, ForceParams<float> P,
+                                                                   const float *__restrict__ gM, int cap, NextBin nb)
+{
+    static_assert(kForceThreads * 8 == (1 << kPairShift), "pair-table row stride");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                                 // [3][cap + kStagePad]
+    float2 *tab2 = reinterpret_cast<float2 *>(smem_raw + (size_t)3 * (cap + kStagePad) * 16); // [m][kForceThreads]
+    __shared__ int s_cell[2], s_start[3], s_len[3];
+
+    const int np = __ldg(npairs);
+    if ((int)(blockIdx.x * kForceThreads) >= np) return; // whole CTA beyond the last pair
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * kForceThreads + tid;
+    const bool valid = t < np;
+    const Grid g = P.g;
+    Cand<float> s0{0.f, 0.f, 0, 0u}, s1{0.f, 0.f, 0, 0u};
+    int i0 = 0, cxy = 0, cxy1 = 0;
+    bool has2 = false;
+    if (valid) {
+        i0 = __ldg(pair_first + t);
+        cxy = __ldg(cell_sorted + i0);
+        const int c = container_of(cxy, g);
+        has2 = P.first + i0 + 1 < __ldg(cell_end + c);
+        s0 = io.cand(P.first + i0);
+        s1 = has2 ? io.cand(P.first + i0 + 1) : s0;
+        // same container, but the un-clamped cell coords can differ in the fat last cell (x or y == nx*rmax..1)
+        cxy1 = has2 ? __ldg(cell_sorted + i0 + 1) : cxy;
+        if (tid == 0) s_cell[0] = c;
+        if (tid == kForceThreads - 1 || t == np - 1) s_cell[1] = c;
+    }
+    {
+        const float *r0 = gM + s0.type * P.m, *r1 = gM + s1.type * P.m;
+        for (int k = 0; k < P.m; ++k) tab2[k * kForceThreads + tid] = make_float2(__ldg(r0 + k) * P.fast_a_scale, __ldg(r1 + k) * P.fast_a_scale);
+    }
+    __syncthreads();
+    if (tid < 3) {
+        const int ncell = g.nx * g.nly;
+        int lo = s_cell[0] + (tid - 1) * g.nx - 1;
+        int hi = s_cell[1] + (tid - 1) * g.nx + 1;
+        lo = max(lo, 0);
+        hi = min(hi, ncell - 1);
+        int start = 0, len = 0;
+        if (lo <= hi) {
+            start = __ldg(cell_end + lo - 1);
+            len = __ldg(cell_end + hi) - start;
+        }
+        s_start[tid] = start;
+        s_len[tid] = len;
+    }
+    __syncthreads();
+    const bool staged_ok = s_len[0] <= cap && s_len[1] <= cap && s_len[2] <= cap;
+    if (staged_ok) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int len = s_len[r];
+            const float4 *src = io.pt + s_start[r];
+            float4 *dst = stage + r * (cap + kStagePad);
+            for (int k = tid; k < len + kStagePad; k += kForceThreads) {
+                float4 q = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
+                if (k < len) {
+                    q = __ldg(src + k);
+                    q.z = __int_as_float(__float_as_int(q.z) << kPairShift);
+                }
+                dst[k] = q;
+            }
+        }
+    }
+    __syncthreads();
+    if (!valid) return;
+
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t row = (uint32_t)__cvta_generic_to_shared(tab2 + tid);
+    const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
+    const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2 && cxy1 == cxy;
+    float ax0, ay0, ax1, ay1;
+    if (interior && staged_ok) {
+        FastPair32 v{0.f, 0.f, 0.f, 0.f, s0.x, s0.y, s1.x, s1.y, P.fast_b, P.fast_d0, P.fast_h, row};
+        const int base0 = (cy0 + g.ly_shift - 1) * g.nx + cx0;
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+            const int base = base0 + r * g.nx;
+            const int s = __ldg(cell_end + base - 2);
+            const int e = __ldg(cell_end + base + 1);
+            uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s - s_start[r]) * 16u;
+            const uint32_t a1 = a + (uint32_t)(e - s) * 16u;
+            for (; a < a1; a += 64u) { // 4 candidates per trip, padded like v2
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v.cand(lds128(a + 16u * u));
+            }
+        }
+        ax0 = v.ax0; ay0 = v.ay0; ax1 = v.ax1; ay1 = v.ay1;
+    } else { // seam lanes / oversized ranges: the literal walk, one target after the other
+        MatrixView<float, kMatLaneTab> M{nullptr, nullptr, P.m, 0, 1.0f, row, 0u};
+        FastParticleLife32<kMatLaneTab> v0{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        traverse_staged<kPairShift>(io, cell_end, g, P.wrap, P.first + i0, s0.x, s0.y, cxy, false, stage_addr, cap, s_start, v0);
+        ax0 = v0.ax; ay0 = v0.ay;
+        ax1 = ay1 = 0.f;
+        if (has2) {
+            M.row = row + 4u;
+            FastParticleLife32<kMatLaneTab> v1{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+            traverse_staged<kPairShift>(io, cell_end, g, P.wrap, P.first + i0 + 1, s1.x, s1.y, cxy1, false, stage_addr, cap, s_start, v1);
+            ax1 = v1.ax; ay1 = v1.ay;
+        }
+    }
+    auto finish = [&](int i, const Cand<float> &self, float ax, float ay) {
+        float vx, vy;
+        io.self_vel(i, vx, vy);
+        const float nvx = fmaf(P.fast_k, ax, vx * P.mu);
+        const float nvy = fmaf(P.fast_k, ay, vy * P.mu);
+        float nx_ = fmaf(nvx, P.dt, self.x);
+        float ny_ = fmaf(nvy, P.dt, self.y);
+        if (P.wrap) {
+            nx_ = range_wrap(nx_);
+            ny_ = range_wrap(ny_);
+        } else {
+            nx_ = range_clamp(nx_);
+            ny_ = range_clamp(ny_);
+        }
+        io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
+        nb.add(i, nx_, ny_, nvx, nvy, self.type, self.id, g);
+    };
+    finish(i0, s0, ax0, ay0);
+    if (has2) finish(i0 + 1, s1, ax1, ay1);
+}
+
+inline cudaError_t launch_force_pairs(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted, const int32_t *pair_first,
+                                      const int32_t *npairs, int max_pairs, const ForceParams<float> &P, const float *gM, int cap,
+                                      NextBin nbin, cudaStream_t stream)
+{
+    if (P.n == 0) return cudaSuccess;
+    const int nb = (max_pairs + kForceThreads - 1) / kForceThreads;
+    const size_t sbytes = (size_t)3 * (cap + kStagePad) * 16 + (size_t)P.m * kForceThreads * 8;
+    if (sbytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(force_kernel_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
+        if (e != cudaSuccess) return e;
+    }
+    force_kernel_pairs<<<nb, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, pair_first, npairs, P, gM, cap, nbin);
     return cudaGetLastError();
 }
 

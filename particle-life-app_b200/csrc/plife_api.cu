@@ -71,7 +71,8 @@ void free_state(plife_handle *h)
     cudaFree(h->d_cell);
     cudaFree(h->d_cell_sorted);
     cudaFree(h->d_perm);
-    h->d_cell = h->d_cell_sorted = h->d_perm = nullptr;
+    cudaFree(h->d_pair_first);
+    h->d_cell = h->d_cell_sorted = h->d_perm = h->d_pair_first = nullptr;
     h->cap = 0;
     h->prebinned = false;
 }
@@ -98,6 +99,7 @@ int ensure_capacity(plife_handle *h, int64_t n)
     CU(h, dev_alloc(&h->d_cell, c));
     CU(h, dev_alloc(&h->d_cell_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
+    CU(h, dev_alloc(&h->d_pair_first, c));
     h->cap = n;
     return PLIFE_OK;
 }
@@ -111,7 +113,9 @@ int ensure_cells(plife_handle *h, int64_t ncell)
     cudaFree(h->d_count);
     if (h->d_cell_end) cudaFree(h->d_cell_end - 4);
     cudaFree(h->d_tile_sums);
-    h->d_count = h->d_cell_end = h->d_tile_sums = nullptr;
+    cudaFree(h->d_pair_start);
+    h->d_count = h->d_cell_end = h->d_pair_start = nullptr;
+    h->d_tile_sums = nullptr;
     h->cell_cap = 0;
     int64_t padded = (ncell + kScanTile - 1) / kScanTile * kScanTile;
     CU(h, dev_alloc(&h->d_count, (size_t)padded));
@@ -120,7 +124,8 @@ int ensure_cells(plife_handle *h, int64_t ncell)
     CU(h, dev_alloc(&raw, (size_t)padded + 4));
     CU(h, cudaMemsetAsync(raw, 0, 16, h->stream));
     h->d_cell_end = raw + 4;
-    CU(h, dev_alloc(&h->d_tile_sums, (size_t)(padded / kScanTile)));
+    CU(h, cudaMalloc(&h->d_tile_sums, sizeof(unsigned long long) * (size_t)(padded / kScanTile)));
+    CU(h, dev_alloc(&h->d_pair_start, (size_t)padded));
     CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)padded, h->stream));
     h->cell_cap = padded;
     h->count_dirty = false;
@@ -414,6 +419,7 @@ int plife_destroy(plife_handle *h)
     cudaFree(h->d_count);
     if (h->d_cell_end) cudaFree(h->d_cell_end - 4);
     cudaFree(h->d_tile_sums);
+    cudaFree(h->d_pair_start);
     cudaFree(h->d_matrix_t);
     cudaFree(h->d_snap);
     cudaFree(h->d_scalar);

@@ -151,12 +151,14 @@ struct plife_handle {
     int32_t *d_cell = nullptr;        // packed cell coords of particle i (pre-sort order)
     int32_t *d_cell_sorted = nullptr; // the same, permuted into sorted order
     int32_t *d_perm = nullptr; // source index of sorted slot d
+    int32_t *d_pair_first = nullptr; // first target of every target pair (two-targets-per-lane force kernel)
+    int32_t *d_pair_start = nullptr; // first pair of every cell
     void *d_snap = nullptr;    // snapshot staging (download_f32)
     int64_t snap_cap = 0;
 
     int32_t *d_count = nullptr;   // per-cell histogram, zero between steps
     int32_t *d_cell_end = nullptr; // `containers`: END offset per cell
-    int32_t *d_tile_sums = nullptr;
+    void *d_tile_sums = nullptr; // u64 per scan tile
     int64_t cell_cap = 0;
     int64_t tile_cap = 0;
     unsigned long long *d_scalar = nullptr; // small device scratch (counters)
