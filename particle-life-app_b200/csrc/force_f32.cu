@@ -37,7 +37,8 @@ cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
         }
     }
     // v2 staged kernel whenever the per-lane matrix table fits; v1 (global-memory walk) otherwise
-    if (p.m <= kTabMaxM && !(h->flags & PLIFE_FLAG_FORCE_V1)) {
+    // (below ~4 particles per cell the per-CTA staging and table fill cost more than they save: v1 wins)
+    if (p.m <= kTabMaxM && rho >= 4.0 && !(h->flags & PLIFE_FLAG_FORCE_V1)) {
         // capacity of one staged row range: 128 targets + the cells hanging over both ends + margin
         int cap = (int)(kForceThreads + 4.0 * rho + 8.0 * sqrt(rho + 1.0) + 32.0);
         cap = (cap + 31) / 32 * 32;
