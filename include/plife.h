@@ -140,6 +140,13 @@ int plife_download(plife_handle *h, double *pos_xy, double *vel_xy, int32_t *typ
 /* float snapshot for rendering: xy + vxy as fp32 (display-time handoff) */
 int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type);
 
+/* The same snapshot without stalling the physics (A/Main.java:600-603 requests the next snapshot while it draws):
+ * a snapshot kernel on the compute stream fills one of two staging buffers, the device->host copies run on a
+ * separate copy stream and overlap the following steps.  The caller's buffers (pinned for full PCIe speed) must
+ * stay valid until plife_snapshot_wait() returns. */
+int plife_snapshot_async(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type);
+int plife_snapshot_wait(plife_handle *h);
+
 /* Headless generators with the distributions of the reference's default setters
  * (B/DefaultPositionSetter.java, B/DefaultTypeSetter.java, B/DefaultMatrix.java:25-31)
  * on a seeded SplitMix64 stream; bit-identical to plife/synth.py. */

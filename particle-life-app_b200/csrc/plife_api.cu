@@ -422,6 +422,15 @@ int plife_destroy(plife_handle *h)
     cudaFree(h->d_pair_start);
     cudaFree(h->d_matrix_t);
     cudaFree(h->d_snap);
+    if (h->snap_init) {
+        cudaStreamSynchronize(h->copy_stream);
+        for (int k = 0; k < 2; k++) {
+            cudaFree(h->d_snap_async[k]);
+            cudaEventDestroy(h->snap_ready[k]);
+            cudaEventDestroy(h->snap_done[k]);
+        }
+        cudaStreamDestroy(h->copy_stream);
+    }
     cudaFree(h->d_scalar);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -621,6 +630,58 @@ int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *t
     if (vel_xy) CU(h, cudaMemcpyAsync(vel_xy, dv, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->stream));
     if (type) CU(h, cudaMemcpyAsync(type, dt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return PLIFE_OK;
+}
+
+// Display-time handoff without stalling the physics: the snapshot kernel runs on the compute stream into one
+// of two staging buffers, the device->host copies run on a separate copy stream, and the physics may step on
+// while they are in flight.  The caller's buffers (ideally pinned) must stay valid until plife_snapshot_wait().
+int plife_snapshot_async(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type)
+{
+    CHECK_HANDLE(h);
+    const int64_t n = h->n;
+    if (n == 0) return PLIFE_OK;
+    if (h->slab.on && h->n_phys != h->n) return fail(h, PLIFE_ERR_STATE, "snapshot_async in slab mode needs a compact array (call it right after a cell-list build)");
+    if (!h->snap_init) {
+        CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CU(h, cudaEventCreateWithFlags(&h->snap_ready[k], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->snap_done[k], cudaEventDisableTiming));
+        }
+        h->snap_init = true;
+    }
+    if (h->snap_async_cap < n) {
+        CU(h, cudaStreamSynchronize(h->copy_stream));
+        for (int k = 0; k < 2; k++) {
+            cudaFree(h->d_snap_async[k]);
+            h->d_snap_async[k] = nullptr;
+        }
+        h->snap_async_cap = 0;
+        for (int k = 0; k < 2; k++) CU(h, cudaMalloc(&h->d_snap_async[k], (size_t)n * 20));
+        h->snap_async_cap = n;
+    }
+    const int k = h->snap_k;
+    h->snap_k ^= 1;
+    float2 *dp = (float2 *)h->d_snap_async[k];
+    float2 *dv = dp + n;
+    int32_t *dt = (int32_t *)(dv + n);
+    CU(h, cudaStreamWaitEvent(h->stream, h->snap_done[k], 0)); // the copy that last used this buffer has finished
+    void *save = h->d_snap;
+    CU(h, launch_snapshot_f32(h, pos_xy ? dp : nullptr, vel_xy ? dv : nullptr, type ? dt : nullptr));
+    (void)save;
+    CU(h, cudaEventRecord(h->snap_ready[k], h->stream));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->snap_ready[k], 0));
+    if (pos_xy) CU(h, cudaMemcpyAsync(pos_xy, dp, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (vel_xy) CU(h, cudaMemcpyAsync(vel_xy, dv, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (type) CU(h, cudaMemcpyAsync(type, dt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaEventRecord(h->snap_done[k], h->copy_stream));
+    return PLIFE_OK;
+}
+
+int plife_snapshot_wait(plife_handle *h)
+{
+    CHECK_HANDLE(h);
+    if (h->snap_init) CU(h, cudaStreamSynchronize(h->copy_stream));
     return PLIFE_OK;
 }
 

@@ -155,6 +155,13 @@ struct plife_handle {
     int32_t *d_pair_start = nullptr; // first pair of every cell
     void *d_snap = nullptr;    // snapshot staging (download_f32)
     int64_t snap_cap = 0;
+    // asynchronous, double-buffered snapshot (display-time handoff that overlaps the next steps)
+    void *d_snap_async[2]{};
+    int64_t snap_async_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t snap_ready[2]{}, snap_done[2]{};
+    int snap_k = 0;
+    bool snap_init = false;
 
     int32_t *d_count = nullptr;   // per-cell histogram, zero between steps
     int32_t *d_cell_end = nullptr; // `containers`: END offset per cell

@@ -127,6 +127,17 @@ class NativePhysics:
             return x.ctypes.data
         self._check(self.L.plife_download_f32(self.h, addr(pos), addr(vel), addr(types)))
 
+    def snapshot_async(self, pos=None, vel=None, types=None):
+        """Start a float snapshot that overlaps the following steps; `snapshot_wait` completes it."""
+        def addr(x):
+            if x is None or isinstance(x, int):
+                return x
+            return x.ctypes.data
+        self._check(self.L.plife_snapshot_async(self.h, addr(pos), addr(vel), addr(types)))
+
+    def snapshot_wait(self):
+        self._check(self.L.plife_snapshot_wait(self.h))
+
     def init_uniform(self, n, seed):
         self._check(self.L.plife_init_uniform(self.h, n, seed))
 

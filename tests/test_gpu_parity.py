@@ -318,3 +318,26 @@ def test_fp32_kernel_variants_match_oracle(native_lib, flags, case):
         assert np.array_equal(got.id, oid)
         assert rel_l2(got.velocity, ovel) <= 1e-5
         assert max_over_rms(got.velocity, ovel) <= 1e-4
+
+
+def test_snapshots_match_download(native_lib):
+    """Display-time handoff: the synchronous and the asynchronous float snapshots equal the fp64 download."""
+    pos, vel, types, matrix = make_state(30_000, 4, seed=21, vel_scale=0.05, f32=True)
+    p = plife.NativePhysics()
+    p.set_settings(0.03, 0.85, 1.0, True)
+    p.set_matrix(matrix)
+    p.upload(pos, vel, types)
+    p.step(DT, 2)
+    ref = p.download()
+    n = p.count
+    a = [np.empty((n, 2), np.float32), np.empty((n, 2), np.float32), np.empty(n, np.int32)]
+    p.download_f32(*a)
+    b = [np.empty((n, 2), np.float32), np.empty((n, 2), np.float32), np.empty(n, np.int32)]
+    p.snapshot_async(*b)
+    p.step(DT, 3)  # the physics moves on while the copy is in flight
+    p.snapshot_wait()
+    for got in (a, b):
+        assert np.array_equal(got[0], ref.position.astype(np.float32))
+        assert np.array_equal(got[1], ref.velocity.astype(np.float32))
+        assert np.array_equal(got[2], ref.type)
+    assert not np.array_equal(p.download().position, ref.position)
