@@ -189,6 +189,27 @@ int plife_kernel_times(plife_handle *h, double *ms_out, int64_t *launches_out);
  * F64: pos = double2[n], vel = double2[n], type = int32[n], id = uint32[n] */
 int plife_device_ptrs(plife_handle *h, void **pos, void **vel, void **type, void **id);
 
+/* ---- particle-set editing on the device (what the GUI does to physics.particles directly) ----
+ * Cursor.isInside (A/cursors/Cursor.java:16-35): delta = p - (x,y); if wrap: delta -= floor(delta + 0.5);
+ * delta /= size; circle |delta| <= 0.5, square |dx|,|dy| <= 0.5, infinity selects everything; size 0 nothing. */
+#define PLIFE_CURSOR_CIRCLE 0
+#define PLIFE_CURSOR_SQUARE 1
+#define PLIFE_CURSOR_INFINITY 2
+typedef struct plife_cursor {
+    double x, y, size;
+    int32_t shape; /* PLIFE_CURSOR_* */
+    int32_t wrap;  /* physics.settings.wrap at the time of the call */
+} plife_cursor;
+/* Cursor.countSelection (A/cursors/Cursor.java:45-51; every frame at A/Main.java:497) */
+int plife_cursor_count(plife_handle *h, const plife_cursor *c, int64_t *out);
+/* cursor action MOVE (A/Main.java:540-548): position += (dx,dy), then ensurePosition with the handle's wrap setting */
+int plife_cursor_move(plife_handle *h, const plife_cursor *c, double dx, double dy);
+/* cursor action DELETE (A/Main.java:568-580): removes the selected particles, keeps the order of the others */
+int plife_cursor_delete(plife_handle *h, const plife_cursor *c, int64_t *removed);
+/* cursor action BRUSH / growing setParticleCount (A/Main.java:550-566, B/Physics.java:212-220): appends k particles
+ * sampled by the caller's setters; ids continue after the largest id seen; vel_xy may be NULL */
+int plife_append(plife_handle *h, int64_t k, const double *pos_xy, const double *vel_xy, const int32_t *type);
+
 /* ---- multi-GPU slab decomposition (one process per GPU) ----
  * Rank g owns grid rows [g*ny/G, (g+1)*ny/G).  The library packs / unpacks the halo and migration
  * messages; the host exchanges them between the phases (NCCL send/recv, e.g. torch.distributed):

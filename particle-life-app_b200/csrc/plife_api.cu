@@ -104,6 +104,66 @@ int ensure_capacity(plife_handle *h, int64_t n)
     return PLIFE_OK;
 }
 
+// grow particle buffers keeping the current state (plife_append)
+int grow_preserve(plife_handle *h, int64_t cap)
+{
+    if (cap <= h->cap) return PLIFE_OK;
+    if (cap > 0x7fffffffLL - 1024) return fail(h, PLIFE_ERR_INVALID, "particle count %lld exceeds int32 indexing", (long long)cap);
+    CU(h, cudaStreamSynchronize(h->stream));
+    const size_t c = (size_t)cap, n = (size_t)h->n_phys;
+    const int cur = h->cur;
+    if (h->precision == PLIFE_F32) {
+        StateF32 nw[2]{};
+        for (int b = 0; b < 2; b++) {
+            CU(h, dev_alloc(&nw[b].pt, c));
+            CU(h, dev_alloc(&nw[b].vel, c));
+        }
+        if (n) {
+            CU(h, cudaMemcpy(nw[cur].pt, h->s32[cur].pt, sizeof(float4) * n, cudaMemcpyDeviceToDevice));
+            CU(h, cudaMemcpy(nw[cur].vel, h->s32[cur].vel, sizeof(float2) * n, cudaMemcpyDeviceToDevice));
+        }
+        for (int b = 0; b < 2; b++) {
+            cudaFree(h->s32[b].pt);
+            cudaFree(h->s32[b].vel);
+            h->s32[b] = nw[b];
+        }
+    } else {
+        StateF64 nw[2]{};
+        for (int b = 0; b < 2; b++) {
+            CU(h, dev_alloc(&nw[b].pos, c));
+            CU(h, dev_alloc(&nw[b].vel, c));
+            CU(h, dev_alloc(&nw[b].type, c));
+            CU(h, dev_alloc(&nw[b].id, c));
+        }
+        if (n) {
+            CU(h, cudaMemcpy(nw[cur].pos, h->s64[cur].pos, sizeof(double2) * n, cudaMemcpyDeviceToDevice));
+            CU(h, cudaMemcpy(nw[cur].vel, h->s64[cur].vel, sizeof(double2) * n, cudaMemcpyDeviceToDevice));
+            CU(h, cudaMemcpy(nw[cur].type, h->s64[cur].type, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice));
+            CU(h, cudaMemcpy(nw[cur].id, h->s64[cur].id, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice));
+        }
+        for (int b = 0; b < 2; b++) {
+            cudaFree(h->s64[b].pos);
+            cudaFree(h->s64[b].vel);
+            cudaFree(h->s64[b].type);
+            cudaFree(h->s64[b].id);
+            h->s64[b] = nw[b];
+        }
+    }
+    cudaFree(h->d_cell);
+    cudaFree(h->d_cell_sorted);
+    cudaFree(h->d_perm);
+    cudaFree(h->d_pair_first);
+    h->d_cell = h->d_cell_sorted = h->d_perm = h->d_pair_first = nullptr;
+    CU(h, dev_alloc(&h->d_cell, c));
+    CU(h, dev_alloc(&h->d_cell_sorted, c));
+    CU(h, dev_alloc(&h->d_perm, c));
+    CU(h, dev_alloc(&h->d_pair_first, c));
+    h->cap = cap;
+    h->prebinned = false;
+    h->has_sorted = false;
+    return PLIFE_OK;
+}
+
 constexpr int64_t kMaxCells = (int64_t)1 << 28;
 constexpr int kScanTile = 4096; // must match cells.cu
 
@@ -325,6 +385,8 @@ int valid_settings(plife_handle *h, const plife_settings *s)
 } // namespace
 
 namespace plife {
+int edit_fail(plife_handle *h, int code, const char *msg) { return fail(h, code, "%s", msg); }
+int edit_grow(plife_handle *h, int64_t cap) { return grow_preserve(h, cap); }
 int slab_make_grid(plife_handle *h, Grid *g) { return make_grid(h, g); }
 int slab_fail(plife_handle *h, int code, const char *msg) { return fail(h, code, "%s", msg); }
 int slab_sort(plife_handle *h, const Grid &g)
@@ -507,7 +569,9 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
     CHECK_HANDLE(h);
     if (n < 0 || (n > 0 && (!pos_xy || !type))) return fail(h, PLIFE_ERR_INVALID, "upload: n=%lld with NULL pos/type", (long long)n);
     int max_type = -1;
+    uint32_t max_id = 0;
     for (int64_t i = 0; i < n; i++) {
+        if (id && id[i] > max_id) max_id = id[i];
         double x = pos_xy[2 * i], y = pos_xy[2 * i + 1];
         if (!(x >= 0 && x <= 1 && y >= 0 && y <= 1)) return fail(h, PLIFE_ERR_INVALID, "upload: particle %lld position (%g,%g) outside [0,1]^2", (long long)i, x, y);
         int t = type[i];
@@ -562,6 +626,7 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
     h->slab.n_old = n;
     h->slab.k_below = h->slab.k_above = 0;
     h->max_type = max_type;
+    h->next_id = id ? (n ? max_id + 1 : 0) : (uint32_t)n;
     return PLIFE_OK;
 }
 
@@ -726,6 +791,7 @@ int plife_init_uniform(plife_handle *h, int64_t n, uint64_t seed)
     h->slab.k_below = h->slab.k_above = 0;
     CU(h, launch_init_uniform(h, n, seed));
     h->max_type = n > 0 ? h->m - 1 : -1;
+    h->next_id = (uint32_t)n;
     return PLIFE_OK;
 }
 

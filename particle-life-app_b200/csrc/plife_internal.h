@@ -145,6 +145,7 @@ struct plife_handle {
     int64_t capacity_hint = 0;
     plife::SlabState slab;
     int max_type = -1;
+    uint32_t next_id = 0; // id given to the next appended particle
     int cur = 0; // index of the buffer holding the current state
     plife::StateF32 s32[2]{};
     plife::StateF64 s64[2]{};

@@ -151,6 +151,31 @@ class NativePhysics:
         self._check(self.L.plife_type_histogram(self.h, _ptr(out)))
         return out
 
+    # -- editing (cursor actions of the GUI, on the device) --
+    @staticmethod
+    def _cursor(x, y, size, shape, wrap):
+        return N.Cursor(x=x, y=y, size=size, shape=shape, wrap=1 if wrap else 0)
+
+    def cursor_count(self, x, y, size, shape=N.CURSOR_CIRCLE, wrap=True) -> int:
+        out = C.c_int64()
+        self._check(self.L.plife_cursor_count(self.h, C.byref(self._cursor(x, y, size, shape, wrap)), C.byref(out)))
+        return out.value
+
+    def cursor_move(self, x, y, size, dx, dy, shape=N.CURSOR_CIRCLE, wrap=True):
+        self._check(self.L.plife_cursor_move(self.h, C.byref(self._cursor(x, y, size, shape, wrap)), dx, dy))
+
+    def cursor_delete(self, x, y, size, shape=N.CURSOR_CIRCLE, wrap=True) -> int:
+        out = C.c_int64()
+        self._check(self.L.plife_cursor_delete(self.h, C.byref(self._cursor(x, y, size, shape, wrap)), C.byref(out)))
+        return out.value
+
+    def append(self, pos, vel, types):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        k = pos.shape[0]
+        vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64).reshape(k, 2)
+        types = np.ascontiguousarray(types, dtype=np.int32).reshape(k)
+        self._check(self.L.plife_append(self.h, k, _ptr(pos), _ptr(vel), _ptr(types)))
+
     # -- stepping --
     def step(self, dt, nsteps=1):
         self._check(self.L.plife_step(self.h, dt, nsteps))

@@ -33,6 +33,13 @@ class StepStats(C.Structure):
                 ("steps", C.c_int64)]
 
 
+class Cursor(C.Structure):
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("size", C.c_double), ("shape", C.c_int32), ("wrap", C.c_int32)]
+
+
+CURSOR_CIRCLE, CURSOR_SQUARE, CURSOR_INFINITY = 0, 1, 2
+
+
 class SlabBuffers(C.Structure):
     _fields_ = [("halo_send", C.c_void_p * 2), ("halo_recv", C.c_void_p * 2),
                 ("mig_send", C.c_void_p * 2), ("mig_recv", C.c_void_p * 2)]
@@ -90,6 +97,10 @@ def lib() -> C.CDLL:
         "plife_set_profiling": (C.c_int, [vp, i32]),
         "plife_kernel_times": (C.c_int, [vp, vp, vp]),
         "plife_device_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "plife_cursor_count": (C.c_int, [vp, C.POINTER(Cursor), C.POINTER(i64)]),
+        "plife_cursor_move": (C.c_int, [vp, C.POINTER(Cursor), dbl, dbl]),
+        "plife_cursor_delete": (C.c_int, [vp, C.POINTER(Cursor), C.POINTER(i64)]),
+        "plife_append": (C.c_int, [vp, i64, vp, vp, vp]),
         "plife_slab_halo_records": (i64, [i32, i64]),
         "plife_slab_migrate_records": (i64, [i64]),
         "plife_slab_configure": (C.c_int, [vp, i32, i32, i64, i64, C.POINTER(SlabBuffers)]),

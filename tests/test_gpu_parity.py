@@ -341,3 +341,80 @@ def test_snapshots_match_download(native_lib):
         assert np.array_equal(got[1], ref.velocity.astype(np.float32))
         assert np.array_equal(got[2], ref.type)
     assert not np.array_equal(p.download().position, ref.position)
+
+
+# ---------------------------------------------------------------------------
+# particle-set editing on the device against a numpy restatement of the reference
+# ---------------------------------------------------------------------------
+
+def ref_inside(pos, cx, cy, size, shape, wrap):
+    """A/cursors/Cursor.java:16-35 + Circle/Square/InfinityCursorShape.isInside."""
+    if size == 0.0:
+        return np.zeros(len(pos), bool)
+    d = pos - np.array([cx, cy])
+    if wrap:
+        d = d - np.floor(d + 0.5)
+    d = d * (1.0 / size)
+    if shape == 0:
+        return np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) <= 0.5
+    if shape == 1:
+        return (np.abs(d[:, 0]) <= 0.5) & (np.abs(d[:, 1]) <= 0.5)
+    return np.ones(len(pos), bool)
+
+
+@pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
+def test_cursor_edit_operations(native_lib, precision):
+    f32 = precision == plife.F32
+    pos, vel, types, matrix = make_state(50_000, 5, seed=8, vel_scale=0.02, f32=f32)
+    p = plife.NativePhysics(precision=precision)
+    p.set_settings(0.02, 0.85, 1.0, True)
+    p.set_matrix(matrix)
+    p.upload(pos, vel, types)
+    ids = np.arange(len(pos), dtype=np.uint32)
+    for (cx, cy, size, shape, wrap) in [(0.5, 0.5, 0.2, 0, True), (0.02, 0.97, 0.3, 0, True), (0.02, 0.97, 0.3, 0, False),
+                                         (0.9, 0.1, 0.25, 1, True), (0.3, 0.3, 0.0, 0, True), (0.1, 0.1, 0.1, 2, True)]:
+        assert p.cursor_count(cx, cy, size, shape, wrap) == int(ref_inside(pos, cx, cy, size, shape, wrap).sum())
+    # MOVE: selected particles are translated and wrapped (A/Main.java:540-548)
+    sel = ref_inside(pos, 0.95, 0.5, 0.2, 0, True)
+    p.cursor_move(0.95, 0.5, 0.2, 0.08, -0.6, 0, True)
+    moved = pos.copy()
+    moved[sel] += np.array([0.08, -0.6])
+    moved[sel] = np.where((moved[sel] < 0) | (moved[sel] >= 1), moved[sel] - np.floor(moved[sel]), moved[sel])
+    if f32:
+        moved = moved.astype(np.float32).astype(np.float64)
+    got = p.download()
+    assert np.array_equal(got.id, ids) and np.array_equal(got.position, moved)
+    pos = moved
+    # DELETE keeps the order of the survivors (A/Main.java:568-580)
+    kill = ref_inside(pos, 0.4, 0.6, 0.35, 1, True)
+    assert p.cursor_delete(0.4, 0.6, 0.35, 1, True) == int(kill.sum())
+    pos, vel, types, ids = pos[~kill], vel[~kill], types[~kill], ids[~kill]
+    got = p.download()
+    assert p.count == len(pos) and np.array_equal(got.id, ids) and np.array_equal(got.position, pos)
+    assert np.array_equal(got.type, types)
+    # BRUSH / growth: append beyond the current capacity, ids continue (A/Main.java:550-566)
+    rng = np.random.default_rng(0)
+    k = 30_000
+    new_pos = rng.random((k, 2))
+    new_typ = rng.integers(0, 5, k).astype(np.int32)
+    p.append(new_pos, None, new_typ)
+    got = p.download()
+    assert p.count == len(pos) + k
+    assert np.array_equal(got.id[-k:], np.arange(50_000, 50_000 + k, dtype=np.uint32))
+    exp_new = new_pos.astype(np.float32).astype(np.float64) if f32 else new_pos
+    assert np.array_equal(got.position[:len(pos)], pos) and np.array_equal(got.position[-k:], exp_new)
+    assert np.array_equal(got.velocity[-k:], np.zeros((k, 2)))
+    # the edited set still steps like the oracle
+    cur = p.download()
+    o = oracle_step(cur.position, cur.velocity, cur.type, matrix, ids=cur.id, rmax=0.02, wrap=True, dt=DT)
+    p.step(DT, 1)
+    _, ovel, _, oid = o.get_particles()
+    got = p.download()
+    assert np.array_equal(got.id, oid)
+    if f32:
+        assert rel_l2(got.velocity, ovel) <= 1e-5
+    else:
+        assert np.array_equal(got.velocity, ovel)
+    assert p.type_histogram().sum() == p.count
+    with pytest.raises(plife.PlifeError):
+        p.append(np.array([[0.5, 0.5]]), None, np.array([9], np.int32))
