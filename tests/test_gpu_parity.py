@@ -418,3 +418,42 @@ def test_cursor_edit_operations(native_lib, precision):
     assert p.type_histogram().sum() == p.count
     with pytest.raises(plife.PlifeError):
         p.append(np.array([[0.5, 0.5]]), None, np.array([9], np.int32))
+
+
+def test_physics_mirror_class(native_lib, tmp_path):
+    """`plife.Physics` mirrors the reference object: constructor defaults (B/Physics.java:65-80), update(),
+    particle-count / matrix-size management (:190-258), type counts, and the save-file round trip."""
+    from plife import io as pio
+    p = plife.Physics(particle_count=5000, seed=3)
+    assert p.particle_count == 5000 and p.settings.matrix.shape == (6, 6)
+    assert (p.settings.rmax, p.settings.friction, p.settings.force, p.settings.dt, p.settings.wrap) == (0.02, 0.85, 1.0, 0.02, True)
+    p.settings.rmax = 0.04
+    before = p.particles
+    # one update() equals one oracle update from the same state
+    o = oracle_step(before.position, before.velocity, before.type, p.settings.matrix, ids=before.id, rmax=0.04, dt=0.02)
+    p.update()
+    after = p.particles
+    _, ovel, _, oid = o.get_particles()
+    assert np.array_equal(after.id, oid) and rel_l2(after.velocity, ovel) <= 1e-5
+    assert after.position.min() >= 0 and after.position.max() <= 1
+    assert p.get_type_count().sum() == 5000
+    p.set_particle_count(3000)   # shuffle + truncate (:201-210)
+    assert p.particle_count == 3000 and len(set(p.particles.id.tolist())) == 3000
+    p.set_particle_count(4500)   # append generated particles (:212-220)
+    assert p.particle_count == 4500
+    p.set_matrix_size(3)         # shrink: ensureTypes retags (:255-257, :266-272)
+    assert p.settings.matrix.shape == (3, 3)
+    p.update()
+    assert p.particles.type.max() <= 2 and p.get_type_count().sum() == 4500
+    p.set_matrix_size(5)
+    p.update()
+    path = tmp_path / "state.zip"
+    pio.save_state(path, p)
+    q = plife.Physics(particle_count=10, seed=4)
+    pio.load_state(path, q)
+    a, b = p.particles, q.particles
+    assert np.array_equal(a.position, b.position) and np.array_equal(a.type, b.type)
+    assert np.array_equal(q.settings.matrix, p.settings.matrix) and q.settings.rmax == 0.04
+    p.update()
+    q.update()
+    assert np.array_equal(p.particles.position, q.particles.position)
