@@ -186,15 +186,28 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
 
 // B/Physics.java:343-348: `i = containers[ci]; buffer[i] = p; containers[ci]++`.
 // Afterwards cell_end[ci] is the END offset of cell ci, as in the reference.
+template <bool AGG>
 __global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n_phys, Grid g, int first,
                                                          int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
 {
     int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n_phys) return;
-    int c = container_of(__ldg(&cell[i]), g);
-    if (c < 0) return; // dead slot: the particle migrated to another slab
-    int dst = atomicAdd(&cell_end[c], 1);
-    perm[dst - first] = i;
+    int c = -1;
+    if (i < n_phys) c = container_of(__ldg(&cell[i]), g); // -1: dead slot (the particle migrated to another slab)
+    // Warp-aggregated cursor: after the first step the array is almost cell-sorted, so the 32 lanes of a warp hit
+    // 2-3 distinct cells; one atomic per distinct cell instead of one per particle, and neighbouring slots for
+    // lanes of the same cell.  (Order inside a cell is still arbitrary across warps; K_GATHER ranks it.)
+    if (!AGG) { // sparse grids: every lane has its own cell, aggregation only costs
+        if (c >= 0) perm[atomicAdd(&cell_end[c], 1) - first] = i;
+        return;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (c < 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cell_end[c], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    perm[base + __popc(peers & ((1u << lane) - 1u)) - first] = i;
 }
 
 // Logical position of pre-sort slot `src`.  Single GPU: the identity.  Slab mode: the pre-sort array is
@@ -215,9 +228,13 @@ struct StableKey {
 };
 
 // slot of `src` in the sorted array; also registers the leader (even rank) of every target pair of the cell
-template <bool STABLE>
+struct IdentityKey { // single GPU: the pre-sort index is the previous array index
+    __device__ __forceinline__ int operator()(int src) const { return src; }
+};
+
+template <bool STABLE, bool PAIRS, typename KEY>
 __device__ __forceinline__ int sorted_slot(int d, int src, int c, const int32_t *__restrict__ cell_end,
-                                           const int32_t *__restrict__ perm, int first, StableKey key,
+                                           const int32_t *__restrict__ perm, int first, KEY key,
                                            const int32_t *__restrict__ pair_start, int32_t *__restrict__ pair_first)
 {
     const int s = __ldg(&cell_end[c - 1]);
@@ -230,14 +247,14 @@ __device__ __forceinline__ int sorted_slot(int d, int src, int c, const int32_t 
     } else {
         rank = d + first - s;
     }
-    if (pair_first && (rank & 1) == 0) pair_first[__ldg(&pair_start[c]) + (rank >> 1)] = s + rank - first;
+    if (PAIRS && (rank & 1) == 0) pair_first[__ldg(&pair_start[c]) + (rank >> 1)] = s + rank - first;
     return s + rank;
 }
 
-template <bool STABLE>
+template <bool STABLE, bool PAIRS, typename KEY>
 __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, const float2 *__restrict__ vel_in,
                                                        float4 *__restrict__ pt_out, float2 *__restrict__ vel_out, int n, Grid g,
-                                                       int first, StableKey key, const int32_t *__restrict__ cell,
+                                                       int first, KEY key, const int32_t *__restrict__ cell,
                                                        int32_t *__restrict__ cell_sorted, const int32_t *__restrict__ cell_end,
                                                        const int32_t *__restrict__ perm, const int32_t *__restrict__ pair_start,
                                                        int32_t *__restrict__ pair_first)
@@ -248,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict_
     float4 p = __ldg(&pt_in[src]);
     float2 v = __ldg(&vel_in[src]);
     int cxy = __ldg(&cell[src]);
-    int dst = sorted_slot<STABLE>(d, src, container_of(cxy, g), cell_end, perm, first, key, pair_start, pair_first);
+    int dst = sorted_slot<STABLE, PAIRS, KEY>(d, src, container_of(cxy, g), cell_end, perm, first, key, pair_start, pair_first);
     pt_out[dst] = p; // sorted positions carry the ghost-below offset `first`; per-target arrays do not
     vel_out[dst - first] = v;
     cell_sorted[dst - first] = cxy;
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out
     int t = __ldg(&in.type[src]);
     uint32_t id = __ldg(&in.id[src]);
     int cxy = __ldg(&cell[src]);
-    int dst = sorted_slot<STABLE>(d, src, container_of(cxy, g), cell_end, perm, 0, StableKey{0x7fffffff, 0, 0, 0, 0}, pair_start, pair_first);
+    int dst = sorted_slot<STABLE, false, IdentityKey>(d, src, container_of(cxy, g), cell_end, perm, 0, IdentityKey{}, pair_start, pair_first);
     cell_sorted[dst] = cxy;
     out.pos[dst] = p;
     out.vel[dst] = v;
@@ -413,7 +430,9 @@ cudaError_t launch_scatter(plife_handle *h, const Grid &g)
 {
     int n = (int)h->n_phys; // physical pre-sort length (dead slots included)
     if (n == 0) return cudaSuccess;
-    scatter_perm<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
+    const double rho = (double)h->n / ((double)g.nx * (g.row_hi - g.row_lo));
+    if (rho >= 4.0) scatter_perm<true><<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
+    else scatter_perm<false><<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
     return cudaGetLastError();
 }
 
@@ -435,12 +454,18 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
         else key = StableKey{no, kb, kb, 0, kb + no};                                                             // below, residents, above
     }
     if (h->precision == PLIFE_F32) {
-        if (stable)
-            gather_f32<true><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
-                                                             first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, pf);
-        else
-            gather_f32<false><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,
-                                                              first_index(h), key, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, pf);
+#define PLIFE_GATHER(ST, PR, KT, KV)                                                                                      \
+    gather_f32<ST, PR, KT><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,  \
+                                                           first_index(h), KV, h->d_cell, h->d_cell_sorted,               \
+                                                           h->d_cell_end, h->d_perm, h->d_pair_start, pf)
+        if (h->slab.on) { // arrivals are ordered by their previous global position (StableKey)
+            if (stable) PLIFE_GATHER(true, false, StableKey, key);
+            else PLIFE_GATHER(false, false, StableKey, key);
+        } else if (stable && pf) PLIFE_GATHER(true, true, IdentityKey, IdentityKey{});
+        else if (stable) PLIFE_GATHER(true, false, IdentityKey, IdentityKey{});
+        else if (pf) PLIFE_GATHER(false, true, IdentityKey, IdentityKey{});
+        else PLIFE_GATHER(false, false, IdentityKey, IdentityKey{});
+#undef PLIFE_GATHER
     } else {
         if (stable)
             gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, nullptr);

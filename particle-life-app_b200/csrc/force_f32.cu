@@ -26,7 +26,7 @@ cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
     const double rho = (double)p.n / ((double)p.g.nx * (p.g.row_hi - p.g.row_lo)); // particles per owned cell
     // v3: two targets per lane.  Opt-in: on B200 it executes 6 % fewer instructions than v2 but its 36 KB of
     // shared memory per CTA caps occupancy at 24 warps/SM and it ends up 3 % slower (profiles/r1_force_kernel.md).
-    if ((h->flags & PLIFE_FLAG_PAIRS) && h->acc_kind == PLIFE_ACC_PARTICLE_LIFE && p.m <= 16 && rho >= 2.0) {
+    if ((h->flags & PLIFE_FLAG_PAIRS) && !h->slab.on && h->acc_kind == PLIFE_ACC_PARTICLE_LIFE && p.m <= 16 && rho >= 2.0) {
         int cap = (int)(2 * kForceThreads + 4.0 * rho + 10.0 * sqrt(rho + 1.0) + 32.0);
         cap = (cap + 31) / 32 * 32;
         if (cap <= 1280) {
