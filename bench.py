@@ -215,12 +215,25 @@ def run_ours(args):
         nx = grid_rows(cfg["rmax"])
         rho = n / nx ** 2
         share = n // world
-        with torch.cuda.stream(stream):
-            slab = SlabPhysics(rank, world, cfg["rmax"], device=local_rank, capacity=share + share // 8 + 65536,
-                               halo_cap=int(nx * rho * 1.5) + 4096, mig_cap=max(65536, share // 64), wrap=cfg["wrap"],
-                               stream=stream.cuda_stream, exchange=args.exchange)
-            if args.exchange == "peer":
-                slab.connect_dist()
+        def make_slab(mode):
+            with torch.cuda.stream(stream):
+                sl = SlabPhysics(rank, world, cfg["rmax"], device=local_rank, capacity=share + share // 8 + 65536,
+                                 halo_cap=int(nx * rho * 1.5) + 4096, mig_cap=max(65536, share // 64), wrap=cfg["wrap"],
+                                 stream=stream.cuda_stream, exchange=mode)
+                if mode == "peer":
+                    sl.connect_dist()
+            return sl
+
+        mode = args.exchange
+        try:
+            slab = make_slab(mode)
+        except RuntimeError as e:  # connect_dist raises on EVERY rank if CUDA IPC is unavailable on any: NCCL instead
+            if mode != "peer":
+                raise
+            if rank == 0:
+                print(f"bench.py: {e}; using NCCL send/recv", file=sys.stderr)
+            mode = args.exchange = "nccl"
+            slab = make_slab(mode)
         p = slab.native
         p.random_matrix(m, cfg["seed"])
         p.init_uniform(n, cfg["seed"])  # every rank scans the global stream and keeps its own rows

@@ -158,13 +158,22 @@ class SlabPhysics:
         self.native._check(self.native.L.plife_slab_connect_ipc(self.native.h, self._ipc[0], self._ipc[1]))
 
     def connect_dist(self, group=None):
-        """All-gather the IPC handles over torch.distributed and map the two ring neighbours."""
+        """All-gather the IPC handles over torch.distributed and map the two ring neighbours.  Collective: if the
+        mapping fails on any rank (e.g. CUDA IPC not permitted), every rank raises."""
+        import torch
         import torch.distributed as dist
         handles = [None] * self.world
         dist.all_gather_object(handles, self.export_handle(), group=group)
         dn, up = neighbours(self.rank, self.world, True)  # map both ring neighbours; closed boundaries just never use them
-        self.connect_ipc(handles[dn] if dn is not None else None, handles[up] if up is not None else None)
-        dist.barrier(group=group)
+        err = None
+        try:
+            self.connect_ipc(handles[dn] if dn is not None else None, handles[up] if up is not None else None)
+        except Exception as e:  # noqa: BLE001 - reported collectively below
+            err = e
+        ok = torch.tensor([0 if err else 1], device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError(f"peer exchange could not be set up on every rank ({err or 'failed on another rank'})")
 
     def rows(self):
         lo, hi, nx = C.c_int32(), C.c_int32(), C.c_int32()
