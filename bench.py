@@ -355,7 +355,11 @@ def run_ours(args):
     force_gbs = ALGO_BYTES_FORCE * n / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
     step_gbs = ALGO_BYTES_STEP * n / (ms / args.steps * 1e-3) / 1e9
     pair_rate = stats["pair_evals"] * world * args.steps / (ms * 1e-3)
-    fp32_peak_tf = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+    fp32_nominal_tf = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+    import ctypes
+    meas = ctypes.c_double(0.0)
+    fp32_peak_tf = meas.value if N.lib().plife_measure_fp32_peak(local_rank, ctypes.byref(meas)) == 0 and meas.value > 0 else fp32_nominal_tf
+    fp32_peak_src = "measured FFMA loop on this GPU (plife_measure_fp32_peak)" if meas.value > 0 else "nominal"
     fp32_force_tf = FLOP_PER_PAIR * stats["pair_evals"] / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
     fp32_step_tf = FLOP_PER_PAIR * stats["pair_evals"] * world / (ms / args.steps * 1e-3) / 1e12
 
@@ -397,7 +401,7 @@ def run_ours(args):
                           "algorithmic_bytes_per_particle_step": ALGO_BYTES_STEP},
         "fp32": {"achieved": fp32_force_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": fp32_force_tf / fp32_peak_tf if fp32_force_tf else None,
                  "whole_step_achieved": fp32_step_tf, "whole_step_frac": fp32_step_tf / (fp32_peak_tf * world),
-                 "flop_per_pair_eval": FLOP_PER_PAIR, "peak_source": "nominal 148 SM x 128 lanes x 2 x max SM clock"},
+                 "flop_per_pair_eval": FLOP_PER_PAIR, "peak_source": fp32_peak_src, "nominal_peak": fp32_nominal_tf},
         "kernel_ms_per_step": per_kernel,
         "secondary": secondary,
         "cpu_baseline": cpu,

@@ -184,6 +184,9 @@ int plife_debug_neighbors(plife_handle *h, int32_t *count, uint64_t *hash);
  * and disables graph replay. */
 int plife_set_profiling(plife_handle *h, int32_t enabled);
 int plife_kernel_times(plife_handle *h, double *ms_out, int64_t *launches_out);
+/* Measured FP32 peak of a device: an FFMA loop (8 independent chains per thread, 2 FLOP per FFMA), best of 6
+ * launches.  The denominator of bench.py's FP32 fraction (MEASURED_PEAKS.json carries no FP32 figure). */
+int plife_measure_fp32_peak(int32_t device, double *tflops_out);
 /* device pointers of the current state (for CUDA-GL interop or torch views):
  * F32: pos = float4{x,y,type bits,id bits}[n], vel = float2[n]
  * F64: pos = double2[n], vel = double2[n], type = int32[n], id = uint32[n] */

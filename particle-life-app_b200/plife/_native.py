@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         "plife_debug_neighbors": (C.c_int, [vp, vp, vp]),
         "plife_set_profiling": (C.c_int, [vp, i32]),
         "plife_kernel_times": (C.c_int, [vp, vp, vp]),
+        "plife_measure_fp32_peak": (C.c_int, [i32, C.POINTER(dbl)]),
         "plife_device_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "plife_cursor_count": (C.c_int, [vp, C.POINTER(Cursor), C.POINTER(i64)]),
         "plife_cursor_move": (C.c_int, [vp, C.POINTER(Cursor), dbl, dbl]),
