@@ -301,13 +301,10 @@ def run_ours(args):
         p.set_settings(cfg["rmax"], 0.85, 1.0, cfg["wrap"])
         p.set_matrix(matrix)
         run_steps(1)
-        if world == 1:
-            p.snapshot_wait()  # the previous snapshot is complete (its buffer is the renderer's now)
-            a, b, c = pins[e2e_k[0] & 1]
-            e2e_k[0] += 1
-            p.snapshot_async(a.data_ptr(), b.data_ptr(), c.data_ptr())
-        else:
-            p.download_f32(pin_pos.data_ptr(), pin_vel.data_ptr(), pin_typ.data_ptr())
+        p.snapshot_wait()  # the previous snapshot is complete (its buffer is the renderer's now)
+        a, b, c = pins[e2e_k[0] & 1]
+        e2e_k[0] += 1
+        p.snapshot_async(a.data_ptr(), b.data_ptr(), c.data_ptr())
 
     with torch.cuda.stream(stream):
         for _ in range(3):
@@ -316,8 +313,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
-        if world == 1:
-            p.snapshot_wait()
+        p.snapshot_wait()
         barrier()
         e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -387,7 +383,7 @@ def run_ours(args):
                    "parallelism": "1 GPU" if world == 1 else f"{world} slabs over grid rows, halo exchange + particle migration every step via " + ("kernel pushes into CUDA-IPC peer memory over NVLink" if args.exchange == "peer" else "NCCL send/recv")},
         "pair_evals_per_sec": pair_rate,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "per step: set_settings + set_matrix from host, plife_step, full fp32 snapshot (xy,vxy,type) into pinned host memory" + (" (copy of step k overlaps step k+1; every snapshot awaited)" if world == 1 else "")},
+                "what": "per step: set_settings + set_matrix from host, plife_step, full fp32 snapshot (xy,vxy,type) into pinned host memory" + " (copy of step k overlaps step k+1; every snapshot awaited)"},
         # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add pack, header
         # reset, 4 pushes, 2 signals, 2 waits and the halo unpack
         "gpu_launches": (6 if world == 1 else 17) * args.steps * world,

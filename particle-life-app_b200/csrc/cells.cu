@@ -398,6 +398,74 @@ __global__ void __launch_bounds__(kThreads) snapshot_from_f64(StateF64 s, int n,
     if (type_out) type_out[i] = s.type[i];
 }
 
+// Slab mode: the array holds dead slots (particles that migrated away) until the next cell-list build; the
+// snapshot skips them, keeping the order: per-block live counts -> scan -> compacting write.
+__global__ void __launch_bounds__(kThreads) live_counts(const int32_t *__restrict__ cell, int n_phys, int *block_counts)
+{
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    int live = (i < n_phys && __ldg(&cell[i]) >= 0) ? 1 : 0;
+    int cnt = __syncthreads_count(live);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(1024) scan_block_counts(int *block_counts, int nblocks)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < nblocks ? block_counts[i] : 0;
+        int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sums[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int ws = warp_sums[lane], winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sums[lane] = winc - ws;
+        }
+        __syncthreads();
+        int ex = carry_s + warp_sums[w] + inc - v;
+        if (i < nblocks) block_counts[i] = ex;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = ex + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) snapshot_live_f32(const float4 *__restrict__ pt, const float2 *__restrict__ vel,
+                                                              const int32_t *__restrict__ cell, int n_phys,
+                                                              const int *__restrict__ block_offsets, float2 *pos_out,
+                                                              float2 *vel_out, int32_t *type_out)
+{
+    __shared__ int warp_sums[kThreads / 32];
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    int live = (i < n_phys && __ldg(&cell[i]) >= 0) ? 1 : 0;
+    unsigned m = __ballot_sync(0xffffffffu, live);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_sums[w] = __popc(m);
+    __syncthreads();
+    if (!live) return;
+    int off = block_offsets[blockIdx.x];
+    for (int k = 0; k < w; k++) off += warp_sums[k];
+    off += __popc(m & ((1u << lane) - 1u));
+    float4 p = __ldg(&pt[i]);
+    if (pos_out) pos_out[off] = make_float2(p.x, p.y);
+    if (vel_out) vel_out[off] = __ldg(&vel[i]);
+    if (type_out) type_out[off] = __float_as_int(p.z);
+}
+
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 inline int first_index(const plife_handle *h) { return h->slab.on ? (int)h->slab.halo_cap : 0; }
 inline int32_t *npairs_ptr(plife_handle *h) { return reinterpret_cast<int32_t *>(h->d_scalar + 7); }
@@ -511,6 +579,14 @@ cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32
 {
     int n = (int)h->n;
     if (n == 0) return cudaSuccess;
+    if (h->slab.on && h->n_phys != h->n) { // dead slots present: compact while copying (fp32 handles only)
+        const int np = (int)h->n_phys, nb = blocks_for(np, kThreads);
+        int *d_blocks = h->d_perm; // scratch: not live between steps
+        live_counts<<<nb, kThreads, 0, h->stream>>>(h->d_cell, np, d_blocks);
+        scan_block_counts<<<1, 1024, 0, h->stream>>>(d_blocks, nb);
+        snapshot_live_f32<<<nb, kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, h->d_cell, np, d_blocks, pos, vel, type);
+        return cudaGetLastError();
+    }
     if (h->precision == PLIFE_F32)
         snapshot_from_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, n, pos, vel, type);
     else

@@ -706,7 +706,6 @@ int plife_snapshot_async(plife_handle *h, float *pos_xy, float *vel_xy, int32_t 
     CHECK_HANDLE(h);
     const int64_t n = h->n;
     if (n == 0) return PLIFE_OK;
-    if (h->slab.on && h->n_phys != h->n) return fail(h, PLIFE_ERR_STATE, "snapshot_async in slab mode needs a compact array (call it right after a cell-list build)");
     if (!h->snap_init) {
         CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (int k = 0; k < 2; k++) {
