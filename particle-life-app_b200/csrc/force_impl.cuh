@@ -475,8 +475,9 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
 // Trip counts are rounded up to a multiple of 4 (no remainder loops): the extra candidates are
 // the first particles of cell cx0+2 or beyond, whose |dx| exceeds rmax for an interior lane, so
 // they contribute exactly zero; each staged range is followed by 3 far-away sentinels for the
-// case where the range itself ends.  Lanes on the domain seam, and CTAs whose ranges exceed
-// the staging capacity (dense clusters), walk global memory with the literal 9-cell loop.
+// case where the range itself ends.  Lanes on the domain seam walk global memory with the literal
+// 9-cell loop; CTAs whose ranges exceed the staging capacity (dense clusters) stream them through
+// it in chunks (traverse_chunked).
 constexpr int kTabMaxM = 32;
 constexpr int kStagePad = 3; // sentinels after each staged range
 
@@ -485,6 +486,42 @@ __device__ __forceinline__ float4 lds128(uint32_t a)
     float4 v;
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
+}
+
+// The literal 9-cell walk over global memory (seam lanes): B/Physics.java:412-437.
+template <int KEYSHIFT, typename V>
+__device__ __forceinline__ void traverse_global32(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g, int wrap,
+                                                  int i, float xi, float yi, int cx0, int cy0, V &v)
+{
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+        const int ox = k % 3 - 1, oy = k / 3 - 1;
+        int cx = wrap_container(cx0 + ox, g.nx);
+        int cy = wrap_container(cy0 + oy, g.ny);
+        if (wrap) {
+            cx = wrap_container(cx, g.nx);
+            cy = wrap_container(cy, g.ny);
+        } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
+            continue;
+        }
+        const int ci = cx + local_row(cy, g) * g.nx;
+        const int s = __ldg(cell_end + ci - 1);
+        const int e = __ldg(cell_end + ci);
+        for (int j = s; j < e; ++j) {
+            if (j == i) continue;
+            Cand<float> q = io.cand(j);
+            q.type <<= KEYSHIFT;
+            float dx, dy;
+            if (wrap) {
+                dx = wrap_connection(xi, q.x);
+                dy = wrap_connection(yi, q.y);
+            } else {
+                dx = q.x - xi;
+                dy = q.y - yi;
+            }
+            v.pair(j, q, dx, dy);
+        }
+    }
 }
 
 template <int KEYSHIFT = kTabShift, typename V>
@@ -512,36 +549,63 @@ __device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *
             }
         }
     } else {
+        traverse_global32<KEYSHIFT>(io, cell_end, g, wrap, i, xi, yi, cx0, cy0, v);
+    }
+}
+
+// Dense clusters: the three row ranges of a CTA do not fit the staging area (it is sized for the mean
+// density).  Instead of sending the whole CTA down the global-memory walk - where an evolved state
+// spends most of its pair evaluations - the ranges are streamed through the staging area in chunks.
+// Every thread of the CTA takes part in every chunk (two barriers each); a lane evaluates the part of
+// its own [s, e) that lies inside the chunk.  The 3 sentinels sit after EVERY chunk, so a padded trip
+// that runs off a chunk's end reads sentinels, never candidates the next chunk will deliver again.
+template <typename V>
+__device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g,
+                                                 int wrap, bool valid, int i, float xi, float yi, int cxy, float4 *stage,
+                                                 uint32_t stage_addr, int chunk_cap, const int *s_start, const int *s_len, V &v)
+{
+    const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
+    const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
+    const int base0 = (cy0 + g.ly_shift - 1) * g.nx + cx0;
+    const int tid = threadIdx.x;
 #pragma unroll 1
-        for (int k = 0; k < 9; ++k) {
-            const int ox = k % 3 - 1, oy = k / 3 - 1;
-            int cx = wrap_container(cx0 + ox, g.nx);
-            int cy = wrap_container(cy0 + oy, g.ny);
-            if (wrap) {
-                cx = wrap_container(cx, g.nx);
-                cy = wrap_container(cy, g.ny);
-            } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
-                continue;
-            }
-            const int ci = cx + local_row(cy, g) * g.nx;
-            const int s = __ldg(cell_end + ci - 1);
-            const int e = __ldg(cell_end + ci);
-            for (int j = s; j < e; ++j) {
-                if (j == i) continue;
-                Cand<float> q = io.cand(j);
-                q.type <<= KEYSHIFT;
-                float dx, dy;
-                if (wrap) {
-                    dx = wrap_connection(xi, q.x);
-                    dy = wrap_connection(yi, q.y);
-                } else {
-                    dx = q.x - xi;
-                    dy = q.y - yi;
+    for (int r = 0; r < 3; ++r) {
+        int s = 0, e = 0;
+        if (interior) {
+            const int base = base0 + r * g.nx;
+            s = __ldg(cell_end + base - 2);
+            e = __ldg(cell_end + base + 1);
+        }
+        const int row_lo = s_start[r], row_hi = row_lo + s_len[r];
+#pragma unroll 1
+        for (int c0 = row_lo; c0 < row_hi; c0 += chunk_cap) {
+            const int clen = min(chunk_cap, row_hi - c0);
+            __syncthreads(); // the previous chunk has been consumed
+            const float4 *src = io.pt + c0;
+            for (int k = tid; k < clen + kStagePad; k += kForceThreads) {
+                float4 q = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
+                if (k < clen) {
+                    q = __ldg(src + k);
+                    q.z = __int_as_float(__float_as_int(q.z) << kTabShift);
                 }
-                v.pair(j, q, dx, dy);
+                stage[k] = q;
+            }
+            __syncthreads();
+            const int a0 = max(s, c0), a1 = min(e, c0 + clen);
+            if (a0 < a1) {
+                uint32_t a = stage_addr + (uint32_t)(a0 - c0) * 16u;
+                const uint32_t aend = stage_addr + (uint32_t)(a1 - c0) * 16u;
+                for (; a < aend; a += 64u) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 q = lds128(a + 16u * u);
+                        v.pair(-1, Cand<float>{q.x, q.y, __float_as_int(q.z), 0u}, q.x - xi, q.y - yi);
+                    }
+                }
             }
         }
     }
+    if (valid && !interior) traverse_global32<kTabShift>(io, cell_end, g, wrap, i, xi, yi, cx0, cy0, v);
 }
 
 // gM: row-major matrix [own][other] (for the vectorised row copy), gMt: transposed
@@ -620,24 +684,32 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_staged(IOF32 io, c
         }
     }
     __syncthreads();
-    if (!valid) return;
+    if (!valid && staged_ok) return; // in chunked mode (CTA-uniform) every thread is needed at the barriers
 
-    float vx, vy;
-    io.self_vel(i, vx, vy);
+    float vx = 0.f, vy = 0.f;
+    if (valid) io.self_vel(i, vx, vy);
     MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, self.type, 1.0f, 0u, 0u};
     M.init();
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+    const int chunk_cap = 3 * (cap + kStagePad) - kStagePad; // the whole staging area as one buffer
     float nvx, nvy;
     if constexpr (FAST) {
         FastParticleLife32<kMatLaneTab> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
-        traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
+        if (staged_ok)
+            traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, true, stage_addr, cap, s_start, v);
+        else
+            traverse_chunked(io, cell_end, g, P.wrap, valid, si, self.x, self.y, cxy, stage, stage_addr, chunk_cap, s_start, s_len, v);
         nvx = fmaf(P.fast_k, v.ax, vx * P.mu);
         nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
     } else {
         LiteralForce<float, KIND, kMatLaneTab> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
-        traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, staged_ok, stage_addr, cap, s_start, v);
+        if (staged_ok)
+            traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, true, stage_addr, cap, s_start, v);
+        else
+            traverse_chunked(io, cell_end, g, P.wrap, valid, si, self.x, self.y, cxy, stage, stage_addr, chunk_cap, s_start, s_len, v);
         v.finish(nvx, nvy);
     }
+    if (!valid) return;
     float nx_ = fmaf(nvx, P.dt, self.x);
     float ny_ = fmaf(nvy, P.dt, self.y);
     if (P.wrap) {

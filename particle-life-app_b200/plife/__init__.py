@@ -389,6 +389,35 @@ class Physics:
         self._push_settings()
         return self.native.type_histogram()
 
+    def set_type_count(self, type_count):
+        """A/ExtendedPhysics.java:40-118 (planned on the host for the whole array, see setters.plan_type_count)."""
+        from .setters import plan_type_count
+        m = self.settings.matrix.shape[0]
+        want = np.asarray(type_count, np.int64).reshape(-1)
+        if want.shape[0] != m:
+            raise ValueError(f"Got array of length {want.shape[0]}, but current matrix size is {m}. "
+                             "Maybe you should change the matrix size before doing this.")
+        p = self.native.download()
+        src, types, fresh = plan_type_count(p.type, want, self.rng)
+        old = src >= 0
+        pos = np.zeros((len(src), 2))
+        vel = np.zeros((len(src), 2))
+        pos[old], vel[old] = p.position[src[old]], p.velocity[src[old]]
+        if fresh.any():
+            pos[fresh] = self.ensure_position(self.position_setter.set(types[fresh], m, self.rng))
+        ids = np.zeros(len(src), np.uint32)
+        ids[old] = p.id[src[old]]
+        first_new = int(p.id.max()) + 1 if len(p.id) else 0
+        ids[~old] = np.arange(first_new, first_new + int((~old).sum()), dtype=np.uint32)
+        self.set_particles(pos, vel, types, ids)
+
+    def set_type_count_equal(self):
+        """A/ExtendedPhysics.java:28-38."""
+        from .setters import equal_type_count
+        want = equal_type_count(self.native.count, self.settings.matrix.shape[0])
+        if want is not None:
+            self.set_type_count(want)
+
     # -- geometry helpers (host, tiny) --
     def ensure_position(self, pos: np.ndarray) -> np.ndarray:
         """B/Physics.java:499-505 with B/Range.java:46-57,89-96."""

@@ -466,6 +466,77 @@ def test_physics_mirror_class(native_lib, tmp_path):
     assert np.array_equal(p.particles.position, q.particles.position)
 
 
+@pytest.mark.gpu
+def test_catalog_setters_and_type_counts_drive_the_backend(native_lib):
+    """The reference app's setter catalogs plugged into `plife.Physics` (A/Main.java:671-761 routes them through the
+    same Physics methods), then setTypeCount / setTypeCountEqual (A/ExtendedPhysics.java:28-118), each followed by a
+    step that must agree with the oracle from the downloaded state."""
+    from plife import setters as S
+    p = plife.Physics(position_setter=S.POSITION_SETTERS["color battle"], matrix_generator=S.MATRIX_GENERATORS["snakes"],
+                      type_setter=S.TYPE_SETTERS["more of first"], particle_count=6000, seed=11)
+    p.settings.rmax = 0.05
+    assert np.array_equal(p.settings.matrix, S.MATRIX_GENERATORS["snakes"].make_matrix(6, None))
+    hist = p.get_type_count()
+    assert hist.sum() == 6000 and all(np.diff(hist) < 0)
+    for name in S.POSITION_SETTERS:
+        p.position_setter = S.POSITION_SETTERS[name]
+        p.set_positions()
+        q = p.particles
+        assert q.position.min() >= 0 and q.position.max() <= 1 and not q.velocity.any()
+    for name in S.TYPE_SETTERS:
+        p.type_setter = S.TYPE_SETTERS[name]
+        p.set_types()
+        assert p.get_type_count().sum() == 6000
+    p.set_type_count_equal()
+    assert p.get_type_count().tolist() == [1000] * 6
+    p.set_type_count([10, 20, 30, 40, 50, 7000])      # grows: new particles, ids stay unique
+    q = p.particles
+    assert p.particle_count == 7150 and p.get_type_count().tolist() == [10, 20, 30, 40, 50, 7000]
+    assert len(set(q.id.tolist())) == 7150
+    p.set_type_count([500, 500, 500, 500, 500, 500])  # shrinks
+    assert p.particle_count == 3000 and p.get_type_count().tolist() == [500] * 6
+    with pytest.raises(ValueError):
+        p.set_type_count([1, 2, 3])
+    for gen in S.MATRIX_GENERATORS.values():
+        p.matrix_generator = gen
+        p.generate_matrix()
+        before = p.particles
+        o = oracle_step(before.position, before.velocity, before.type, p.settings.matrix, ids=before.id, rmax=0.05, dt=0.02)
+        p.update()
+        after = p.particles
+        _, ovel, _, oid = o.get_particles()
+        assert np.array_equal(after.id, oid)
+        assert rel_l2(after.velocity, ovel) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_simulation_loop_and_snapshots(native_lib):
+    """B/Loop.java + A/Main.java:245-300,583-604: physics thread, queued commands, snapshot hand-off."""
+    import time
+    from plife.loop import Simulation
+    p = plife.Physics(particle_count=4000, seed=5)
+    sim = Simulation(p, auto_dt=False, dt=0.02)
+    assert sim.new_snapshot_available.is_set() and sim.snapshot.particle_count == 4000
+    first = sim.snapshot.positions.copy()
+    sim.start()
+    sim.loop.enqueue(lambda: p.set_particle_count(5000))
+    deadline = time.time() + 20
+    while sim.steps < 5 and time.time() < deadline:
+        time.sleep(0.01)
+    sim.request_snapshot()
+    assert sim.new_snapshot_available.wait(20)
+    snap = sim.snapshot
+    assert snap.particle_count == 5000 and snap.type_count.sum() == 5000 and snap.settings.dt == 0.02
+    assert snap.positions.shape == (5000, 2) and snap.positions.dtype == np.float32
+    assert snap.positions.min() >= 0 and snap.positions.max() <= 1 and snap.velocities.any()
+    assert sim.close(5000) and sim.loop.error is None
+    steps = sim.steps
+    time.sleep(0.05)
+    assert sim.steps == steps and steps >= 5
+    # the loop is gone: the handle can be used from this thread again, and matches what the snapshot chain saw
+    assert p.particle_count == 5000 and first.shape == (4000, 2)
+
+
 @pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
 @pytest.mark.parametrize("flags", [0, plife.FLAG_PAIRS], ids=["default", "pairs"])
 def test_clustered_state(native_lib, precision, flags):
@@ -498,3 +569,45 @@ def test_clustered_state(native_lib, precision, flags):
             assert max_over_rms(got.velocity, ovel) <= 1e-4
         else:
             assert np.array_equal(got.velocity, ovel) and np.array_equal(got.position, opos)
+
+
+def _blob_state(n, m, seed):
+    rng = np.random.default_rng(seed)
+    pos = np.concatenate([np.clip(rng.normal(0.5, 0.03, (n // 2, 2)), 0, 1), np.clip(rng.normal([0.98, 0.02], 0.01, (n // 4, 2)), 0, 1),
+                          rng.random((n - n // 2 - n // 4, 2))])
+    vel = rng.normal(0, 0.01, (n, 2)).astype(np.float32).astype(np.float64)
+    return pos.astype(np.float32).astype(np.float64), vel, rng.integers(0, m, n).astype(np.int32), rng.random((m, m)) * 2 - 1
+
+
+@pytest.mark.parametrize("accel", [(3, ()), (5, ()), (0, (0.45,))], ids=["rotator90", "planets", "beta045"])
+def test_clustered_state_chunked_staging_other_accelerators(native_lib, accel):
+    """Dense CTAs stream their candidate ranges through shared memory in chunks (traverse_chunked); the literal
+    visitors (distance test per candidate) take the same route as the branch-free default one."""
+    pos, vel, types, matrix = _blob_state(30_000, 4, 21)
+    params = tuple(accel[1]) + (0.0,) * (4 - len(accel[1])) if accel[1] else (0.3, 0, 0, 0)
+    for wrap in (True, False):
+        kw = dict(rmax=0.02, wrap=wrap, dt=DT)
+        o = oracle_step(pos, vel, types, matrix, accel_kind=accel[0], accel_params=params, **kw)
+        _, ovel, _, oid = o.get_particles()
+        g = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, accel=accel, **kw)
+        got = g.download()
+        assert np.array_equal(got.id, oid) and g.step_stats()["pair_evals"] == o.pair_stats()[0]
+        assert rel_l2(got.velocity, ovel) <= 1e-5
+
+
+def test_clustered_state_many_steps_fp32_tracks_fp64(native_lib):
+    """A blob evolving for 40 steps: cells of a thousand particles, CTAs that need many chunks, CTAs that end
+    inside a chunk, trailing partial CTA.  fp32 against the bit-exact fp64 mode; ids (the sort order) must agree
+    while no particle sits within rounding distance of a cell boundary, so compare sets and drift instead."""
+    pos, vel, types, matrix = _blob_state(50_001, 6, 22)
+    kw = dict(rmax=0.01, wrap=True, dt=DT)
+    a = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, steps=40, **kw)
+    b = gpu_step(native_lib, plife.F64, pos, vel, types, matrix, steps=40, **kw)
+    pa, pb = a.download(), b.download()
+    ia, ib = np.argsort(pa.id), np.argsort(pb.id)
+    assert np.array_equal(pa.id[ia], pb.id[ib]) and np.array_equal(pa.type[ia], pb.type[ib])
+    d = np.abs(pa.position[ia] - pb.position[ib])
+    d = np.minimum(d, 1 - d)
+    assert np.median(d) < 1e-5 and np.percentile(d, 99) < 1e-3
+    counts = np.diff(np.r_[0, a.containers()])
+    assert counts.max() > 500
