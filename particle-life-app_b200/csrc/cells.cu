@@ -243,7 +243,15 @@ __device__ __forceinline__ int sorted_slot(int d, int src, int c, const int32_t 
         const int e = __ldg(&cell_end[c]);
         rank = 0;
         const int ksrc = key(src);
-        for (int k = s; k < e; k++) rank += (key(__ldg(&perm[k - first])) < ksrc) ? 1 : 0;
+        // four keys per load: cells of an evolved state hold thousands of particles and this loop is O(count^2) per cell
+        const int32_t *pp = perm - first;
+        int k = s;
+        for (; k < e && ((k - first) & 3); ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
+        for (; k + 4 <= e; k += 4) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(pp + k));
+            rank += ((key(q.x) < ksrc) ? 1 : 0) + ((key(q.y) < ksrc) ? 1 : 0) + ((key(q.z) < ksrc) ? 1 : 0) + ((key(q.w) < ksrc) ? 1 : 0);
+        }
+        for (; k < e; ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
     } else {
         rank = d + first - s;
     }

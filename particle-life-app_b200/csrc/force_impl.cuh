@@ -610,7 +610,7 @@ __device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t 
 
 // gM: row-major matrix [own][other] (for the vectorised row copy), gMt: transposed
 template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kForceThreads) force_kernel_staged(IOF32 io, const int32_t *__restrict__ cell_end,
+__global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 io, const int32_t *__restrict__ cell_end,
                                                                     const int32_t *__restrict__ cell_sorted,
                                                                     ForceParams<float> P, const float *__restrict__ gM,
                                                                     int cap, NextBin nb)

@@ -10,13 +10,18 @@ non-uniform) and write saves the Java app can open.
   physics.toml   boundaries = "periodic" | "clamped", radius, friction, force
                  (A/PhysicsSettingsToml.java:9-34); dt is NOT saved
 
+  clipboard      matrix text copied / pasted by the GUI (A/MatrixParser.java:28-74): parsed through **float**,
+                 written with `%f` (6 decimals) or `%4.1f`
+
 Numbers are written like Java's Double.toString (shortest digits that round-trip; decimal notation for
 1e-3 <= |x| < 1e7, otherwise `d.dddE[-]n`), so files are textually what the app would write with JDK >= 19.
 """
 from __future__ import annotations
 
 import io
+import re
 import zipfile
+from decimal import ROUND_HALF_UP, Decimal
 from typing import Optional, Tuple
 
 import numpy as np
@@ -109,6 +114,63 @@ def load_matrix(stream) -> np.ndarray:
     rows = [[float(v) for v in ln.split("\t")] for ln in text.splitlines() if ln.strip()]
     n = len(rows)
     return np.array([r[:n] for r in rows], np.float64).reshape(n, n)
+
+
+# -- clipboard matrix text ----------------------------------------------------
+
+_JAVA_FLOAT = re.compile(r"[+-]?(NaN|Infinity|(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?[fFdD]?"
+                         r"|0[xX]([0-9a-fA-F]+\.?[0-9a-fA-F]*|\.[0-9a-fA-F]+)[pP][+-]?\d+[fFdD]?)")
+
+
+def _java_parse_float(token: str):
+    """Float.parseFloat: None where Java throws NumberFormatException (Python's float() is laxer: '1_0', 'inf')."""
+    t = token.strip()
+    if not _JAVA_FLOAT.fullmatch(t):
+        return None
+    low = t.lower().lstrip("+-")
+    if low.startswith("0x"):
+        v = float.fromhex(t[:-1] if t[-1] in "fFdD" else t)   # after the p-exponent a trailing f/d is a suffix
+    elif low == "nan":
+        v = float("nan")
+    elif low == "infinity":
+        v = float("-inf") if t.startswith("-") else float("inf")
+    else:
+        v = float(t.rstrip("fFdD"))
+    return float(np.float32(v))
+
+
+def parse_matrix(text: str) -> Optional[np.ndarray]:
+    """MatrixParser.parseMatrix (A/MatrixParser.java:28-52): split on single whitespace characters, keep what
+    parses as a float, size = floor(sqrt(count)), surplus numbers dropped; None when nothing parses.  Values pass
+    through float, so a pasted 0.1 becomes 0.10000000149011612."""
+    numbers = [v for v in (_java_parse_float(p) for p in re.split(r"\s", text)) if v is not None]
+    size = int(np.sqrt(len(numbers)))
+    if size < 1:
+        return None
+    return np.array(numbers[: size * size], np.float64).reshape(size, size)
+
+
+def _java_format_f(x: float, decimals: int, width: int = 0) -> str:
+    """String.format(Locale.US, "%<width>.<decimals>f"): the JDK rounds HALF_UP on the decimal digits of
+    Double.toString, not on the binary value (0.25 -> "0.3", 0.35 -> "0.4")."""
+    x = float(x)
+    if x != x:
+        out = "NaN"
+    elif x in (float("inf"), float("-inf")):
+        out = "Infinity" if x > 0 else "-Infinity"
+    else:
+        d = Decimal(repr(x)).quantize(Decimal(1).scaleb(-decimals), rounding=ROUND_HALF_UP)
+        out = f"{d:.{decimals}f}"
+        if d == 0 and str(x).startswith("-"):
+            out = "-" + out.lstrip("-")
+    return out.rjust(width)
+
+
+def matrix_to_string(matrix, rounded: bool = False) -> str:
+    """MatrixParser.matrixToString / matrixToStringRoundAndFormat (A/MatrixParser.java:54-74)."""
+    m = np.asarray(matrix, np.float64)
+    enc = (lambda v: _java_format_f(v, 1, 4)) if rounded else (lambda v: _java_format_f(v, 6))
+    return "".join("\t".join(enc(v) for v in row) + "\n" for row in m)
 
 
 # -- physics.toml -------------------------------------------------------------

@@ -89,3 +89,22 @@ def test_zip_save_load(tmp_path):
     assert np.array_equal(b.state[0], a.state[0]) and np.array_equal(b.state[2], a.state[2])
     assert np.array_equal(b.settings.matrix, a.settings.matrix) and b.ensured == 1
     assert (b.settings.rmax, b.settings.wrap) == (0.05, False)
+
+
+def test_clipboard_matrix_text():
+    """A/MatrixParser.java:28-74: parse through float, tolerate junk, floor(sqrt(count)) size; %f and %4.1f writers."""
+    m = pio.parse_matrix("0.1 0.2 -0.3\n-0.1 0.4 0.1\n1.0 -1.0 0.0")
+    assert m.shape == (3, 3) and m[0, 0] == float(np.float32(0.1)) and m[0, 0] != 0.1 and m[2].tolist() == [1.0, -1.0, 0.0]
+    assert pio.parse_matrix("") is None and pio.parse_matrix("a b\tc") is None
+    assert pio.parse_matrix("1 2 3 4 5 6 7 8").tolist() == [[1, 2], [3, 4]]          # surplus dropped
+    assert pio.parse_matrix("x 1\t\t2\n\n3 y 4").tolist() == [[1, 2], [3, 4]]         # empty / junk tokens skipped
+    # Float.parseFloat accepts suffixes, hex floats, NaN/Infinity; rejects what only Python accepts
+    got = pio.parse_matrix("1f 2d .5 1e1 0x1p1 inf 1_0 nan -Infinity")
+    assert got.shape == (2, 2) and got.tolist() == [[1.0, 2.0], [0.5, 10.0]]
+    got = pio.parse_matrix("0x1p1 -Infinity 3. +4")
+    assert got.tolist() == [[2.0, float("-inf")], [3.0, 4.0]]
+    assert pio.matrix_to_string([[0.1, -1 / 3], [1e-7, 1.0]]) == "0.100000\t-0.333333\n0.000000\t1.000000\n"
+    # HALF_UP on the shortest decimal digits (JDK Formatter), width 4
+    assert pio.matrix_to_string([[0.25, -0.35], [1, -0.04]], rounded=True) == " 0.3\t-0.4\n 1.0\t-0.0\n"
+    rt = pio.parse_matrix(pio.matrix_to_string(m))
+    assert np.abs(rt - m).max() <= 5e-7
