@@ -398,9 +398,9 @@ def run_ours(args):
         "pair_evals_per_sec": pair_rate,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "per step: set_settings + set_matrix from host, plife_step, full fp32 snapshot (xy,vxy,type) into pinned host memory" + " (copy of step k overlaps step k+1; every snapshot awaited)"},
-        # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add pack, header
-        # reset, 4 pushes, 2 signals, 2 waits and the halo unpack
-        "gpu_launches": (6 if world == 1 else 17) * args.steps * world,
+        # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add pack,
+        # 4 pushes, 2 signals, the halo wait + unpack and the wait-and-collect of phase FINISH (arrival appends not counted)
+        "gpu_launches": (6 if world == 1 else 16) * args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "force_kernel (3x3 force + friction + integrate + wrap)",
                      "achieved": force_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": force_gbs / hbm_peak if force_gbs else None, "traffic": 54.5 * cfg["n_per_gpu"] / 1e9 if world == 1 else None,

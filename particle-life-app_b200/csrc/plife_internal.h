@@ -113,6 +113,7 @@ struct SlabState {
     unsigned long long seq = 1;     // step sequence number written into the neighbours' flags
     float4 *peer_base[2]{};         // the neighbours' xbuf mapped into this process / device
     bool peer_ipc[2]{};
+    volatile int4 *h_hdr = nullptr; // mapped pinned: 4 migration headers + error word, written by finish_headers
 };
 } // namespace plife
 

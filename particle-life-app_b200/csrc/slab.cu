@@ -50,10 +50,12 @@ __device__ __forceinline__ int offsets_records(int nx) { return (nx + 3) >> 2; }
 // dir 0: first owned row (local row 1) -> becomes the down neighbour's top ghost row
 // dir 1: last owned row (local row nly-2) -> becomes the up neighbour's bottom ghost row
 __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__ pt_sorted, const int32_t *__restrict__ cell_end,
-                                                      Grid g, int halo_cap, float4 *__restrict__ msg0, float4 *__restrict__ msg1)
+                                                      Grid g, int halo_cap, float4 *__restrict__ msg0, float4 *__restrict__ msg1,
+                                                      float4 *__restrict__ mig0, float4 *__restrict__ mig1)
 {
     const int dir = blockIdx.y;
     float4 *msg = dir ? msg1 : msg0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) (dir ? mig1 : mig0)[0] = make_float4(0.f, 0.f, 0.f, 0.f); // this step's migration cursor
     const int row = dir ? g.nly - 2 : 1;
     const int start = __ldg(cell_end + row * g.nx - 1);
     const int end = __ldg(cell_end + (row + 1) * g.nx - 1);
@@ -158,12 +160,37 @@ __global__ void wait_flags(const volatile unsigned long long *f0, const volatile
     __threadfence_system();
 }
 
-__global__ void zero_headers(float4 *a, float4 *b)
+// Phase FINISH: wait for the neighbours' migration messages (peer mode), then put the four message headers and the
+// error word where the host can read them after one stream synchronisation - mapped pinned memory, no copies.
+__global__ void finish_headers(const volatile unsigned long long *f0, const volatile unsigned long long *f1, unsigned long long seq,
+                               int *err, const float4 *ms0, const float4 *ms1, const float4 *mi0, const float4 *mi1,
+                               volatile int4 *out)
 {
-    if (threadIdx.x == 0) {
-        a[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        b[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long t0 = clock64();
+    const long long limit = 20000000000ll;
+    for (int k = 0; k < 2; ++k) {
+        const volatile unsigned long long *f = k ? f1 : f0;
+        if (!f) continue;
+        while (*f < seq) {
+            if (clock64() - t0 > limit) {
+                atomicAdd(err, 1 << 16);
+                break;
+            }
+            __nanosleep(200);
+        }
     }
+    __threadfence_system();
+    const float4 *src[4] = {ms0, ms1, mi0, mi1};
+    for (int k = 0; k < 4; ++k) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (src[k]) {
+            const volatile int *p = reinterpret_cast<const volatile int *>(src[k]);
+            v = make_int4(p[0], p[1], p[2], p[3]);
+        }
+        out[k].x = v.x; out[k].y = v.y; out[k].z = v.z; out[k].w = v.w;
+    }
+    out[4].x = *reinterpret_cast<volatile int *>(err);
+    __threadfence_system();
 }
 
 int fail(plife_handle *h, int code, const char *msg) { return slab_fail(h, code, msg); }
@@ -208,6 +235,7 @@ void slab_release(plife_handle *h)
         S.peer_base[d] = nullptr;
         S.peer_ipc[d] = false;
     }
+    if (S.h_hdr) cudaFreeHost((void *)S.h_hdr);
     if (S.peer_mode) {
         cudaFree(S.xbuf);
         for (int d = 0; d < 2; d++) {
@@ -278,6 +306,10 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
             slab_release(h);
             return fail(h, PLIFE_ERR_OOM, "slab_configure: allocating exchange buffers failed");
         }
+    }
+    if (cudaHostAlloc((void **)&S.h_hdr, 5 * sizeof(int4), cudaHostAllocMapped) != cudaSuccess) {
+        slab_release(h);
+        return fail(h, PLIFE_ERR_OOM, "slab_configure: allocating the pinned header block failed");
     }
     S.phase = PLIFE_SLAB_SORT;
     h->prebinned = false;
@@ -386,8 +418,8 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         if (rc) return rc;
         const int sorted = h->cur ^ 1;
         dim3 grid(32, 2);
-        pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1]);
-        zero_headers<<<1, 32, 0, h->stream>>>(S.mig_send[0], S.mig_send[1]);
+        pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1],
+                                                    S.mig_send[0], S.mig_send[1]);
         if (S.peer_mode) {
             // my first row is the down neighbour's ghost row ABOVE its slab (its slot dir 1), and vice versa
             if (has_dn) push_msg<<<32, kThreads, 0, h->stream>>>(S.halo_send[0], halo_slot(dn, S, parity, 1), 1, g.nx, (int)S.halo_cap);
@@ -419,16 +451,17 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         return PLIFE_OK;
     }
     // PLIFE_SLAB_FINISH: headers back to the host (the only synchronisation of the step)
-    if (S.peer_mode && (has_dn || has_up))
-        wait_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr, S.seq, d_err);
-    int4 hs[4] = {};
-    int err = 0;
-    CUS(h, cudaMemcpyAsync(&hs[0], S.mig_send[0], 16, cudaMemcpyDeviceToHost, h->stream));
-    CUS(h, cudaMemcpyAsync(&hs[1], S.mig_send[1], 16, cudaMemcpyDeviceToHost, h->stream));
-    if (has_dn) CUS(h, cudaMemcpyAsync(&hs[2], mig_in[0], 16, cudaMemcpyDeviceToHost, h->stream));
-    if (has_up) CUS(h, cudaMemcpyAsync(&hs[3], mig_in[1], 16, cudaMemcpyDeviceToHost, h->stream));
-    CUS(h, cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    {
+        const bool waits = S.peer_mode && (has_dn || has_up);
+        finish_headers<<<1, 1, 0, h->stream>>>(waits && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, waits && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr,
+                                               S.seq, d_err, S.mig_send[0], S.mig_send[1], has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr,
+                                               S.h_hdr);
+    }
+    CUS(h, cudaGetLastError());
     CUS(h, cudaStreamSynchronize(h->stream));
+    int4 hs[4];
+    for (int k = 0; k < 4; k++) hs[k] = make_int4(S.h_hdr[k].x, S.h_hdr[k].y, S.h_hdr[k].z, S.h_hdr[k].w);
+    const int err = S.h_hdr[4].x;
     S.phase = PLIFE_SLAB_SORT;
     S.seq++;
     const int sent_dn = hs[0].x, sent_up = hs[1].x;
