@@ -225,11 +225,13 @@ struct StableKey {
         src -= n_old;
         return src < k_below ? src + base_below : src - k_below + base_above;
     }
+    __device__ __forceinline__ bool mixed(int max_src) const { return max_src >= n_old; } // the cell holds an arrival
 };
 
 // slot of `src` in the sorted array; also registers the leader (even rank) of every target pair of the cell
 struct IdentityKey { // single GPU: the pre-sort index is the previous array index
     __device__ __forceinline__ int operator()(int src) const { return src; }
+    __device__ __forceinline__ bool mixed(int) const { return false; }
 };
 
 template <bool STABLE, bool PAIRS, typename KEY>
@@ -241,17 +243,34 @@ __device__ __forceinline__ int sorted_slot(int d, int src, int c, const int32_t 
     int rank;
     if (STABLE) {
         const int e = __ldg(&cell_end[c]);
-        rank = 0;
-        const int ksrc = key(src);
-        // four keys per load: cells of an evolved state hold thousands of particles and this loop is O(count^2) per cell
+        // Raw pre-sort indices order the residents exactly like their keys do, and almost every cell holds residents
+        // only, so rank on the raw indices (four per load: cells of an evolved state hold thousands of particles and
+        // this loop is O(count^2) per cell) and track the largest one; only cells that received migrants (slab mode)
+        // are ranked again through the key.
         const int32_t *pp = perm - first;
+        rank = 0;
+        int mx = src;
         int k = s;
-        for (; k < e && ((k - first) & 3); ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
+        for (; k < e && ((k - first) & 3); ++k) {
+            const int q = __ldg(pp + k);
+            rank += (q < src) ? 1 : 0;
+            mx = max(mx, q);
+        }
         for (; k + 4 <= e; k += 4) {
             const int4 q = __ldg(reinterpret_cast<const int4 *>(pp + k));
-            rank += ((key(q.x) < ksrc) ? 1 : 0) + ((key(q.y) < ksrc) ? 1 : 0) + ((key(q.z) < ksrc) ? 1 : 0) + ((key(q.w) < ksrc) ? 1 : 0);
+            rank += ((q.x < src) ? 1 : 0) + ((q.y < src) ? 1 : 0) + ((q.z < src) ? 1 : 0) + ((q.w < src) ? 1 : 0);
+            mx = max(max(mx, q.x), max(q.y, max(q.z, q.w)));
         }
-        for (; k < e; ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
+        for (; k < e; ++k) {
+            const int q = __ldg(pp + k);
+            rank += (q < src) ? 1 : 0;
+            mx = max(mx, q);
+        }
+        if (key.mixed(mx)) {
+            rank = 0;
+            const int ksrc = key(src);
+            for (k = s; k < e; ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
+        }
     } else {
         rank = d + first - s;
     }
