@@ -272,13 +272,12 @@ def run_ours(args):
 
     # ---- per-kernel device time of the same steps (events between kernels) ----
     with torch.cuda.stream(stream):
-        if world == 1:
-            p.set_profiling(True)
-            run_steps(args.steps)
-            kt = p.kernel_times()
-            p.set_profiling(False)
-        else:
-            kt = {k: (0.0, 0) for k in N.KERNEL_NAMES}
+        # slabs: every rank runs the same profiled steps (the exchange needs all of them); rank 0's times are reported,
+        # and the "gather" bucket there also holds the halo pack / push / wait / unpack kernels
+        p.set_profiling(True)
+        run_steps(args.steps)
+        kt = p.kernel_times()
+        p.set_profiling(False)
     force_ms = kt["force"][0] / max(1, kt["force"][1])
     per_kernel = {k: v[0] / args.steps for k, v in kt.items()}
 
@@ -362,7 +361,7 @@ def run_ours(args):
         return 0
 
     hbm_peak, peak_src = peaks()
-    force_gbs = ALGO_BYTES_FORCE * n / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
+    force_gbs = ALGO_BYTES_FORCE * n_local / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None  # one launch = this rank's particles
     step_gbs = ALGO_BYTES_STEP * n / (ms / args.steps * 1e-3) / 1e9
     pair_rate = stats["pair_evals"] * world * args.steps / (ms * 1e-3)
     fp32_nominal_tf = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
@@ -398,12 +397,13 @@ def run_ours(args):
         "pair_evals_per_sec": pair_rate,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "per step: set_settings + set_matrix from host, plife_step, full fp32 snapshot (xy,vxy,type) into pinned host memory" + " (copy of step k overlaps step k+1; every snapshot awaited)"},
-        # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add pack,
-        # 4 pushes, 2 signals, the halo wait + unpack and the wait-and-collect of phase FINISH (arrival appends not counted)
-        "gpu_launches": (6 if world == 1 else 16) * args.steps * world,
+        # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add the halo pack
+        # (writes into the neighbours' memory and signals), the halo wait + unpack, 2 migration pushes (with signal) and the
+        # wait-and-collect of phase FINISH; arrival appends are not counted
+        "gpu_launches": (6 if world == 1 else (11 if args.exchange == "peer" else 9)) * args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "force_kernel (3x3 force + friction + integrate + wrap)",
-                     "achieved": force_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": force_gbs / hbm_peak if force_gbs else None, "traffic": 54.5 * cfg["n_per_gpu"] / 1e9 if world == 1 else None,
+                     "achieved": force_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": force_gbs / hbm_peak if force_gbs else None, "traffic": 54.5 * cfg["n_per_gpu"] / 1e9,
                      "traffic_note": "GB per launch: dram__bytes_read+write of force_kernel_staged from profiles/r1_force_kernel.md (54.5 B/particle)",
                      "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES_FORCE,
                      "binding": "fp32 issue (9*rho-1 = 143 pair evaluations per particle at 16 particles/cell); HBM fraction is low by construction, see fp32"},

@@ -317,7 +317,7 @@ int resolve_timings(plife_handle *h)
 }
 
 // makeContainers (B/Physics.java:309-354): state buffer cur -> sorted into cur^1
-int sort_current(plife_handle *h, const Grid &g, StepTimer *tm)
+int sort_current(plife_handle *h, const Grid &g, StepTimer *tm, bool mark_gather_end = true)
 {
     int rc = ensure_cells(h, (int64_t)g.nx * g.nly);
     if (rc) return rc;
@@ -337,7 +337,7 @@ int sort_current(plife_handle *h, const Grid &g, StepTimer *tm)
     CU(h, launch_scatter(h, g));
     if (tm) CU(h, tm->mark(3));
     CU(h, launch_gather(h, g));
-    if (tm) CU(h, tm->mark(4));
+    if (tm && mark_gather_end) CU(h, tm->mark(4));
     return PLIFE_OK;
 }
 
@@ -389,15 +389,31 @@ int edit_fail(plife_handle *h, int code, const char *msg) { return fail(h, code,
 int edit_grow(plife_handle *h, int64_t cap) { return grow_preserve(h, cap); }
 int slab_make_grid(plife_handle *h, Grid *g) { return make_grid(h, g); }
 int slab_fail(plife_handle *h, int code, const char *msg) { return fail(h, code, "%s", msg); }
+// Slab-mode profiling: event 4 is recorded right before the force kernel, so the K_GATHER bucket also holds the halo
+// pack / push / wait / unpack kernels that run between the gather and the force pass; K_FORCE is the kernel alone.
 int slab_sort(plife_handle *h, const Grid &g)
 {
     int rc = sync_matrix(h);
     if (rc) return rc;
-    return sort_current(h, g, nullptr);
+    StepTimer tm(h);
+    rc = sort_current(h, g, tm.on ? &tm : nullptr, false);
+    h->slab_timing = tm.t;
+    h->slab_timing_on = tm.on && rc == PLIFE_OK;
+    return rc;
 }
 cudaError_t slab_force(plife_handle *h, const Grid &g, double dt)
 {
-    cudaError_t e = launch_force_f32(h, make_params<float>(h, g, dt));
+    StepTimer tm(h);
+    tm.t = h->slab_timing;
+    tm.on = h->slab_timing_on;
+    cudaError_t e = tm.mark(4);
+    if (e == cudaSuccess) e = launch_force_f32(h, make_params<float>(h, g, dt));
+    if (e == cudaSuccess) e = tm.mark(PLIFE_K_COUNT);
+    if (tm.on && e == cudaSuccess) {
+        h->pending.push_back(tm.t);
+        if (h->pending.size() >= 256 && resolve_timings(h) != PLIFE_OK) e = cudaErrorUnknown;
+    }
+    h->slab_timing_on = false;
     h->prebinned = true; // the epilogue binned the stayers; arrivals are binned by phase FINISH
     h->prebinned_grid = g;
     h->count_dirty = true;

@@ -188,6 +188,8 @@ struct plife_handle {
         cudaEvent_t ev[PLIFE_K_COUNT + 1];
     };
     std::vector<PendingTiming> pending;
+    PendingTiming slab_timing{}; // slab mode: one step's events span the SORT and FORCE phases
+    bool slab_timing_on = false;
 
     std::atomic<int> stop_requested{0};
     std::string last_error;

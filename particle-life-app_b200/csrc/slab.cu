@@ -49,12 +49,34 @@ __device__ __forceinline__ int offsets_records(int nx) { return (nx + 3) >> 2; }
 
 // dir 0: first owned row (local row 1) -> becomes the down neighbour's top ghost row
 // dir 1: last owned row (local row nly-2) -> becomes the up neighbour's bottom ghost row
+// Completion signal of a multi-CTA producer: every CTA fences its (remote) writes and takes a ticket; the CTA that draws
+// the last one publishes `seq` in the consumer's flag and resets the ticket for the next step.
+__device__ __forceinline__ void signal_when_all_done(unsigned int *ticket, volatile unsigned long long *flag, unsigned long long seq,
+                                                     unsigned int nblocks)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == nblocks - 1) {
+            *ticket = 0;
+            __threadfence_system();
+            *flag = seq;
+        }
+    }
+}
+
+// `msg0/msg1` are where the two messages are written: the local send buffers (external exchange), or - peer exchange -
+// straight into the neighbours' receive slots over NVLink, followed by the flag (flag0/flag1 non-NULL).
 __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__ pt_sorted, const int32_t *__restrict__ cell_end,
                                                       Grid g, int halo_cap, float4 *__restrict__ msg0, float4 *__restrict__ msg1,
-                                                      float4 *__restrict__ mig0, float4 *__restrict__ mig1)
+                                                      float4 *__restrict__ mig0, float4 *__restrict__ mig1,
+                                                      volatile unsigned long long *flag0, volatile unsigned long long *flag1,
+                                                      unsigned int *tickets, unsigned long long seq)
 {
     const int dir = blockIdx.y;
     float4 *msg = dir ? msg1 : msg0;
+    volatile unsigned long long *flag = dir ? flag1 : flag0;
     if (blockIdx.x == 0 && threadIdx.x == 0) (dir ? mig1 : mig0)[0] = make_float4(0.f, 0.f, 0.f, 0.f); // this step's migration cursor
     const int row = dir ? g.nly - 2 : 1;
     const int start = __ldg(cell_end + row * g.nx - 1);
@@ -66,22 +88,49 @@ __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__
         int4 hd = make_int4(count <= halo_cap ? count : -count, g.nx, 0, 0);
         msg[0] = *reinterpret_cast<float4 *>(&hd);
     }
-    if (count > halo_cap) return; // overflow: reported by the receiver and by phase FINISH
-    int32_t *off = reinterpret_cast<int32_t *>(msg + 1);
-    for (int c = t; c < 4 * noff; c += gridDim.x * kThreads) off[c] = c < g.nx ? __ldg(cell_end + row * g.nx + c) - start : 0;
-    for (int k = t; k < count; k += gridDim.x * kThreads) msg[1 + noff + k] = __ldg(pt_sorted + start + k);
+    if (count <= halo_cap) { // else overflow: reported by the receiver and by phase FINISH
+        int32_t *off = reinterpret_cast<int32_t *>(msg + 1);
+        for (int c = t; c < 4 * noff; c += gridDim.x * kThreads) off[c] = c < g.nx ? __ldg(cell_end + row * g.nx + c) - start : 0;
+        for (int k = t; k < count; k += gridDim.x * kThreads) msg[1 + noff + k] = __ldg(pt_sorted + start + k);
+    }
+    if (flag) signal_when_all_done(tickets + dir, flag, seq, gridDim.x);
 }
 
 // which 0: ghost row below (local row 0), right-aligned before the owned block at `first`
 // which 1: ghost row above (local row nly-1), placed after the owned block
 __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_sorted, int32_t *__restrict__ cell_end, Grid g,
-                                                        int first, int n, const float4 *__restrict__ msg0,
-                                                        const float4 *__restrict__ msg1, int *__restrict__ err)
+                                                        int first, int n, const float4 *msg0, const float4 *msg1, int *__restrict__ err,
+                                                        const volatile unsigned long long *flag0, const volatile unsigned long long *flag1,
+                                                        unsigned long long seq)
 {
     const int which = blockIdx.y;
     const float4 *msg = which ? msg1 : msg0;
     if (!msg) return;
-    const int4 hd = *reinterpret_cast<const int4 *>(msg);
+    // peer exchange: the message is complete once the neighbour's flag reaches this step's sequence number; every CTA
+    // checks for itself (bounded spin, so a dead peer cannot hang the GPU).  The message was written during this
+    // kernel's lifetime, so it is read with ld.cg, not through the read-only path.
+    const volatile unsigned long long *flag = which ? flag1 : flag0;
+    if (flag) {
+        __shared__ int s_timeout;
+        if (threadIdx.x == 0) {
+            s_timeout = 0;
+            const long long t0 = clock64();
+            while (*flag < seq) {
+                if (clock64() - t0 > 20000000000ll) {
+                    s_timeout = 1;
+                    break;
+                }
+                __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (s_timeout) {
+            if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(err, 1 << 16);
+            return;
+        }
+    }
+    const int4 hd = __ldcg(reinterpret_cast<const int4 *>(msg));
     const int t = blockIdx.x * kThreads + threadIdx.x;
     if (hd.x < 0 || hd.y != g.nx) {
         if (t == 0) atomicAdd(err, 1);
@@ -92,9 +141,9 @@ __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_
     const int base = which ? first + n : first - count;
     const int row = which ? g.nly - 1 : 0;
     const int32_t *off = reinterpret_cast<const int32_t *>(msg + 1);
-    for (int c = t; c < g.nx; c += gridDim.x * kThreads) cell_end[row * g.nx + c] = base + off[c];
+    for (int c = t; c < g.nx; c += gridDim.x * kThreads) cell_end[row * g.nx + c] = base + __ldcg(off + c);
     if (which == 0 && t == 0) cell_end[-1] = base;
-    for (int k = t; k < count; k += gridDim.x * kThreads) pt_sorted[base + k] = __ldg(msg + 1 + noff + k);
+    for (int k = t; k < count; k += gridDim.x * kThreads) pt_sorted[base + k] = __ldcg(msg + 1 + noff + k);
 }
 
 // Arrivals: message records {x,y,type,id},{vx,vy,source slot,-}.  Each is placed at
@@ -123,41 +172,16 @@ __global__ void __launch_bounds__(kThreads) append_arrivals(const float4 *__rest
 
 // copy a message (its used records only) into the neighbour's receive slot
 __global__ void __launch_bounds__(kThreads) push_msg(const float4 *__restrict__ local, float4 *__restrict__ peer, int is_halo, int nx,
-                                                     int cap)
+                                                     int cap, volatile unsigned long long *flag, unsigned int *ticket,
+                                                     unsigned long long seq)
 {
     const int count = *reinterpret_cast<const int *>(local);
     int nrec;
     if (is_halo) nrec = count < 0 ? 1 : 1 + offsets_records(nx) + count;
     else nrec = 1 + 2 * min(count, cap);
     for (int k = blockIdx.x * kThreads + threadIdx.x; k < nrec; k += gridDim.x * kThreads) peer[k] = local[k];
-    __threadfence_system();
-}
-
-__global__ void signal_flags(volatile unsigned long long *f0, volatile unsigned long long *f1, unsigned long long seq)
-{
-    __threadfence_system();
-    if (f0) *f0 = seq;
-    if (f1) *f1 = seq;
-}
-
-// spin until both flags (written by the neighbours) reach seq; bounded so a dead peer cannot hang the GPU
-__global__ void wait_flags(const volatile unsigned long long *f0, const volatile unsigned long long *f1, unsigned long long seq,
-                           int *err)
-{
-    const long long t0 = clock64();
-    const long long limit = 20000000000ll; // ~10 s of SM clocks
-    for (int k = 0; k < 2; ++k) {
-        const volatile unsigned long long *f = k ? f1 : f0;
-        if (!f) continue;
-        while (*f < seq) {
-            if (clock64() - t0 > limit) {
-                atomicAdd(err, 1 << 16); // timeout
-                return;
-            }
-            __nanosleep(200);
-        }
-    }
-    __threadfence_system();
+    if (flag) signal_when_all_done(ticket, flag, seq, gridDim.x);
+    else __threadfence_system();
 }
 
 // Phase FINISH: wait for the neighbours' migration messages (peer mode), then put the four message headers and the
@@ -211,7 +235,7 @@ int fail(plife_handle *h, int code, const char *msg) { return slab_fail(h, code,
 //                 then halo slots [parity][dir][hrec], then migration slots [parity][dir][mrec]
 namespace {
 constexpr int kFlagRecords = 8;
-enum { F_HALO_DN = 0, F_HALO_UP = 1, F_MIG_DN = 2, F_MIG_UP = 3 };
+enum { F_HALO_DN = 0, F_HALO_UP = 1, F_MIG_DN = 2, F_MIG_UP = 3, F_TICKETS = 8 }; // u64 slots of the flag block; 8..9 hold four local u32 tickets
 
 inline float4 *halo_slot(float4 *base, const SlabState &S, int parity, int dir)
 {
@@ -418,14 +442,18 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         if (rc) return rc;
         const int sorted = h->cur ^ 1;
         dim3 grid(32, 2);
-        pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1],
-                                                    S.mig_send[0], S.mig_send[1]);
+        unsigned int *tickets = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(S.xbuf) + F_TICKETS); // 4 local counters
         if (S.peer_mode) {
-            // my first row is the down neighbour's ghost row ABOVE its slab (its slot dir 1), and vice versa
-            if (has_dn) push_msg<<<32, kThreads, 0, h->stream>>>(S.halo_send[0], halo_slot(dn, S, parity, 1), 1, g.nx, (int)S.halo_cap);
-            if (has_up) push_msg<<<32, kThreads, 0, h->stream>>>(S.halo_send[1], halo_slot(up, S, parity, 0), 1, g.nx, (int)S.halo_cap);
-            if (has_dn || has_up)
-                signal_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(dn, F_HALO_UP) : nullptr, has_up ? flag_of(up, F_HALO_DN) : nullptr, S.seq);
+            // my first row is the down neighbour's ghost row ABOVE its slab (its slot dir 1), and vice versa; the pack kernel
+            // writes it there and raises the neighbour's flag when its last CTA is done
+            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap,
+                                                        has_dn ? halo_slot(dn, S, parity, 1) : S.halo_send[0],
+                                                        has_up ? halo_slot(up, S, parity, 0) : S.halo_send[1], S.mig_send[0], S.mig_send[1],
+                                                        has_dn ? flag_of(dn, F_HALO_UP) : nullptr, has_up ? flag_of(up, F_HALO_DN) : nullptr,
+                                                        tickets, S.seq);
+        } else {
+            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1],
+                                                        S.mig_send[0], S.mig_send[1], nullptr, nullptr, nullptr, 0ull);
         }
         CUS(h, cudaGetLastError());
         S.phase = PLIFE_SLAB_FORCE;
@@ -433,18 +461,20 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
     }
     if (phase == PLIFE_SLAB_FORCE) {
         const int sorted = h->cur ^ 1;
-        if (S.peer_mode && (has_dn || has_up))
-            wait_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr, has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq, d_err);
         dim3 grid(32, 2);
+        const bool peer = S.peer_mode;
         unpack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, first, (int)h->n,
-                                                      has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr, d_err);
+                                                      has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr, d_err,
+                                                      peer && has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr,
+                                                      peer && has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq);
         CUS(h, cudaGetLastError());
         CUS(h, slab_force(h, g, dt));
         if (S.peer_mode) {
-            if (has_dn) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[0], mig_slot(dn, S, parity, 1), 0, g.nx, (int)S.mig_cap);
-            if (has_up) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[1], mig_slot(up, S, parity, 0), 0, g.nx, (int)S.mig_cap);
-            if (has_dn || has_up)
-                signal_flags<<<1, 1, 0, h->stream>>>(has_dn ? flag_of(dn, F_MIG_UP) : nullptr, has_up ? flag_of(up, F_MIG_DN) : nullptr, S.seq);
+            unsigned int *tickets = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(S.xbuf) + F_TICKETS);
+            if (has_dn) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[0], mig_slot(dn, S, parity, 1), 0, g.nx, (int)S.mig_cap,
+                                                                flag_of(dn, F_MIG_UP), tickets + 2, S.seq);
+            if (has_up) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[1], mig_slot(up, S, parity, 0), 0, g.nx, (int)S.mig_cap,
+                                                                flag_of(up, F_MIG_DN), tickets + 3, S.seq);
             CUS(h, cudaGetLastError());
         }
         S.phase = PLIFE_SLAB_FINISH;
