@@ -611,3 +611,26 @@ def test_clustered_state_many_steps_fp32_tracks_fp64(native_lib):
     assert np.median(d) < 1e-5 and np.percentile(d, 99) < 1e-3
     counts = np.diff(np.r_[0, a.containers()])
     assert counts.max() > 500
+
+
+def test_one_huge_cell_fp64_and_fp32(native_lib):
+    """24 000 particles inside a single interior cell plus a thin background: row ranges longer than the 14-bit offsets
+    of the hit list (forces a rebase mid-row), hundreds of list flushes per lane, hundreds of staging chunks per CTA.
+    fp64 must stay bit-identical to the oracle."""
+    rng = np.random.default_rng(31)
+    n_blob, n_bg, m, rmax = 24_000, 3_000, 3, 0.05
+    centre = np.array([0.525, 0.475])                       # middle of cell (10, 9) of a 20 x 20 grid
+    pos = np.concatenate([centre + rng.normal(0, 0.006, (n_blob, 2)), rng.random((n_bg, 2))])
+    pos = np.clip(pos, 0, 0.999999).astype(np.float32).astype(np.float64)
+    vel = np.zeros_like(pos)
+    types = rng.integers(0, m, len(pos)).astype(np.int32)
+    matrix = rng.random((m, m)) * 2 - 1
+    o = oracle_step(pos, vel, types, matrix, rmax=rmax, wrap=True, dt=DT, threads=8)
+    opos, ovel, _, oid = o.get_particles()
+    assert np.diff(np.r_[0, o.containers()]).max() > 16_384
+    g = gpu_step(native_lib, plife.F64, pos, vel, types, matrix, rmax=rmax, wrap=True, dt=DT)
+    got = g.download()
+    assert np.array_equal(got.id, oid) and np.array_equal(got.velocity, ovel) and np.array_equal(got.position, opos)
+    g = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, rmax=rmax, wrap=True, dt=DT)
+    got = g.download()
+    assert np.array_equal(got.id, oid) and rel_l2(got.velocity, ovel) <= 1e-5
