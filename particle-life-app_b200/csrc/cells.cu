@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(1024) scan_sums(u64 *__restrict__ tile_sums, i
 
 // writes the exclusive prefixes (the cursor start of every cell, the first pair of every cell) and
 // zeroes count for the next step
+template <bool PAIRS>
 __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__ count, int64_t ncell,
                                                            const u64 *__restrict__ tile_sums,
                                                            int32_t *__restrict__ cell_end, int32_t *__restrict__ pair_start)
@@ -170,14 +171,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
             q.z = (int)ex; r.z = (int)(ex >> 32); ex += pack_count(v[4 * k + 2]);
             q.w = (int)ex; r.w = (int)(ex >> 32); ex += pack_count(v[4 * k + 3]);
             o[k] = q;
-            po[k] = r;
+            if (PAIRS) po[k] = r; // only the two-targets-per-lane kernel reads pair_start
         }
     } else {
 #pragma unroll
         for (int k = 0; k < kScanItems; k++) {
             if (first + k < ncell) {
                 cell_end[first + k] = (int)ex;
-                pair_start[first + k] = (int)(ex >> 32);
+                if (PAIRS) pair_start[first + k] = (int)(ex >> 32);
             }
             ex += pack_count(v[k]);
         }
@@ -517,7 +518,8 @@ cudaError_t launch_scan(plife_handle *h, const Grid &g)
     u64 *ts = reinterpret_cast<u64 *>(h->d_tile_sums);
     scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts);
     scan_sums<<<1, 1024, 0, h->stream>>>(ts, ntiles, first_index(h), h->d_cell_end, npairs_ptr(h));
-    scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts, h->d_cell_end, h->d_pair_start);
+    if (h->flags & PLIFE_FLAG_PAIRS) scan_apply<true><<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts, h->d_cell_end, h->d_pair_start);
+    else scan_apply<false><<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts, h->d_cell_end, h->d_pair_start);
     return cudaGetLastError();
 }
 
