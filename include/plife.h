@@ -180,8 +180,10 @@ int plife_get_step_stats(plife_handle *h, plife_step_stats *out);
  * (sum of mix64(id_j)) per particle, in the sorted order.  Synchronises. */
 int plife_debug_neighbors(plife_handle *h, int32_t *count, uint64_t *hash);
 /* Per-kernel device time: enable, run steps, read accumulated milliseconds and
- * launch counts (PLIFE_K_* slots).  Profiling inserts events between kernels
- * and disables graph replay. */
+ * launch counts (PLIFE_K_* slots).  Profiling inserts events between kernels.
+ * In slab mode the PLIFE_K_GATHER slot also covers the halo pack / wait / unpack
+ * kernels that run between the gather and the force pass; PLIFE_K_FORCE is the
+ * force kernel alone. */
 int plife_set_profiling(plife_handle *h, int32_t enabled);
 int plife_kernel_times(plife_handle *h, double *ms_out, int64_t *launches_out);
 /* Measured FP32 peak of a device: an FFMA loop (8 independent chains per thread, 2 FLOP per FFMA), best of 6
