@@ -77,5 +77,22 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_c_client() -> str:
+    """gcc examples/plife_headless.c against include/plife.h and libplife.so: a plain C user of the ABI
+    (no CUDA headers, no Python).  The binary is git-ignored and travels to the GPU box like the library."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "examples", "plife_headless.c")
+    out = os.path.join(root, "examples", "plife_headless")
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(OUT), os.path.getmtime(os.path.join(INCLUDE, "plife.h"))):
+        return out
+    libdir = os.path.dirname(OUT)
+    cmd = ["gcc", "-O2", "-std=c11", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wextra", "-Werror", "-I", INCLUDE, src, "-o", out,
+           "-L", libdir, "-lplife", "-Wl,-rpath,$ORIGIN/../particle-life-app_b200/plife"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"gcc failed on the C client:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
