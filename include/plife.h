@@ -46,7 +46,7 @@ extern "C" {
 
 /* plife_config.flags */
 #define PLIFE_FLAG_UNSTABLE_SORT 1 /* skip the in-cell stable ordering (faster; order in a cell arbitrary) */
-#define PLIFE_FLAG_NO_GRAPH 2      /* never capture the step into a CUDA graph */
+#define PLIFE_FLAG_NO_GRAPH 2      /* reserved: this version never captures the step into a CUDA graph */
 #define PLIFE_FLAG_PAIRS 16        /* fp32, kind 0: opt into the two-targets-per-lane force kernel (experimental) */
 #define PLIFE_FLAG_NO_FUSED_BIN 8  /* do not fuse the next step's binning into the force pass */
 #define PLIFE_FLAG_FORCE_V1 4      /* fp32: use the global-memory force kernel instead of the shared-memory staged one */
