@@ -10,7 +10,7 @@ particle set: cell-list rebuild + 3x3 force pass + friction/integrate/wrap.
             launching stream, max over ranks
   e2e       the same metric through the C ABI with host buffers: every step
             re-sends settings + matrix from host memory and pulls the full fp32
-            render snapshot (xy, vxy, type = 20 B/particle) into pinned host memory
+            render snapshot (xy, vxy as fp32, type as u8 = 17 B/particle) into pinned host memory
   roofline  dominant kernel (force/integrate) against measured HBM peak; the
             path is FP32-issue bound at the benchmark density, so `fp32` carries
             the binding fraction
@@ -285,9 +285,9 @@ def run_ours(args):
     ncap = n if world == 1 else n_local + n_local // 8 + 65536
     pin_pos = torch.empty((ncap, 2), dtype=torch.float32).pin_memory()
     pin_vel = torch.empty((ncap, 2), dtype=torch.float32).pin_memory()
-    pin_typ = torch.empty((ncap,), dtype=torch.int32).pin_memory()
+    pin_typ = torch.empty((ncap,), dtype=torch.uint8).pin_memory()  # one byte per type: the app allows at most 256 types
     h2d = (matrix.nbytes + 32) * world
-    d2h = n * 20
+    d2h = n * 17  # xy + vxy as fp32, type as u8
     e2e_steps = max(3, min(args.steps, 10))
 
     pins = [(pin_pos, pin_vel, pin_typ),
@@ -303,7 +303,7 @@ def run_ours(args):
         p.snapshot_wait()  # the previous snapshot is complete (its buffer is the renderer's now)
         a, b, c = pins[e2e_k[0] & 1]
         e2e_k[0] += 1
-        p.snapshot_async(a.data_ptr(), b.data_ptr(), c.data_ptr())
+        p.snapshot_async(a.data_ptr(), b.data_ptr(), c.data_ptr(), types_u8=True)
 
     with torch.cuda.stream(stream):
         for _ in range(3):
@@ -396,7 +396,7 @@ def run_ours(args):
                    "parallelism": "1 GPU" if world == 1 else f"{world} slabs over grid rows, halo exchange + particle migration every step via " + ("kernel pushes into CUDA-IPC peer memory over NVLink" if args.exchange == "peer" else "NCCL send/recv")},
         "pair_evals_per_sec": pair_rate,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "per step: set_settings + set_matrix from host, plife_step, full fp32 snapshot (xy,vxy,type) into pinned host memory" + " (copy of step k overlaps step k+1; every snapshot awaited)"},
+                "what": "per step: set_settings + set_matrix from host, plife_step, full snapshot (xy, vxy as fp32, type as u8: 17 B/particle) into pinned host memory" + " (copy of step k overlaps step k+1; every snapshot awaited)"},
         # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add the halo pack
         # (writes into the neighbours' memory and signals), the halo wait + unpack, 2 migration pushes (with signal) and the
         # wait-and-collect of phase FINISH; arrival appends are not counted

@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(kThreads) init_uniform_f64(StateF64 s, int n, 
 }
 
 __global__ void __launch_bounds__(kThreads) snapshot_from_f32(const float4 *__restrict__ pt, const float2 *__restrict__ vel,
-                                                              int n, float2 *pos_out, float2 *vel_out, int32_t *type_out)
+                                                              int n, float2 *pos_out, float2 *vel_out, int32_t *type_out,
+                                                              uint8_t *type8_out)
 {
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
@@ -408,10 +409,11 @@ __global__ void __launch_bounds__(kThreads) snapshot_from_f32(const float4 *__re
     if (pos_out) pos_out[i] = make_float2(p.x, p.y);
     if (vel_out) vel_out[i] = __ldg(&vel[i]);
     if (type_out) type_out[i] = __float_as_int(p.z);
+    if (type8_out) type8_out[i] = (uint8_t)__float_as_int(p.z); // m <= 256
 }
 
 __global__ void __launch_bounds__(kThreads) snapshot_from_f64(StateF64 s, int n, float2 *pos_out, float2 *vel_out,
-                                                              int32_t *type_out)
+                                                              int32_t *type_out, uint8_t *type8_out)
 {
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(kThreads) snapshot_from_f64(StateF64 s, int n,
         vel_out[i] = make_float2((float)v.x, (float)v.y);
     }
     if (type_out) type_out[i] = s.type[i];
+    if (type8_out) type8_out[i] = (uint8_t)s.type[i];
 }
 
 // Slab mode: the array holds dead slots (particles that migrated away) until the next cell-list build; the
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(1024) scan_block_counts(int *block_counts, int
 __global__ void __launch_bounds__(kThreads) snapshot_live_f32(const float4 *__restrict__ pt, const float2 *__restrict__ vel,
                                                               const int32_t *__restrict__ cell, int n_phys,
                                                               const int *__restrict__ block_offsets, float2 *pos_out,
-                                                              float2 *vel_out, int32_t *type_out)
+                                                              float2 *vel_out, int32_t *type_out, uint8_t *type8_out)
 {
     __shared__ int warp_sums[kThreads / 32];
     int i = blockIdx.x * kThreads + threadIdx.x;
@@ -492,6 +495,7 @@ __global__ void __launch_bounds__(kThreads) snapshot_live_f32(const float4 *__re
     if (pos_out) pos_out[off] = make_float2(p.x, p.y);
     if (vel_out) vel_out[off] = __ldg(&vel[i]);
     if (type_out) type_out[off] = __float_as_int(p.z);
+    if (type8_out) type8_out[off] = (uint8_t)__float_as_int(p.z);
 }
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -604,7 +608,7 @@ cudaError_t launch_init_uniform_owned(plife_handle *h, int64_t n_global, uint64_
     return cudaGetLastError();
 }
 
-cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32_t *type)
+cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32_t *type, uint8_t *type8)
 {
     int n = (int)h->n;
     if (n == 0) return cudaSuccess;
@@ -613,13 +617,13 @@ cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32
         int *d_blocks = h->d_perm; // scratch: not live between steps
         live_counts<<<nb, kThreads, 0, h->stream>>>(h->d_cell, np, d_blocks);
         scan_block_counts<<<1, 1024, 0, h->stream>>>(d_blocks, nb);
-        snapshot_live_f32<<<nb, kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, h->d_cell, np, d_blocks, pos, vel, type);
+        snapshot_live_f32<<<nb, kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, h->d_cell, np, d_blocks, pos, vel, type, type8);
         return cudaGetLastError();
     }
     if (h->precision == PLIFE_F32)
-        snapshot_from_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, n, pos, vel, type);
+        snapshot_from_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, h->s32[h->cur].vel, n, pos, vel, type, type8);
     else
-        snapshot_from_f64<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s64[h->cur], n, pos, vel, type);
+        snapshot_from_f64<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s64[h->cur], n, pos, vel, type, type8);
     return cudaGetLastError();
 }
 

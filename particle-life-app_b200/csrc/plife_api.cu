@@ -717,7 +717,7 @@ int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *t
 // Display-time handoff without stalling the physics: the snapshot kernel runs on the compute stream into one
 // of two staging buffers, the device->host copies run on a separate copy stream, and the physics may step on
 // while they are in flight.  The caller's buffers (ideally pinned) must stay valid until plife_snapshot_wait().
-int plife_snapshot_async(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type)
+static int snapshot_async_impl(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type, uint8_t *type8)
 {
     CHECK_HANDLE(h);
     const int64_t n = h->n;
@@ -746,16 +746,28 @@ int plife_snapshot_async(plife_handle *h, float *pos_xy, float *vel_xy, int32_t 
     float2 *dv = dp + n;
     int32_t *dt = (int32_t *)(dv + n);
     CU(h, cudaStreamWaitEvent(h->stream, h->snap_done[k], 0)); // the copy that last used this buffer has finished
-    void *save = h->d_snap;
-    CU(h, launch_snapshot_f32(h, pos_xy ? dp : nullptr, vel_xy ? dv : nullptr, type ? dt : nullptr));
-    (void)save;
+    uint8_t *dt8 = reinterpret_cast<uint8_t *>(dt); // the compact form reuses the type region
+    if (type && type8) return fail(h, PLIFE_ERR_INVALID, "snapshot: int32 and u8 types requested together");
+    if (type8 && h->m > 256) return fail(h, PLIFE_ERR_STATE, "snapshot: more than 256 types do not fit u8");
+    CU(h, launch_snapshot_f32(h, pos_xy ? dp : nullptr, vel_xy ? dv : nullptr, type ? dt : nullptr, type8 ? dt8 : nullptr));
     CU(h, cudaEventRecord(h->snap_ready[k], h->stream));
     CU(h, cudaStreamWaitEvent(h->copy_stream, h->snap_ready[k], 0));
     if (pos_xy) CU(h, cudaMemcpyAsync(pos_xy, dp, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->copy_stream));
     if (vel_xy) CU(h, cudaMemcpyAsync(vel_xy, dv, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->copy_stream));
     if (type) CU(h, cudaMemcpyAsync(type, dt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (type8) CU(h, cudaMemcpyAsync(type8, dt8, (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
     CU(h, cudaEventRecord(h->snap_done[k], h->copy_stream));
     return PLIFE_OK;
+}
+
+int plife_snapshot_async(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type)
+{
+    return snapshot_async_impl(h, pos_xy, vel_xy, type, nullptr);
+}
+
+int plife_snapshot_async_u8(plife_handle *h, float *pos_xy, float *vel_xy, uint8_t *type_u8)
+{
+    return snapshot_async_impl(h, pos_xy, vel_xy, nullptr, type_u8);
 }
 
 int plife_snapshot_wait(plife_handle *h)

@@ -205,7 +205,7 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g);
 cudaError_t launch_type_histogram(plife_handle *h, unsigned long long *d_hist);
 cudaError_t launch_init_uniform(plife_handle *h, int64_t n, uint64_t seed);
 cudaError_t launch_init_uniform_owned(plife_handle *h, int64_t n_global, uint64_t seed, const Grid &g, int *d_counter);
-cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32_t *type);
+cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32_t *type, uint8_t *type8 = nullptr);
 
 // force_f32.cu / force_f64.cu
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p);

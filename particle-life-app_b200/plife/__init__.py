@@ -127,13 +127,17 @@ class NativePhysics:
             return x.ctypes.data
         self._check(self.L.plife_download_f32(self.h, addr(pos), addr(vel), addr(types)))
 
-    def snapshot_async(self, pos=None, vel=None, types=None):
-        """Start a float snapshot that overlaps the following steps; `snapshot_wait` completes it."""
+    def snapshot_async(self, pos=None, vel=None, types=None, types_u8=False):
+        """Start a float snapshot that overlaps the following steps; `snapshot_wait` completes it.  `types` may be an
+        int32 or a uint8 array (addresses: say which with `types_u8`); the one-byte form moves 17 B/particle, not 20."""
         def addr(x):
             if x is None or isinstance(x, int):
                 return x
             return x.ctypes.data
-        self._check(self.L.plife_snapshot_async(self.h, addr(pos), addr(vel), addr(types)))
+        if types is not None and not isinstance(types, int):
+            types_u8 = types.dtype == np.uint8
+        fn = self.L.plife_snapshot_async_u8 if types_u8 else self.L.plife_snapshot_async
+        self._check(fn(self.h, addr(pos), addr(vel), addr(types)))
 
     def snapshot_wait(self):
         self._check(self.L.plife_snapshot_wait(self.h))

@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         "plife_download": (C.c_int, [vp, vp, vp, vp, vp]),
         "plife_download_f32": (C.c_int, [vp, vp, vp, vp]),
         "plife_snapshot_async": (C.c_int, [vp, vp, vp, vp]),
+        "plife_snapshot_async_u8": (C.c_int, [vp, vp, vp, vp]),
         "plife_snapshot_wait": (C.c_int, [vp]),
         "plife_init_uniform": (C.c_int, [vp, i64, C.c_uint64]),
         "plife_random_matrix": (C.c_int, [vp, i32, C.c_uint64]),

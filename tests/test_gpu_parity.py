@@ -348,6 +348,20 @@ def test_snapshots_match_download(native_lib):
         assert np.array_equal(got[1], ref.velocity.astype(np.float32))
         assert np.array_equal(got[2], ref.type)
     assert not np.array_equal(p.download().position, ref.position)
+    # compact form: one byte per type (17 B/particle over PCIe), also from an fp64 handle
+    for precision in (plife.F32, plife.F64):
+        q = plife.NativePhysics(precision=precision)
+        q.set_settings(0.03, 0.85, 1.0, True)
+        q.set_matrix(matrix)
+        q.upload(pos, vel, types)
+        q.step(DT, 1)
+        want = q.download()
+        c = [np.empty((n, 2), np.float32), None, np.full(n, 255, np.uint8)]
+        q.snapshot_async(*c)
+        q.step(DT, 1)
+        q.snapshot_wait()
+        assert np.array_equal(c[0], want.position.astype(np.float32)) and np.array_equal(c[2], want.type.astype(np.uint8))
+        q.close()
 
 
 # ---------------------------------------------------------------------------
