@@ -189,6 +189,16 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one process per GPU: run on the CPUs next to this GPU, so that the pinned snapshot buffers (first touch) and the
+        # launch thread live on its NUMA node; best effort, the numbers are valid without it
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(local_rank)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"  # CUDA order may differ from NVML's
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+        except Exception:  # noqa: BLE001
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import plife
