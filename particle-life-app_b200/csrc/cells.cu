@@ -187,28 +187,46 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
 
 // B/Physics.java:343-348: `i = containers[ci]; buffer[i] = p; containers[ci]++`.
 // Afterwards cell_end[ci] is the END offset of cell ci, as in the reference.
+constexpr int kScatterUnroll = 4; // measured: 1 -> 0.078 ms, 4 -> 0.056 ms at 16M particles
+
 template <bool AGG>
 __global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n_phys, Grid g, int first,
                                                          int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
 {
-    int i = blockIdx.x * kThreads + threadIdx.x;
-    int c = -1;
-    if (i < n_phys) c = container_of(__ldg(&cell[i]), g); // -1: dead slot (the particle migrated to another slab)
+    // Several slots per thread: the kernel is load -> atomic round trip -> store, so what counts is how many atomics are
+    // in flight.  All loads first, then all atomics, then the stores.
+    constexpr int U = kScatterUnroll;
+    const int i0 = blockIdx.x * (kThreads * U) + threadIdx.x;
+    int c[U], slot[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * kThreads;
+        c[u] = i < n_phys ? container_of(__ldg(&cell[i]), g) : -1; // -1: dead slot (the particle migrated to another slab)
+    }
+    if (!AGG) { // sparse grids: every lane has its own cell, aggregation only costs
+#pragma unroll
+        for (int u = 0; u < U; ++u) slot[u] = c[u] >= 0 ? atomicAdd(&cell_end[c[u]], 1) : -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (c[u] >= 0) perm[slot[u] - first] = i0 + u * kThreads;
+        return;
+    }
     // Warp-aggregated cursor: after the first step the array is almost cell-sorted, so the 32 lanes of a warp hit
     // 2-3 distinct cells; one atomic per distinct cell instead of one per particle, and neighbouring slots for
     // lanes of the same cell.  (Order inside a cell is still arbitrary across warps; K_GATHER ranks it.)
-    if (!AGG) { // sparse grids: every lane has its own cell, aggregation only costs
-        if (c >= 0) perm[atomicAdd(&cell_end[c], 1) - first] = i;
-        return;
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    if (c < 0) return;
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&cell_end[c], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    perm[base + __popc(peers & ((1u << lane) - 1u)) - first] = i;
+    unsigned peers[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        peers[u] = __match_any_sync(0xffffffffu, c[u]);
+        slot[u] = 0;
+        if (c[u] >= 0 && lane == __ffs(peers[u]) - 1) slot[u] = atomicAdd(&cell_end[c[u]], __popc(peers[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int base = __shfl_sync(0xffffffffu, slot[u], __ffs(peers[u]) - 1);
+        if (c[u] >= 0) perm[base + __popc(peers[u] & ((1u << lane) - 1u)) - first] = i0 + u * kThreads;
+    }
 }
 
 // Logical position of pre-sort slot `src`.  Single GPU: the identity.  Slab mode: the pre-sort array is
@@ -279,24 +297,46 @@ __device__ __forceinline__ int sorted_slot(int d, int src, int c, const int32_t 
     return s + rank;
 }
 
+constexpr int kGatherUnroll = 2; // measured: 1 -> 0.186 ms, 2 -> 0.166 ms, 4 -> 0.190 ms at 16M particles
+
+// fp32: only the 16-byte candidate record moves.  Velocities stay where they are - each is needed once, by its own
+// particle - and the force pass reads them through src_sorted (12 bytes per particle less traffic here).
 template <bool STABLE, bool PAIRS, typename KEY>
-__global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, const float2 *__restrict__ vel_in,
-                                                       float4 *__restrict__ pt_out, float2 *__restrict__ vel_out, int n, Grid g,
+__global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, float4 *__restrict__ pt_out, int n, Grid g,
                                                        int first, KEY key, const int32_t *__restrict__ cell,
-                                                       int32_t *__restrict__ cell_sorted, const int32_t *__restrict__ cell_end,
-                                                       const int32_t *__restrict__ perm, const int32_t *__restrict__ pair_start,
-                                                       int32_t *__restrict__ pair_first)
+                                                       int32_t *__restrict__ cell_sorted, int32_t *__restrict__ src_sorted,
+                                                       const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm,
+                                                       const int32_t *__restrict__ pair_start, int32_t *__restrict__ pair_first)
 {
-    int d = blockIdx.x * kThreads + threadIdx.x;
-    if (d >= n) return;
-    int src = __ldg(&perm[d]);
-    float4 p = __ldg(&pt_in[src]);
-    float2 v = __ldg(&vel_in[src]);
-    int cxy = __ldg(&cell[src]);
-    int dst = sorted_slot<STABLE, PAIRS, KEY>(d, src, container_of(cxy, g), cell_end, perm, first, key, pair_start, pair_first);
-    pt_out[dst] = p; // sorted positions carry the ghost-below offset `first`; per-target arrays do not
-    vel_out[dst - first] = v;
-    cell_sorted[dst - first] = cxy;
+    // Two slots per thread: the kernel is a chain of four dependent memory round trips (perm -> record and cell ->
+    // cell offsets -> keys of the cell), so its speed is the number of chains in flight; two per thread instead of one.
+    constexpr int U = kGatherUnroll;
+    const int d0 = blockIdx.x * (kThreads * U) + threadIdx.x;
+    int src[U], cxy[U], c[U];
+    float4 p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int d = d0 + u * kThreads;
+        src[u] = d < n ? __ldg(&perm[d]) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (src[u] >= 0) {
+            p[u] = __ldg(&pt_in[src[u]]);
+            cxy[u] = __ldg(&cell[src[u]]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = src[u] >= 0 ? container_of(cxy[u], g) : 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (src[u] < 0) continue;
+        const int d = d0 + u * kThreads;
+        const int dst = sorted_slot<STABLE, PAIRS, KEY>(d, src[u], c[u], cell_end, perm, first, key, pair_start, pair_first);
+        pt_out[dst] = p[u]; // sorted positions carry the ghost-below offset `first`; per-target arrays do not
+        cell_sorted[dst - first] = cxy[u];
+        src_sorted[dst - first] = src[u];
+    }
 }
 
 template <bool STABLE>
@@ -532,8 +572,8 @@ cudaError_t launch_scatter(plife_handle *h, const Grid &g)
     int n = (int)h->n_phys; // physical pre-sort length (dead slots included)
     if (n == 0) return cudaSuccess;
     const double rho = (double)h->n / ((double)g.nx * (g.row_hi - g.row_lo));
-    if (rho >= 4.0) scatter_perm<true><<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
-    else scatter_perm<false><<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
+    if (rho >= 4.0) scatter_perm<true><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
+    else scatter_perm<false><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
     return cudaGetLastError();
 }
 
@@ -543,7 +583,7 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
     if (n == 0) return cudaSuccess;
     int a = h->cur, b = h->cur ^ 1;
     bool stable = !(h->flags & PLIFE_FLAG_UNSTABLE_SORT);
-    int nb = blocks_for(n, kThreads);
+    int nb = h->precision == PLIFE_F32 ? blocks_for(n, kThreads * kGatherUnroll) : blocks_for(n, kThreads);
     int32_t *pf = (h->flags & PLIFE_FLAG_PAIRS) ? h->d_pair_first : nullptr; // only the opt-in pairs kernel needs it
     StableKey key{0x7fffffff, 0, 0, 0, 0};
     if (h->slab.on) {
@@ -556,9 +596,9 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
     }
     if (h->precision == PLIFE_F32) {
 #define PLIFE_GATHER(ST, PR, KT, KV)                                                                                      \
-    gather_f32<ST, PR, KT><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[a].vel, h->s32[b].pt, h->s32[b].vel, n, g,  \
-                                                           first_index(h), KV, h->d_cell, h->d_cell_sorted,               \
-                                                           h->d_cell_end, h->d_perm, h->d_pair_start, pf)
+    gather_f32<ST, PR, KT><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[b].pt, n, g, first_index(h), KV, h->d_cell,  \
+                                                           h->d_cell_sorted, h->d_src_sorted, h->d_cell_end, h->d_perm,     \
+                                                           h->d_pair_start, pf)
         if (h->slab.on) { // arrivals are ordered by their previous global position (StableKey)
             if (stable) PLIFE_GATHER(true, false, StableKey, key);
             else PLIFE_GATHER(false, false, StableKey, key);

@@ -9,7 +9,9 @@ namespace plife {
 static IOF32 make_io(plife_handle *h)
 {
     const int src = h->cur ^ 1, dst = h->cur; // sorted scratch -> current
-    return IOF32{h->s32[src].pt, h->s32[src].vel, h->s32[dst].pt, h->s32[dst].vel};
+    // velocities: read from the current buffer (pre-sort order, through d_src_sorted), written to the scratch one;
+    // launch_force_f32 swaps the two pointers afterwards so that s32[cur] is again the complete new state
+    return IOF32{h->s32[src].pt, h->s32[dst].vel, h->s32[dst].pt, h->s32[src].vel, h->d_src_sorted};
 }
 
 static NextBin next_bin(plife_handle *h)
@@ -19,7 +21,22 @@ static NextBin next_bin(plife_handle *h)
     return nb;
 }
 
+static cudaError_t launch_force_f32_impl(plife_handle *h, const ForceParams<float> &p);
+
+// The kernels read the old velocities from s32[cur].vel and write the new ones into s32[cur ^ 1].vel; swapping the two
+// pointers makes s32[cur] = {new positions, new velocities} again for every other entry point.
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
+{
+    const cudaError_t e = launch_force_f32_impl(h, p);
+    if (e == cudaSuccess && p.n > 0) {
+        float2 *t = h->s32[0].vel;
+        h->s32[0].vel = h->s32[1].vel;
+        h->s32[1].vel = t;
+    }
+    return e;
+}
+
+static cudaError_t launch_force_f32_impl(plife_handle *h, const ForceParams<float> &p)
 {
     const float *mt = (const float *)h->d_matrix_t;
     const float *mrow = mt + (size_t)p.m * p.m; // row-major copy follows the transposed one

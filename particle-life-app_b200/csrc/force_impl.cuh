@@ -27,10 +27,11 @@ struct Cand {
 // ---- state access policies -------------------------------------------------
 struct IOF32 {
     using R = float;
-    const float4 *__restrict__ pt;
-    const float2 *__restrict__ vel;
+    const float4 *__restrict__ pt;        // sorted records (candidates and own position)
+    const float2 *__restrict__ vel;       // velocities in PRE-sort order: the gather does not move them
     float4 *__restrict__ pt_out;
-    float2 *__restrict__ vel_out;
+    float2 *__restrict__ vel_out;         // the other velocity buffer; the launcher swaps the two afterwards
+    const int32_t *__restrict__ src;      // pre-sort slot of sorted particle i
     __device__ __forceinline__ Cand<float> cand(int j) const
     {
         float4 q = __ldg(pt + j);
@@ -40,7 +41,7 @@ struct IOF32 {
     __device__ __forceinline__ void cand_type(int, Cand<float> &) const {}
     __device__ __forceinline__ void self_vel(int i, float &vx, float &vy) const
     {
-        float2 v = __ldg(vel + i);
+        float2 v = __ldg(vel + __ldg(src + i));
         vx = v.x;
         vy = v.y;
     }

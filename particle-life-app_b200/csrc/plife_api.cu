@@ -70,9 +70,10 @@ void free_state(plife_handle *h)
     }
     cudaFree(h->d_cell);
     cudaFree(h->d_cell_sorted);
+    cudaFree(h->d_src_sorted);
     cudaFree(h->d_perm);
     cudaFree(h->d_pair_first);
-    h->d_cell = h->d_cell_sorted = h->d_perm = h->d_pair_first = nullptr;
+    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_pair_first = nullptr;
     h->cap = 0;
     h->prebinned = false;
 }
@@ -98,6 +99,7 @@ int ensure_capacity(plife_handle *h, int64_t n)
     }
     CU(h, dev_alloc(&h->d_cell, c));
     CU(h, dev_alloc(&h->d_cell_sorted, c));
+    CU(h, dev_alloc(&h->d_src_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
     CU(h, dev_alloc(&h->d_pair_first, c));
     h->cap = n;
@@ -151,11 +153,13 @@ int grow_preserve(plife_handle *h, int64_t cap)
     }
     cudaFree(h->d_cell);
     cudaFree(h->d_cell_sorted);
+    cudaFree(h->d_src_sorted);
     cudaFree(h->d_perm);
     cudaFree(h->d_pair_first);
-    h->d_cell = h->d_cell_sorted = h->d_perm = h->d_pair_first = nullptr;
+    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_pair_first = nullptr;
     CU(h, dev_alloc(&h->d_cell, c));
     CU(h, dev_alloc(&h->d_cell_sorted, c));
+    CU(h, dev_alloc(&h->d_src_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
     CU(h, dev_alloc(&h->d_pair_first, c));
     h->cap = cap;

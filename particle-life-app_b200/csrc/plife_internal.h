@@ -152,6 +152,7 @@ struct plife_handle {
     plife::StateF64 s64[2]{};
     int32_t *d_cell = nullptr;        // packed cell coords of particle i (pre-sort order)
     int32_t *d_cell_sorted = nullptr; // the same, permuted into sorted order
+    int32_t *d_src_sorted = nullptr;  // fp32: pre-sort slot of every sorted particle (velocities are read through it)
     int32_t *d_perm = nullptr; // source index of sorted slot d
     int32_t *d_pair_first = nullptr; // first target of every target pair (two-targets-per-lane force kernel)
     int32_t *d_pair_start = nullptr; // first pair of every cell
