@@ -194,7 +194,9 @@ int plife_kernel_times(plife_handle *h, double *ms_out, int64_t *launches_out);
 int plife_measure_fp32_peak(int32_t device, double *tflops_out);
 /* device pointers of the current state (for CUDA-GL interop or torch views):
  * F32: pos = float4{x,y,type bits,id bits}[n], vel = float2[n]
- * F64: pos = double2[n], vel = double2[n], type = int32[n], id = uint32[n] */
+ * F64: pos = double2[n], vel = double2[n], type = int32[n], id = uint32[n]
+ * The pointers are valid until the next call that steps, edits or uploads: query again afterwards (the
+ * velocity buffers of an F32 handle alternate from step to step). */
 int plife_device_ptrs(plife_handle *h, void **pos, void **vel, void **type, void **id);
 
 /* ---- particle-set editing on the device (what the GUI does to physics.particles directly) ----
