@@ -16,8 +16,9 @@ import org.joml.Vector3d;
  * <p>Usage in {@code Main.createPhysics()} (A/Main.java:281-285): construct this class instead of
  * {@code ExtendedPhysics}.  {@code Loop} and everything above stay unchanged: they call
  * {@code update()}, mutate {@code settings}, and read {@code particles} when a snapshot is due.
- * The particle buffers live on the GPU; {@link #pull()} refreshes the Java-side array for the
- * display-time handoff (A/PhysicsSnapshot.java:24-62) and {@link #push()} uploads edits.
+ * The particle buffers live on the GPU; {@link #requestSnapshot()} / {@link #finishSnapshot()} hand the renderer
+ * float buffers without stalling the physics (A/PhysicsSnapshot.java:24-62), {@link #pull()} refreshes the Java-side
+ * {@code particles} array when Java code wants to edit it, and {@link #push()} uploads the edits.
  */
 public class NativePhysics extends Physics {
 
@@ -44,6 +45,10 @@ public class NativePhysics extends Physics {
     private static final MethodHandle SYNC = fn("plife_sync", FunctionDescriptor.of(I32, PTR));
     private static final MethodHandle REQUEST_STOP = fn("plife_request_stop", FunctionDescriptor.of(I32, PTR));
     private static final MethodHandle LAST_ERROR = fn("plife_last_error", FunctionDescriptor.of(PTR, PTR));
+    private static final MethodHandle COUNT = fn("plife_count", FunctionDescriptor.of(I64, PTR));
+    private static final MethodHandle TYPE_HISTOGRAM = fn("plife_type_histogram", FunctionDescriptor.of(I32, PTR, PTR));
+    private static final MethodHandle SNAPSHOT_ASYNC_U8 = fn("plife_snapshot_async_u8", FunctionDescriptor.of(I32, PTR, PTR, PTR, PTR));
+    private static final MethodHandle SNAPSHOT_WAIT = fn("plife_snapshot_wait", FunctionDescriptor.of(I32, PTR));
 
     /** struct plife_config { int32 device, precision; int64 capacity; int32 flags, reserved; void* stream; } */
     private static final MemoryLayout CONFIG = MemoryLayout.structLayout(I32.withName("device"), I32.withName("precision"),
@@ -52,19 +57,29 @@ public class NativePhysics extends Physics {
     private static final MemoryLayout SETTINGS = MemoryLayout.structLayout(F64.withName("rmax"), F64.withName("friction"),
             F64.withName("force"), I32.withName("wrap"), I32.withName("reserved"));
 
-    private final Arena arena = Arena.ofShared();
+    private final Arena arena = Arena.ofShared(); // lives as long as the handle: settings block, matrix, snapshot buffers
+    private final MemorySegment settingsBlock = arena.allocate(SETTINGS);
+    private MemorySegment matrixBlock = MemorySegment.NULL; // re-allocated when the matrix size changes
+    private int matrixBlockSize = -1;
     private MemorySegment handle;
     private boolean dirty = true; // Java-side particles changed since the last upload
+
+    /** Float snapshot for the renderer (A/PhysicsSnapshot.java + A/ParticleRenderer.java): xy, vxy as float, type as byte. */
+    public static final class Snapshot {
+        public MemorySegment positions, velocities, types; // n*2 floats, n*2 floats, n bytes; off-heap, GL-uploadable
+        public int particleCount;
+    }
+
+    private final Snapshot[] snapshots = {new Snapshot(), new Snapshot()};
+    private int snapshotIndex = 0;
 
     public NativePhysics(Accelerator accelerator, PositionSetter positionSetter, MatrixGenerator matrixGenerator,
                          TypeSetter typeSetter) {
         super(accelerator, positionSetter, matrixGenerator, typeSetter); // generates matrix + 10000 particles on the host
-        try {
-            MemorySegment cfg = arena.allocate(CONFIG);
-            cfg.set(I32, 0, 0);   // device 0
-            cfg.set(I32, 4, 0);   // PLIFE_F32
+        try (Arena tmp = Arena.ofConfined()) {
+            MemorySegment cfg = tmp.allocate(CONFIG); // zero-initialised: device 0, PLIFE_F32, library-owned stream
             cfg.set(I64, 8, particles.length);
-            MemorySegment out = arena.allocate(PTR);
+            MemorySegment out = tmp.allocate(PTR);
             check((int) CREATE.invoke(cfg, out));
             handle = out.get(PTR, 0);
         } catch (Throwable t) {
@@ -85,14 +100,18 @@ public class NativePhysics extends Physics {
     }
 
     private void pushSettings() throws Throwable {
-        MemorySegment s = arena.allocate(SETTINGS);
+        MemorySegment s = settingsBlock;
         s.set(F64, 0, settings.rmax);
         s.set(F64, 8, settings.friction);
         s.set(F64, 16, settings.force);
         s.set(I32, 24, settings.wrap ? 1 : 0);
         check((int) SET_SETTINGS.invoke(handle, s));
         int m = settings.matrix.size();
-        MemorySegment mat = arena.allocate(F64, (long) m * m);
+        if (m != matrixBlockSize) { // a handful of sizes over the life of the app: the shared arena keeps them
+            matrixBlock = arena.allocate(F64, (long) m * m);
+            matrixBlockSize = m;
+        }
+        MemorySegment mat = matrixBlock;
         for (int i = 0; i < m; i++)
             for (int j = 0; j < m; j++) mat.setAtIndex(F64, (long) i * m + j, settings.matrix.get(i, j));
         check((int) SET_MATRIX.invoke(handle, m, mat));
@@ -103,7 +122,8 @@ public class NativePhysics extends Physics {
     /** Upload the Java-side particle array (after setParticleCount / cursor edits / load). */
     public void push() throws Throwable {
         int n = particles.length;
-        MemorySegment pos = arena.allocate(F64, 2L * n), vel = arena.allocate(F64, 2L * n), typ = arena.allocate(I32, n);
+        try (Arena tmp = Arena.ofConfined()) {
+        MemorySegment pos = tmp.allocate(F64, 2L * n), vel = tmp.allocate(F64, 2L * n), typ = tmp.allocate(I32, n);
         for (int i = 0; i < n; i++) {
             Particle p = particles[i];
             pos.setAtIndex(F64, 2L * i, p.position.x);
@@ -113,19 +133,58 @@ public class NativePhysics extends Physics {
             typ.setAtIndex(I32, i, p.type);
         }
         check((int) UPLOAD.invoke(handle, (long) n, pos, vel, typ, MemorySegment.NULL));
+        }
         dirty = false;
     }
 
     /** Display-time handoff: refresh the Java-side particles from the GPU (cell-sorted order, like the reference). */
     public void pull() throws Throwable {
         int n = particles.length;
-        MemorySegment pos = arena.allocate(F64, 2L * n), vel = arena.allocate(F64, 2L * n), typ = arena.allocate(I32, n);
-        check((int) DOWNLOAD.invoke(handle, pos, vel, typ, MemorySegment.NULL));
-        for (int i = 0; i < n; i++) {
-            Particle p = particles[i];
-            p.position.set(pos.getAtIndex(F64, 2L * i), pos.getAtIndex(F64, 2L * i + 1), 0);
-            p.velocity.set(vel.getAtIndex(F64, 2L * i), vel.getAtIndex(F64, 2L * i + 1), 0);
-            p.type = typ.getAtIndex(I32, i);
+        try (Arena tmp = Arena.ofConfined()) {
+            MemorySegment pos = tmp.allocate(F64, 2L * n), vel = tmp.allocate(F64, 2L * n), typ = tmp.allocate(I32, n);
+            check((int) DOWNLOAD.invoke(handle, pos, vel, typ, MemorySegment.NULL));
+            for (int i = 0; i < n; i++) {
+                Particle p = particles[i];
+                p.position.set(pos.getAtIndex(F64, 2L * i), pos.getAtIndex(F64, 2L * i + 1), 0);
+                p.velocity.set(vel.getAtIndex(F64, 2L * i), vel.getAtIndex(F64, 2L * i + 1), 0);
+                p.type = typ.getAtIndex(I32, i);
+            }
+        }
+    }
+
+    /**
+     * What Main.java:600-603 does with {@code loop.doOnce(() -> physicsSnapshot.take(...))}: start a float snapshot of the
+     * current state.  The copy overlaps the following {@code update()} calls; {@link #finishSnapshot()} returns it.
+     * Two buffer sets alternate, so the renderer may keep reading the previous snapshot meanwhile.
+     */
+    public void requestSnapshot() throws Throwable {
+        int n = (int) (long) COUNT.invoke(handle);
+        Snapshot s = snapshots[snapshotIndex];
+        if (s.particleCount != n || s.positions == null) { // size changed: new buffers (the old ones die with the arena)
+            s.positions = arena.allocate(ValueLayout.JAVA_FLOAT, 2L * n);
+            s.velocities = arena.allocate(ValueLayout.JAVA_FLOAT, 2L * n);
+            s.types = arena.allocate(ValueLayout.JAVA_BYTE, n);
+            s.particleCount = n;
+        }
+        check((int) SNAPSHOT_ASYNC_U8.invoke(handle, s.positions, s.velocities, s.types));
+    }
+
+    public Snapshot finishSnapshot() throws Throwable {
+        check((int) SNAPSHOT_WAIT.invoke(handle));
+        Snapshot s = snapshots[snapshotIndex];
+        snapshotIndex ^= 1;
+        return s;
+    }
+
+    /** ExtendedPhysics.getTypeCount (A/ExtendedPhysics.java:19-26) without a download. */
+    public int[] getTypeCount() throws Throwable {
+        int m = settings.matrix.size();
+        try (Arena tmp = Arena.ofConfined()) {
+            MemorySegment out = tmp.allocate(I64, m);
+            check((int) TYPE_HISTOGRAM.invoke(handle, out));
+            int[] counts = new int[m];
+            for (int i = 0; i < m; i++) counts[i] = (int) out.getAtIndex(I64, i);
+            return counts;
         }
     }
 
@@ -147,6 +206,7 @@ public class NativePhysics extends Physics {
         try {
             if (handle != null) DESTROY.invoke(handle);
             handle = null;
+            arena.close(); // settings block, matrix block, snapshot buffers
         } catch (Throwable ignored) {
         }
         super.kill();
