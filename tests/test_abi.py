@@ -97,3 +97,21 @@ def test_every_kernel_lives_in_exactly_one_object():
             assert k not in seen, f"kernel {k} is compiled in both {seen[k]} and {os.path.basename(o)}"
             seen[k] = os.path.basename(o)
     assert any("force_kernel_staged" in k for k in seen)
+
+
+def test_java_shim_binds_only_declared_and_exported_symbols(native_lib):
+    """particle-life-app_b200/java/.../NativePhysics.java cannot be compiled here (no JVM); at least every symbol it looks up
+    must be declared in include/plife.h and exported by the library, with the argument count the header states."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    java = open(os.path.join(root, "particle-life-app_b200", "java", "com", "particle_life", "backend", "NativePhysics.java")).read()
+    header = open(os.path.join(root, "include", "plife.h")).read()
+    bound = re.findall(r'fn\("(plife_\w+)",\s*FunctionDescriptor\.of\(([^)]*)\)\)', java)
+    assert len(bound) >= 12
+    lib = native_lib if isinstance(native_lib, C.CDLL) else C.CDLL(native_lib)
+    for name, desc in bound:
+        assert hasattr(lib, name), f"{name} is not exported"
+        m = re.search(r"^(?:int|int64_t|const char \*)\s*%s\s*\(([^;]*?)\)\s*;" % name, header, re.S | re.M)
+        assert m, f"{name} is not declared in plife.h"
+        params = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+        assert len(desc.split(",")) - 1 == len(params), f"{name}: the shim passes {len(desc.split(',')) - 1} arguments, the header declares {len(params)}"
