@@ -25,6 +25,9 @@ CASES = {
     "fat_cell": dict(n=1500, m=3, rmax=0.065, wrap=True, seed=0x5EED0021, steps=2),
     "nx2_dup": dict(n=400, m=2, rmax=0.5, wrap=True, seed=0x5EED0031, steps=1),
     "rotator": dict(n=1200, m=4, rmax=0.05, wrap=True, seed=0x5EED0041, steps=2, accel_kind=3),
+    # half of the particles in a gaussian blob: cells of several hundred particles next to empty ones (what an evolved
+    # state looks like); on the GPU the dense CTAs stream their candidates through shared memory in chunks
+    "blob": dict(n=8000, m=4, rmax=0.025, wrap=True, seed=0x5EED0051, steps=1),
 }
 
 
@@ -36,6 +39,10 @@ def make(name, c):
     vel = vel.astype(np.float32).astype(np.float64)
     if name == "c1_wrap":
         pos[:8, 0] = 1.0  # E1: x == 1.0 is reachable in wrap mode
+    if name == "blob":
+        g = np.random.default_rng(c["seed"])
+        k = c["n"] // 2
+        pos[:k] = np.clip(g.normal(0.5, 0.03, (k, 2)), 0, 0.999999).astype(np.float32).astype(np.float64)
     M = synth.random_matrix(c["m"], c["seed"])
     o = oracle.Oracle(rmax=c["rmax"], wrap=c["wrap"], matrix=M, dt=0.02, accel_kind=c.get("accel_kind", 0), diag=True)
     o.set_particles(pos, vel, types)
@@ -53,6 +60,9 @@ def make(name, c):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for k, v in CASES.items():
+        if only and k not in only:
+            continue
         make(k, v)
         print("wrote", k)
