@@ -5,8 +5,9 @@ and the snapshot hand-off to the renderer, for a headless driver of the native b
   Loop             B/Loop.java         thread that calls a callback with the (capped) frame time, runs queued
                                        commands between iterations, can be paused / stopped / abandoned
   PhysicsSnapshot  A/PhysicsSnapshot.java   host copy of the particle arrays + settings + type histogram
-  Simulation       A/Main.java:245-300,583-604  the glue: `update_physics(real_dt)` picks dt and steps, a
-                                       `do_once` command takes a snapshot when the consumer asks for the next
+  Simulation       A/Main.java:245-300,583-604,993-1016  the glue: `update_physics(real_dt)` picks dt and steps, a
+                                       `do_once` command takes a snapshot when the consumer asks for the next, and the
+                                       "physics not reacting" reset
 
 Everything the reference serialises through `loop.enqueue(...)` (setters, matrix edits, cursor edits,
 loading a save) must go through `Loop.enqueue` here too: the native handle is not thread safe, and like the
@@ -260,3 +261,30 @@ class Simulation:
             self.loop.kill()
             self.physics.force_update_stop()
         return clean
+
+    # -- watchdog (A/Main.java:993-1016) --
+    def not_reacting_for(self) -> float:
+        """Milliseconds since the last snapshot was taken - the reference's only liveness signal (snapshots are
+        requested every frame, so an old one means the physics thread is stuck)."""
+        return time.time() * 1000.0 - self.snapshot.snapshot_time
+
+    def reset_if_not_reacting(self, make_physics: Callable[[], object], threshold_ms: float = 3000.0, stop_millis: int = 1000) -> bool:
+        """What the "Reset Physics" button does once the physics has not reacted for `threshold_ms` (the app's
+        physicsNotReactingThreshold): stop the loop, or abandon it and kill the physics if it does not stop in time,
+        then start over with a fresh physics object and a fresh loop.  Returns True if a reset happened."""
+        if self.not_reacting_for() <= threshold_ms:
+            return False
+        if not self.loop.stop(stop_millis):
+            self.loop.kill()
+            try:
+                self.physics.force_update_stop()
+                self.physics.kill()
+            except Exception:  # noqa: BLE001 - a wedged backend must not keep the reset from happening
+                pass
+        self.physics = make_physics()
+        self.loop = Loop()
+        self.steps = 0
+        self.snapshot.take(self.physics)
+        self.new_snapshot_available.set()
+        self.loop.start(self.update_physics)
+        return True

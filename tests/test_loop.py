@@ -123,3 +123,73 @@ def test_failing_command_stops_the_loop_and_keeps_the_error():
         time.sleep(0.005)
     assert isinstance(loop.error, ZeroDivisionError)
     assert loop.stop(1000)
+
+
+class _FakeNative:
+    def download_f32(self, *a):
+        pass
+
+
+class _FakePhysics:
+    """Stands in for plife.Physics where no GPU exists: counts updates, can be made to hang."""
+
+    def __init__(self, hang=None):
+        from plife import PhysicsSettings
+        self.settings = PhysicsSettings()
+        self.native = _FakeNative()
+        self.particle_count = 0
+        self.updates = 0
+        self.killed = False
+        self.hang = hang
+
+    def update(self):
+        self.updates += 1
+        if self.hang is not None:
+            self.hang.wait(10.0)
+        time.sleep(0.001)
+
+    def get_type_count(self):
+        return np.zeros(6, np.int64)
+
+    def force_update_stop(self):
+        pass
+
+    def kill(self):
+        self.killed = True
+
+
+def test_simulation_dt_policy_snapshots_and_watchdog():
+    """A/Main.java:291-295 (dt policy), :583-604 (snapshot hand-off), :993-1016 (reset of a physics that stopped reacting)."""
+    from plife.loop import Simulation
+    p = _FakePhysics()
+    sim = Simulation(p, auto_dt=False, dt=0.0125)
+    sim.update_physics(0.5)
+    assert p.settings.dt == 0.0125
+    sim.auto_dt = True
+    sim.update_physics(0.031)
+    assert p.settings.dt == 0.031 and sim.steps == 2
+    sim.start()
+    sim.request_snapshot()
+    assert sim.new_snapshot_available.wait(5.0)
+    assert sim.reset_if_not_reacting(lambda: _FakePhysics(), threshold_ms=3000) is False     # fresh snapshot: alive
+    assert sim.close(2000)
+    # a physics that hangs inside update(): no new snapshots, stop() times out, the loop is abandoned and everything restarts
+    gate = threading.Event()
+    stuck = _FakePhysics(hang=gate)
+    sim = Simulation(stuck, auto_dt=False)
+    sim.start()
+    for _ in range(200):
+        if stuck.updates:
+            break
+        time.sleep(0.005)
+    sim.snapshot.snapshot_time -= 10_000                      # as if the last snapshot were ten seconds old
+    fresh = []
+    assert sim.reset_if_not_reacting(lambda: fresh.append(_FakePhysics()) or fresh[-1], threshold_ms=3000, stop_millis=50) is True
+    assert stuck.killed and sim.physics is fresh[0] and sim.not_reacting_for() < 3000
+    for _ in range(200):
+        if fresh[0].updates > 3:
+            break
+        time.sleep(0.005)
+    assert fresh[0].updates > 3                                # the new loop runs the new physics
+    gate.set()                                                  # let the abandoned thread finish
+    assert sim.close(2000)
