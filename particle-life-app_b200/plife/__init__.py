@@ -197,6 +197,13 @@ class NativePhysics:
         self._check(self.L.plife_get_containers(self.h, _ptr(out), out.size))
         return out
 
+    def containers_local(self, ncell):
+        """Slab mode: END offsets of this rank's LOCAL cells (ghost row below, owned rows, ghost row above), as offsets
+        into the rank's sorted array (owned block starts at halo_cap)."""
+        out = np.empty(ncell, np.int32)
+        self._check(self.L.plife_get_containers(self.h, _ptr(out), out.size))
+        return out
+
     def step_stats(self, pairs=True):
         s = N.StepStats()
         self._check(self.L.plife_get_step_stats(self.h, C.byref(s)))
