@@ -228,7 +228,8 @@ int plife_append(plife_handle *h, int64_t k, const double *pos_xy, const double 
  * (down = rank-1, up = rank+1, periodic when wrap is on; no exchange across a closed boundary).
  * External exchange (bufs != NULL): buffers are device memory owned by the caller, in 16-byte records:
  * plife_slab_halo_records(nx, halo_cap) / plife_slab_migrate_records(mig_cap) records each.
- * fp32 handles only.  Upload only particles of the rank's own rows (others are dropped). */
+ * fp32 handles only.  plife_upload accepts only particles of the rank's own rows (PLIFE_ERR_INVALID otherwise);
+ * plife_init_uniform keeps the rank's share of the global stream. */
 typedef struct plife_slab_buffers {
     void *halo_send[2], *halo_recv[2], *mig_send[2], *mig_recv[2];
 } plife_slab_buffers;

@@ -212,6 +212,7 @@ int make_grid(plife_handle *h, Grid *g)
     g->ly_shift = 0;
     g->nly = nx;
     g->rows_up = g->rows_dn = 0;
+    g->ks = 0;
     if (h->slab.on) {
         const int G = h->slab.world, r = h->slab.rank, ny = g->ny;
         if (ny < 4 * G) return fail(h, PLIFE_ERR_INVALID, "slab mode needs ny >= 4*world (ny=%d, world=%d)", ny, G);
@@ -341,6 +342,7 @@ int sort_current(plife_handle *h, const Grid &g, StepTimer *tm, bool mark_gather
     CU(h, launch_scatter(h, g));
     if (tm) CU(h, tm->mark(3));
     CU(h, launch_gather(h, g));
+    h->n_sorted = h->n;
     if (tm && mark_gather_end) CU(h, tm->mark(4));
     return PLIFE_OK;
 }
@@ -393,6 +395,13 @@ int edit_fail(plife_handle *h, int code, const char *msg) { return fail(h, code,
 int edit_grow(plife_handle *h, int64_t cap) { return grow_preserve(h, cap); }
 int slab_make_grid(plife_handle *h, Grid *g) { return make_grid(h, g); }
 int slab_fail(plife_handle *h, int code, const char *msg) { return fail(h, code, "%s", msg); }
+// plife_slab_configure: buffers allocated before slab mode was switched on (plife_create with a capacity) have no room
+// for the two ghost rows around the owned block of the sorted array; drop them and allocate again with that room.
+int slab_reset_capacity(plife_handle *h)
+{
+    free_state(h);
+    return h->capacity_hint > 0 ? ensure_capacity(h, h->capacity_hint) : PLIFE_OK;
+}
 // Slab-mode profiling: event 4 is recorded right before the force kernel, so the K_GATHER bucket also holds the halo
 // pack / push / wait / unpack kernels that run between the gather and the force pass; K_FORCE is the kernel alone.
 int slab_sort(plife_handle *h, const Grid &g)
@@ -471,12 +480,13 @@ int plife_create(const plife_config *cfg, plife_handle **out)
         }
         h->own_stream = true;
     }
-    if (cudaMalloc((void **)&h->d_scalar, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc((void **)&h->d_scalar, (8 + 256) * sizeof(unsigned long long)) != cudaSuccess) {
         if (h->own_stream) cudaStreamDestroy(h->stream);
         delete h;
         return PLIFE_ERR_OOM;
     }
-    cudaMemset(h->d_scalar, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(h->d_scalar, 0, (8 + 256) * sizeof(unsigned long long));
+    h->d_hist = h->d_scalar + 8;
     h->capacity_hint = cfg->capacity;
     if (cfg->capacity > 0) {
         int rc = ensure_capacity(h, cfg->capacity);
@@ -598,6 +608,15 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
         if (t < 0 || t >= h->m) return fail(h, PLIFE_ERR_INVALID, "upload: particle %lld type %d outside [0,%d)", (long long)i, t, h->m);
         if (t > max_type) max_type = t;
     }
+    if (h->slab.on) { // a slab holds the particles of its own rows only (as the fp32 storage sees them)
+        Grid g;
+        int rcg = make_grid(h, &g);
+        if (rcg) return rcg;
+        for (int64_t i = 0; i < n; i++)
+            if (container_of(cell_coords((double)(float)pos_xy[2 * i], (double)(float)pos_xy[2 * i + 1], g), g) < 0)
+                return fail(h, PLIFE_ERR_INVALID, "upload: particle %lld (y=%g) does not belong to the rows [%d,%d) of slab rank %d", (long long)i,
+                            pos_xy[2 * i + 1], g.row_lo, g.row_hi, h->slab.rank);
+    }
     int rc = ensure_capacity(h, h->slab.on && h->capacity_hint > n ? h->capacity_hint : n);
     if (rc) return rc;
     h->cur = 0;
@@ -700,16 +719,17 @@ int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *t
     CHECK_HANDLE(h);
     int64_t n = h->n;
     if (n == 0) return PLIFE_OK;
-    if (h->snap_cap < n) {
+    if (h->snap_cap < n) { // sized by the handle's capacity: in slab mode n changes every step
+        const int64_t want = h->cap > n ? h->cap : n;
         cudaFree(h->d_snap);
         h->d_snap = nullptr;
         h->snap_cap = 0;
-        CU(h, cudaMalloc(&h->d_snap, (size_t)n * 20));
-        h->snap_cap = n;
+        CU(h, cudaMalloc(&h->d_snap, (size_t)want * 20));
+        h->snap_cap = want;
     }
     float2 *dp = (float2 *)h->d_snap;
-    float2 *dv = dp + n;
-    int32_t *dt = (int32_t *)(dv + n);
+    float2 *dv = dp + h->snap_cap;
+    int32_t *dt = (int32_t *)(dv + h->snap_cap);
     CU(h, launch_snapshot_f32(h, pos_xy ? dp : nullptr, vel_xy ? dv : nullptr, type ? dt : nullptr));
     if (pos_xy) CU(h, cudaMemcpyAsync(pos_xy, dp, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->stream));
     if (vel_xy) CU(h, cudaMemcpyAsync(vel_xy, dv, sizeof(float2) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -734,21 +754,23 @@ static int snapshot_async_impl(plife_handle *h, float *pos_xy, float *vel_xy, in
         }
         h->snap_init = true;
     }
-    if (h->snap_async_cap < n) {
+    if (h->snap_async_cap < n) { // sized by the handle's capacity: in slab mode n changes every step
+        const int64_t want = h->cap > n ? h->cap : n;
         CU(h, cudaStreamSynchronize(h->copy_stream));
+        CU(h, cudaStreamSynchronize(h->stream));
         for (int k = 0; k < 2; k++) {
             cudaFree(h->d_snap_async[k]);
             h->d_snap_async[k] = nullptr;
         }
         h->snap_async_cap = 0;
-        for (int k = 0; k < 2; k++) CU(h, cudaMalloc(&h->d_snap_async[k], (size_t)n * 20));
-        h->snap_async_cap = n;
+        for (int k = 0; k < 2; k++) CU(h, cudaMalloc(&h->d_snap_async[k], (size_t)want * 20));
+        h->snap_async_cap = want;
     }
     const int k = h->snap_k;
     h->snap_k ^= 1;
     float2 *dp = (float2 *)h->d_snap_async[k];
-    float2 *dv = dp + n;
-    int32_t *dt = (int32_t *)(dv + n);
+    float2 *dv = dp + h->snap_async_cap;
+    int32_t *dt = (int32_t *)(dv + h->snap_async_cap);
     CU(h, cudaStreamWaitEvent(h->stream, h->snap_done[k], 0)); // the copy that last used this buffer has finished
     uint8_t *dt8 = reinterpret_cast<uint8_t *>(dt); // the compact form reuses the type region
     if (type && type8) return fail(h, PLIFE_ERR_INVALID, "snapshot: int32 and u8 types requested together");
@@ -868,14 +890,12 @@ int plife_type_histogram(plife_handle *h, int64_t *out_m)
 {
     CHECK_HANDLE(h);
     if (!out_m) return fail(h, PLIFE_ERR_INVALID, "out is NULL");
-    unsigned long long *d_hist = nullptr;
-    CU(h, cudaMalloc((void **)&d_hist, sizeof(unsigned long long) * 256));
+    unsigned long long *d_hist = h->d_hist; // 256 counters, allocated with the handle
     cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256, h->stream);
     if (e == cudaSuccess) e = launch_type_histogram(h, d_hist);
     unsigned long long host[256];
     if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_hist, sizeof host, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_hist);
     if (e != cudaSuccess) return cuda_fail(h, e, "type histogram");
     for (int k = 0; k < h->m; k++) out_m[k] = (int64_t)host[k];
     return PLIFE_OK;
@@ -909,12 +929,17 @@ int plife_get_step_stats(plife_handle *h, plife_step_stats *out)
     // buffer cur^1 still holds the sorted pre-step state of the last step
     const Grid g = h->last_grid;
     CU(h, cudaMemsetAsync(h->d_scalar, 0, sizeof(unsigned long long), h->stream));
-    if (h->precision == PLIFE_F32) CU(h, launch_pair_count_f32(h, make_params<float>(h, g, 0.0), h->d_scalar));
-    else CU(h, launch_pair_count_f64(h, make_params<double>(h, g, 0.0), h->d_scalar));
+    // the sorted scratch holds the particles of the last SORT: in slab mode h->n has moved on since (migration),
+    // and walking h->n targets would read cell words past the sorted block (the round-1 8-GPU abort, profiles/r2_n8_repro.md)
+    auto pf = make_params<float>(h, g, 0.0);
+    auto pd = make_params<double>(h, g, 0.0);
+    pf.n = pd.n = (int)h->n_sorted;
+    if (h->precision == PLIFE_F32) CU(h, launch_pair_count_f32(h, pf, h->d_scalar));
+    else CU(h, launch_pair_count_f64(h, pd, h->d_scalar));
     unsigned long long total = 0;
     CU(h, cudaMemcpyAsync(&total, h->d_scalar, sizeof total, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    out->n = h->n;
+    out->n = h->n_sorted;
     out->nx = g.nx;
     out->ny = g.ny;
     out->pair_evals = (int64_t)total;

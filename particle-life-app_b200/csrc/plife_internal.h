@@ -16,6 +16,14 @@ namespace plife {
 // Uniform grid of the reference: cell edge = rmax, nx = ny = floor(1/rmax)
 // (B/Physics.java:82-85, :312-313).  cs stays double: cell assignment is done
 // with IEEE double division in every precision mode.
+//
+// Fine bins (fp32 handles at high density): every cell is cut into K = 1 << ks bins along x.  The counting sort is
+// keyed by the fine bin, so the working ("compute") order of the force pass is (row, cell, bin) and a target only
+// has to scan the bins within rmax of its own - (2 + 1/K) cell widths per row instead of 3 (-29 % candidates at
+// K = 8).  Fine bins nest in cells (bin >> ks == cell), so a cell is still ONE contiguous index range, cell END
+// offsets are every K-th entry of the bin END offsets, and the reference's particle order (stable by cell,
+// B/Physics.java:343-348) is restored when the force pass writes its results (cells.cu: ref slot).  ks = 0 is the
+// plain cell list.
 struct Grid {
     int nx, ny;  // global grid
     double cs;   // cell edge = rmax
@@ -25,27 +33,31 @@ struct Grid {
     int row_lo, row_hi;
     int ly_shift, nly;
     int rows_up, rows_dn; // rows owned by the ring neighbours (migration reach check)
+    int ks;               // log2 of the fine bins per cell along x
+    __host__ __device__ int nxk() const { return nx << ks; } // fine bins per row
 };
 
-// Cell coordinates of a position, packed cx | cy << 16.  cx = (int)(x / containerSize) in fp64 is
-// both the un-clamped cx0 of the force pass (B/Physics.java:404, floor == truncation for x >= 0) and,
-// after the `== nx -> nx-1` clamp, the container of the sort (:362-375).  nx <= 16384 (kMaxCells),
-// so cx in [0, nx] fits 15 bits.  A negative value marks a dead slot (a particle that migrated away).
+// Bin word of a position: fx | cy << 16 with fx = (int)(x / containerSize * K) the un-clamped fine x index (so
+// fx >> ks = (int)(x / containerSize) is both the un-clamped cx0 of the force pass, B/Physics.java:404 - floor ==
+// truncation for x >= 0 - and, after the `== nx -> nx-1` clamp, the container of the sort, :362-375) and cy the
+// un-clamped row.  The scaling by K = 2^ks is exact, so fine bins nest in cells bit for bit.  (nx + 1) << ks
+// <= 65535 and ny <= 16384 (checked by make_grid), so both fit.  A negative word marks a dead slot (a particle
+// that migrated away).
 __host__ __device__ inline int cell_coords(double x, double y, const Grid &g)
 {
-    int cx = (int)(x / g.cs);
+    int fx = (int)((x / g.cs) * (double)(1 << g.ks));
     int cy = (int)(y / g.cs);
-    return cx | (cy << 16);
+    return fx | (cy << 16);
 }
-// local container index, or -1 if the particle is dead / its row is not owned by this rank
+// local fine-bin index of a bin word, or -1 if the particle is dead / its row is not owned by this rank
 __host__ __device__ inline int container_of(int cxy, const Grid &g)
 {
     if (cxy < 0) return -1;
-    int cx = cxy & 0xffff, cy = cxy >> 16;
-    if (cx == g.nx) cx = g.nx - 1; // for solid borders, :367-372
+    int fx = cxy & 0xffff, cy = cxy >> 16;
+    if (fx >= g.nxk()) fx = g.nxk() - 1; // cx == nx -> nx-1 (for solid borders, :367-372): the last bin of the last cell
     if (cy == g.ny) cy = g.ny - 1;
     if (cy < g.row_lo || cy >= g.row_hi) return -1;
-    return cx + (cy + g.ly_shift) * g.nx;
+    return fx + (cy + g.ly_shift) * g.nxk();
 }
 // local row of a (wrapped) global row reached from an owned row's 3x3 neighbourhood
 __host__ __device__ inline int local_row(int cy, const Grid &g)
@@ -54,6 +66,12 @@ __host__ __device__ inline int local_row(int cy, const Grid &g)
     if (ly < 0) ly += g.ny;
     else if (ly >= g.ny) ly -= g.ny;
     return ly;
+}
+// [start, end) of the local CELLS c_lo .. c_hi (inclusive, same row) in the sorted array: bin END offsets, cell_end[-1] valid
+__device__ __forceinline__ void cell_span(const int32_t *__restrict__ cell_end, int c_lo, int c_hi, int ks, int &s, int &e)
+{
+    s = __ldg(cell_end + (c_lo << ks) - 1);
+    e = __ldg(cell_end + ((c_hi + 1) << ks) - 1);
 }
 
 // Kernel parameters of the force/integrate pass for one step, in the
@@ -111,6 +129,7 @@ struct SlabState {
     int64_t xrecords = 0, hrec = 0, mrec = 0;
     int nx_cfg = 0;
     unsigned long long seq = 1;     // step sequence number written into the neighbours' flags
+    unsigned long long spin_ns = 30000000000ull; // device-side wait limit for a neighbour's message (PLIFE_SLAB_TIMEOUT_MS)
     float4 *peer_base[2]{};         // the neighbours' xbuf mapped into this process / device
     bool peer_ipc[2]{};
     volatile int4 *h_hdr = nullptr; // mapped pinned: 4 migration headers + error word, written by finish_headers
@@ -142,6 +161,7 @@ struct plife_handle {
 
     int64_t n = 0;      // live particles
     int64_t n_phys = 0; // physical length of the pre-sort array (== n except in slab mode: dead slots)
+    int64_t n_sorted = 0; // particles in the sorted scratch (the n of the last cell-list build)
     int64_t cap = 0;
     int64_t capacity_hint = 0;
     plife::SlabState slab;
@@ -172,6 +192,7 @@ struct plife_handle {
     int64_t cell_cap = 0;
     int64_t tile_cap = 0;
     unsigned long long *d_scalar = nullptr; // small device scratch (counters)
+    unsigned long long *d_hist = nullptr;   // 256 type counters (inside the d_scalar allocation)
 
     plife::Grid last_grid{0, 0, 0.0};
     bool prebinned = false;   // d_cell / d_count already hold the binning of the current state (fused into the last force pass)

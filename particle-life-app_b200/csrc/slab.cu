@@ -28,6 +28,7 @@
 // single-GPU particle order.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "plife_internal.h"
@@ -39,6 +40,7 @@ int slab_make_grid(plife_handle *h, Grid *g);
 int slab_sort(plife_handle *h, const Grid &g);
 int slab_fail(plife_handle *h, int code, const char *msg);
 cudaError_t slab_force(plife_handle *h, const Grid &g, double dt);
+int slab_reset_capacity(plife_handle *h);
 } // namespace plife
 
 namespace {
@@ -46,6 +48,14 @@ namespace {
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ int offsets_records(int nx) { return (nx + 3) >> 2; }
+
+// wall-clock nanoseconds (not SM cycles: the spin limits below are times, whatever the clock does)
+__device__ __forceinline__ unsigned long long wall_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // dir 0: first owned row (local row 1) -> becomes the down neighbour's top ghost row
 // dir 1: last owned row (local row nly-2) -> becomes the up neighbour's bottom ghost row
@@ -101,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__
 __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_sorted, int32_t *__restrict__ cell_end, Grid g,
                                                         int first, int n, const float4 *msg0, const float4 *msg1, int *__restrict__ err,
                                                         const volatile unsigned long long *flag0, const volatile unsigned long long *flag1,
-                                                        unsigned long long seq)
+                                                        unsigned long long seq, unsigned long long spin_ns)
 {
     const int which = blockIdx.y;
     const float4 *msg = which ? msg1 : msg0;
@@ -114,9 +124,9 @@ __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_
         __shared__ int s_timeout;
         if (threadIdx.x == 0) {
             s_timeout = 0;
-            const long long t0 = clock64();
+            const unsigned long long t0 = wall_ns();
             while (*flag < seq) {
-                if (clock64() - t0 > 20000000000ll) {
+                if (wall_ns() - t0 > spin_ns) {
                     s_timeout = 1;
                     break;
                 }
@@ -188,15 +198,14 @@ __global__ void __launch_bounds__(kThreads) push_msg(const float4 *__restrict__ 
 // error word where the host can read them after one stream synchronisation - mapped pinned memory, no copies.
 __global__ void finish_headers(const volatile unsigned long long *f0, const volatile unsigned long long *f1, unsigned long long seq,
                                int *err, const float4 *ms0, const float4 *ms1, const float4 *mi0, const float4 *mi1,
-                               volatile int4 *out)
+                               volatile int4 *out, unsigned long long spin_ns)
 {
-    const long long t0 = clock64();
-    const long long limit = 20000000000ll;
+    const unsigned long long t0 = wall_ns();
     for (int k = 0; k < 2; ++k) {
         const volatile unsigned long long *f = k ? f1 : f0;
         if (!f) continue;
         while (*f < seq) {
-            if (clock64() - t0 > limit) {
+            if (wall_ns() - t0 > spin_ns) {
                 atomicAdd(err, 1 << 16);
                 break;
             }
@@ -304,6 +313,11 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
     S.hrec = plife_slab_halo_records(g.nx, halo_cap);
     S.mrec = plife_slab_migrate_records(mig_cap);
     S.seq = 1;
+    // how long a kernel waits for a neighbour's message before it reports a dead peer (wall time; default 30 s)
+    if (const char *ev = getenv("PLIFE_SLAB_TIMEOUT_MS")) {
+        const double ms = atof(ev);
+        if (ms > 0) S.spin_ns = (unsigned long long)(ms * 1e6);
+    }
     if (bufs) { // external exchange: the host moves the messages between the phases
         for (int d = 0; d < 2; d++) {
             if (!bufs->halo_send[d] || !bufs->halo_recv[d] || !bufs->mig_send[d] || !bufs->mig_recv[d]) {
@@ -337,7 +351,7 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
     }
     S.phase = PLIFE_SLAB_SORT;
     h->prebinned = false;
-    return PLIFE_OK;
+    return slab_reset_capacity(h); // the particle buffers need room for the ghost rows
 }
 
 int plife_slab_export(plife_handle *h, void *ipc_handle_64_bytes)
@@ -466,7 +480,7 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         unpack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, first, (int)h->n,
                                                       has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr, d_err,
                                                       peer && has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr,
-                                                      peer && has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq);
+                                                      peer && has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq, S.spin_ns);
         CUS(h, cudaGetLastError());
         CUS(h, slab_force(h, g, dt));
         if (S.peer_mode) {
@@ -485,7 +499,7 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         const bool waits = S.peer_mode && (has_dn || has_up);
         finish_headers<<<1, 1, 0, h->stream>>>(waits && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, waits && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr,
                                                S.seq, d_err, S.mig_send[0], S.mig_send[1], has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr,
-                                               S.h_hdr);
+                                               S.h_hdr, S.spin_ns);
     }
     CUS(h, cudaGetLastError());
     CUS(h, cudaStreamSynchronize(h->stream));
