@@ -311,7 +311,8 @@ def slab_parity_check(torch, dist, plife, stream, rank, world, local_rank, excha
     pos, vel, types = synth.uniform_state(n, m, c["seed"])
     pos = pos.astype(np.float32).astype(np.float64)
     M = synth.random_matrix(m, c["seed"])
-    single = plife.NativePhysics(device=local_rank, precision=plife.F32, stream=stream.cuda_stream)
+    # same fine-bin count on both sides: the fp32 summation order follows the internal cell list
+    single = plife.NativePhysics(device=local_rank, precision=plife.F32, stream=stream.cuda_stream, bins=8)
     single.set_settings(rmax, 0.85, 1.0, True)
     single.set_matrix(M)
     single.upload(pos, vel, types)
@@ -321,7 +322,7 @@ def slab_parity_check(torch, dist, plife, stream, rank, world, local_rank, excha
     single.close()
     with torch.cuda.stream(stream):
         sl = SlabPhysics(rank, world, rmax, device=local_rank, capacity=n // world + n // 8 + 65536, halo_cap=16384, mig_cap=16384,
-                         wrap=True, stream=stream.cuda_stream, exchange=exchange)
+                         wrap=True, stream=stream.cuda_stream, exchange=exchange, bins=8)
         if exchange == "peer":
             sl.connect_dist()
         sl.native.set_matrix(M)

@@ -47,7 +47,7 @@ extern "C" {
 /* plife_config.flags */
 #define PLIFE_FLAG_UNSTABLE_SORT 1 /* skip the in-cell stable ordering (faster; order in a cell arbitrary) */
 #define PLIFE_FLAG_NO_GRAPH 2      /* reserved: this version never captures the step into a CUDA graph */
-#define PLIFE_FLAG_PAIRS 16        /* fp32, kind 0: opt into the two-targets-per-lane force kernel (experimental) */
+/* 16 was PLIFE_FLAG_PAIRS (round 1's experimental two-targets-per-lane kernel, removed); the bit is ignored */
 #define PLIFE_FLAG_NO_FUSED_BIN 8  /* do not fuse the next step's binning into the force pass */
 #define PLIFE_FLAG_FORCE_V1 4      /* fp32: use the global-memory force kernel instead of the shared-memory staged one */
 
@@ -69,7 +69,8 @@ typedef struct plife_config {
     int32_t precision; /* PLIFE_F32 | PLIFE_F64 */
     int64_t capacity;  /* particle capacity hint (buffers grow on upload) */
     int32_t flags;     /* PLIFE_FLAG_* */
-    int32_t reserved;
+    int32_t bins;      /* fp32: fine bins per cell along x for the internal cell list: 0 = chosen from the density, or 1, 2, 4, 8
+                          (results and the particle order do not depend on it, only the speed) */
     void *stream;      /* cudaStream_t to run on, or NULL: the library creates its own */
 } plife_config;
 
@@ -234,9 +235,14 @@ typedef struct plife_slab_buffers {
     void *halo_send[2], *halo_recv[2], *mig_send[2], *mig_recv[2];
 } plife_slab_buffers;
 
+/* A slab step never synchronises with the host: the particle counts of a rank (they change with migration) live in
+ * device memory, kernels are sized by an upper bound, and the host reads the counts back a few steps late.  So an error
+ * the device finds in a step (halo / migration overflow, a particle crossing more than one slab, a dead neighbour)
+ * is returned by a LATER call: the next plife_slab_phase that sees it, or any synchronising call (plife_sync,
+ * plife_count, plife_download, snapshots).  plife_count() drains the queued steps first. */
 #define PLIFE_SLAB_SORT 0   /* cell-list build of the owned particles + pack halo rows */
-#define PLIFE_SLAB_FORCE 1  /* place ghost rows, force + integrate, pack leavers */
-#define PLIFE_SLAB_FINISH 2 /* append arrivals; synchronises; updates plife_count() */
+#define PLIFE_SLAB_FORCE 1  /* force + integrate: interior rows, then place the ghost rows, then the two edge rows; pack leavers */
+#define PLIFE_SLAB_FINISH 2 /* new counts on the device, append arrivals */
 
 int64_t plife_slab_halo_records(int32_t nx, int64_t halo_cap);
 int64_t plife_slab_migrate_records(int64_t mig_cap);

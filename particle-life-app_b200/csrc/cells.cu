@@ -42,101 +42,93 @@ __global__ void __launch_bounds__(kThreads) bin_f64(const double2 *__restrict__ 
     atomicAdd(&count[container_of(cxy, g)], 1);
 }
 
-// ---- exclusive scan over cells: tile sums -> scan of sums -> apply ----
-// One pass scans two quantities packed into 64 bits: the particle count of a cell (low word ->
-// cell_end, the reference's `containers`) and its number of target PAIRS ceil(count/2) (high word ->
-// pair_start, used by the two-targets-per-lane force kernel).
+// ---- exclusive scan over the (fine) bins: tile sums -> scan of sums -> apply ----
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
-constexpr int kScanTile = kScanThreads * kScanItems; // 4096 cells per CTA
+constexpr int kScanTile = kScanThreads * kScanItems; // 4096 bins per CTA
 using u64 = unsigned long long;
 
-__device__ __forceinline__ u64 pack_count(int c) { return (u64)(unsigned)c | ((u64)(unsigned)((c + 1) >> 1) << 32); }
-
-__device__ __forceinline__ u64 warp_inclusive_scan(u64 v, int lane)
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane)
 {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        u64 t = __shfl_up_sync(0xffffffffu, v, o);
+        int t = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o) v += t;
     }
     return v;
 }
 
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix and the block total
-__device__ __forceinline__ u64 block_exclusive_scan(u64 v, u64 &total, u64 *smem /* >= 33 */)
+__device__ __forceinline__ int block_exclusive_scan(int v, int &total, int *smem /* >= 33 */)
 {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 inc = warp_inclusive_scan(v, lane);
+    int inc = warp_inclusive_scan(v, lane);
     if (lane == 31) smem[warp] = inc;
     __syncthreads();
     if (warp == 0) {
         int nw = (blockDim.x + 31) >> 5;
-        u64 w = lane < nw ? smem[lane] : 0;
-        u64 winc = warp_inclusive_scan(w, lane);
+        int w = lane < nw ? smem[lane] : 0;
+        int winc = warp_inclusive_scan(w, lane);
         smem[lane] = winc - w;
         if (lane == 31) smem[32] = winc;
     }
     __syncthreads();
-    u64 r = smem[warp] + inc - v;
+    int r = smem[warp] + inc - v;
     total = smem[32];
     __syncthreads();
     return r;
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *__restrict__ count, int64_t ncell,
-                                                               u64 *__restrict__ tile_sums)
+                                                               int32_t *__restrict__ tile_sums)
 {
-    __shared__ u64 sm[33];
+    __shared__ int sm[33];
     int64_t base = (int64_t)blockIdx.x * kScanTile;
-    u64 s = 0;
-    // vectorised: each thread sums 16 consecutive cells (4 x int4)
+    int s = 0;
+    // vectorised: each thread sums 16 consecutive bins (4 x int4)
     int64_t first = base + (int64_t)threadIdx.x * kScanItems;
     if (first + kScanItems <= ncell) {
         const int4 *p = reinterpret_cast<const int4 *>(count + first);
 #pragma unroll
         for (int k = 0; k < kScanItems / 4; k++) {
             int4 v = __ldg(p + k);
-            s += pack_count(v.x) + pack_count(v.y) + pack_count(v.z) + pack_count(v.w);
+            s += v.x + v.y + v.z + v.w;
         }
     } else {
         for (int k = 0; k < kScanItems; k++)
-            if (first + k < ncell) s += pack_count(count[first + k]);
+            if (first + k < ncell) s += count[first + k];
     }
-    u64 total;
+    int total;
     block_exclusive_scan(s, total, sm);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) scan_sums(u64 *__restrict__ tile_sums, int ntiles, int carry0,
-                                                  int32_t *__restrict__ cell_end, int32_t *__restrict__ npairs)
+__global__ void __launch_bounds__(1024) scan_sums(int32_t *__restrict__ tile_sums, int ntiles, int carry0,
+                                                  int32_t *__restrict__ cell_end)
 {
-    __shared__ u64 sm[33];
-    u64 carry = (u64)(unsigned)carry0; // particle offsets start after the ghost-below capacity; pairs at 0
-    if (threadIdx.x == 0) cell_end[-1] = carry0; // start of local cell 0
+    __shared__ int sm[33];
+    int carry = carry0; // particle offsets start after the ghost-below capacity
+    if (threadIdx.x == 0) cell_end[-1] = carry0; // start of local bin 0
     for (int base = 0; base < ntiles; base += 1024) {
         int i = base + threadIdx.x;
-        u64 v = i < ntiles ? tile_sums[i] : 0;
-        u64 total;
-        u64 ex = block_exclusive_scan(v, total, sm);
+        int v = i < ntiles ? tile_sums[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, total, sm);
         if (i < ntiles) tile_sums[i] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) *npairs = (int32_t)(carry >> 32);
 }
 
-// writes the exclusive prefixes (the cursor start of every cell, the first pair of every cell) and
-// zeroes count for the next step
-template <bool PAIRS>
+// writes the exclusive prefixes (the cursor start of every bin) and zeroes count for the next step
 __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__ count, int64_t ncell,
-                                                           const u64 *__restrict__ tile_sums,
-                                                           int32_t *__restrict__ cell_end, int32_t *__restrict__ pair_start)
+                                                           const int32_t *__restrict__ tile_sums,
+                                                           int32_t *__restrict__ cell_end)
 {
-    __shared__ u64 sm[33];
+    __shared__ int sm[33];
     int64_t base = (int64_t)blockIdx.x * kScanTile;
     int64_t first = base + (int64_t)threadIdx.x * kScanItems;
     int v[kScanItems];
-    u64 s = 0;
+    int s = 0;
     bool full = first + kScanItems <= ncell;
     if (full) {
         int4 *p = reinterpret_cast<int4 *>(count + first);
@@ -157,53 +149,50 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
         }
     }
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) s += pack_count(v[k]);
-    u64 total;
-    u64 ex = block_exclusive_scan(s, total, sm) + tile_sums[blockIdx.x];
+    for (int k = 0; k < kScanItems; k++) s += v[k];
+    int total;
+    int ex = block_exclusive_scan(s, total, sm) + tile_sums[blockIdx.x];
     if (full) {
         int4 *o = reinterpret_cast<int4 *>(cell_end + first);
-        int4 *po = reinterpret_cast<int4 *>(pair_start + first);
 #pragma unroll
         for (int k = 0; k < kScanItems / 4; k++) {
-            int4 q, r;
-            q.x = (int)ex; r.x = (int)(ex >> 32); ex += pack_count(v[4 * k]);
-            q.y = (int)ex; r.y = (int)(ex >> 32); ex += pack_count(v[4 * k + 1]);
-            q.z = (int)ex; r.z = (int)(ex >> 32); ex += pack_count(v[4 * k + 2]);
-            q.w = (int)ex; r.w = (int)(ex >> 32); ex += pack_count(v[4 * k + 3]);
+            int4 q;
+            q.x = ex; ex += v[4 * k];
+            q.y = ex; ex += v[4 * k + 1];
+            q.z = ex; ex += v[4 * k + 2];
+            q.w = ex; ex += v[4 * k + 3];
             o[k] = q;
-            if (PAIRS) po[k] = r; // only the two-targets-per-lane kernel reads pair_start
         }
     } else {
 #pragma unroll
         for (int k = 0; k < kScanItems; k++) {
-            if (first + k < ncell) {
-                cell_end[first + k] = (int)ex;
-                if (PAIRS) pair_start[first + k] = (int)(ex >> 32);
-            }
-            ex += pack_count(v[k]);
+            if (first + k < ncell) cell_end[first + k] = ex;
+            ex += v[k];
         }
     }
 }
 
 // B/Physics.java:343-348: `i = containers[ci]; buffer[i] = p; containers[ci]++`.
-// Afterwards cell_end[ci] is the END offset of cell ci, as in the reference.
+// Afterwards cell_end[b] is the END offset of bin b, as in the reference (per cell: every K-th entry).
 constexpr int kScatterUnroll = 4; // measured: 1 -> 0.078 ms, 4 -> 0.056 ms at 16M particles
 
 template <bool AGG>
-__global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, int n_phys, Grid g, int first,
+__global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restrict__ cell, DevInt n_phys_, Grid g, int first,
                                                          int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
 {
     // Several slots per thread: the kernel is load -> atomic round trip -> store, so what counts is how many atomics are
     // in flight.  All loads first, then all atomics, then the stores.
     constexpr int U = kScatterUnroll;
+    const int n_phys = n_phys_.get();
     const int i0 = blockIdx.x * (kThreads * U) + threadIdx.x;
+    if (blockIdx.x * (kThreads * U) >= n_phys) return;
     int c[U], slot[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int i = i0 + u * kThreads;
         c[u] = i < n_phys ? container_of(__ldg(&cell[i]), g) : -1; // -1: dead slot (the particle migrated to another slab)
     }
-    if (!AGG) { // sparse grids: every lane has its own cell, aggregation only costs
+    if (!AGG) { // sparse grids: every lane has its own bin, aggregation only costs
 #pragma unroll
         for (int u = 0; u < U; ++u) slot[u] = c[u] >= 0 ? atomicAdd(&cell_end[c[u]], 1) : -1;
 #pragma unroll
@@ -212,8 +201,8 @@ __global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restri
         return;
     }
     // Warp-aggregated cursor: after the first step the array is almost cell-sorted, so the 32 lanes of a warp hit
-    // 2-3 distinct cells; one atomic per distinct cell instead of one per particle, and neighbouring slots for
-    // lanes of the same cell.  (Order inside a cell is still arbitrary across warps; K_GATHER ranks it.)
+    // few distinct bins; one atomic per distinct bin instead of one per particle, and neighbouring slots for
+    // lanes of the same bin.  (Order inside a bin is still arbitrary across warps; K_GATHER ranks it.)
     const int lane = threadIdx.x & 31;
     unsigned peers[U];
 #pragma unroll
@@ -234,84 +223,94 @@ __global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restri
 // three groups in the order of their previous GLOBAL array index, which is what the reference's stable
 // sort preserves: below < residents < above, except across the periodic seam, where rank 0's arrivals
 // from "below" come from the END of the global array and the last rank's arrivals from "above" from its
-// beginning (launch_gather picks the bases).
+// beginning.  The counts live in device memory (SlabCounts): the host does not know them when it queues the step.
 struct StableKey {
-    int n_old, k_below;
-    int base_res, base_below, base_above;
+    const SlabCounts *cnt;
+    int order; // 0: below, residents, above   1 (rank 0, periodic): residents, above, below   2 (last rank, periodic): above, below, residents
+    int n_old, k_below, base_res, base_below, base_above;
+    __device__ __forceinline__ void load()
+    {
+        n_old = cnt->n_old;
+        k_below = cnt->k_below;
+        const int ka = cnt->k_above;
+        if (order == 1) { base_res = 0; base_below = n_old + ka; base_above = n_old; }
+        else if (order == 2) { base_res = ka + k_below; base_below = ka; base_above = 0; }
+        else { base_res = k_below; base_below = 0; base_above = k_below + n_old; }
+    }
     __device__ __forceinline__ int operator()(int src) const
     {
         if (src < n_old) return src + base_res;
         src -= n_old;
         return src < k_below ? src + base_below : src - k_below + base_above;
     }
-    __device__ __forceinline__ bool mixed(int max_src) const { return max_src >= n_old; } // the cell holds an arrival
+    __device__ __forceinline__ bool mixed(int max_src) const { return max_src >= n_old; } // the range holds an arrival
 };
 
-// slot of `src` in the sorted array; also registers the leader (even rank) of every target pair of the cell
 struct IdentityKey { // single GPU: the pre-sort index is the previous array index
+    __device__ __forceinline__ void load() {}
     __device__ __forceinline__ int operator()(int src) const { return src; }
     __device__ __forceinline__ bool mixed(int) const { return false; }
 };
 
-template <bool STABLE, bool PAIRS, typename KEY>
-__device__ __forceinline__ int sorted_slot(int d, int src, int c, const int32_t *__restrict__ cell_end,
-                                           const int32_t *__restrict__ perm, int first, KEY key,
-                                           const int32_t *__restrict__ pair_start, int32_t *__restrict__ pair_first)
+// number of entries of pp[s, e) (pre-sort slots of one cell or bin) that precede `src` in the previous array order
+template <typename KEY>
+__device__ __forceinline__ int stable_rank(const int32_t *__restrict__ pp, int s, int e, int src, int align, const KEY &key)
 {
-    const int s = __ldg(&cell_end[c - 1]);
-    int rank;
-    if (STABLE) {
-        const int e = __ldg(&cell_end[c]);
-        // Raw pre-sort indices order the residents exactly like their keys do, and almost every cell holds residents
-        // only, so rank on the raw indices (four per load: cells of an evolved state hold thousands of particles and
-        // this loop is O(count^2) per cell) and track the largest one; only cells that received migrants (slab mode)
-        // are ranked again through the key.
-        const int32_t *pp = perm - first;
-        rank = 0;
-        int mx = src;
-        int k = s;
-        for (; k < e && ((k - first) & 3); ++k) {
-            const int q = __ldg(pp + k);
-            rank += (q < src) ? 1 : 0;
-            mx = max(mx, q);
-        }
-        for (; k + 4 <= e; k += 4) {
-            const int4 q = __ldg(reinterpret_cast<const int4 *>(pp + k));
-            rank += ((q.x < src) ? 1 : 0) + ((q.y < src) ? 1 : 0) + ((q.z < src) ? 1 : 0) + ((q.w < src) ? 1 : 0);
-            mx = max(max(mx, q.x), max(q.y, max(q.z, q.w)));
-        }
-        for (; k < e; ++k) {
-            const int q = __ldg(pp + k);
-            rank += (q < src) ? 1 : 0;
-            mx = max(mx, q);
-        }
-        if (key.mixed(mx)) {
-            rank = 0;
-            const int ksrc = key(src);
-            for (k = s; k < e; ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
-        }
-    } else {
-        rank = d + first - s;
+    // Raw pre-sort indices order the residents exactly like their keys do, and almost every cell holds residents
+    // only, so rank on the raw indices (four per load: cells of an evolved state hold thousands of particles and
+    // this loop is O(count^2) per cell) and track the largest one; only cells that received migrants (slab mode)
+    // are ranked again through the key.
+    int rank = 0;
+    int mx = src;
+    int k = s;
+    for (; k < e && ((k - align) & 3); ++k) {
+        const int q = __ldg(pp + k);
+        rank += (q < src) ? 1 : 0;
+        mx = max(mx, q);
     }
-    if (PAIRS && (rank & 1) == 0) pair_first[__ldg(&pair_start[c]) + (rank >> 1)] = s + rank - first;
-    return s + rank;
+    for (; k + 4 <= e; k += 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(pp + k));
+        rank += ((q.x < src) ? 1 : 0) + ((q.y < src) ? 1 : 0) + ((q.z < src) ? 1 : 0) + ((q.w < src) ? 1 : 0);
+        mx = max(max(mx, q.x), max(q.y, max(q.z, q.w)));
+    }
+    for (; k < e; ++k) {
+        const int q = __ldg(pp + k);
+        rank += (q < src) ? 1 : 0;
+        mx = max(mx, q);
+    }
+    if (key.mixed(mx)) {
+        rank = 0;
+        const int ksrc = key(src);
+        for (k = s; k < e; ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
+    }
+    return rank;
 }
 
 constexpr int kGatherUnroll = 2; // measured: 1 -> 0.186 ms, 2 -> 0.166 ms, 4 -> 0.190 ms at 16M particles
 
 // fp32: only the 16-byte candidate record moves.  Velocities stay where they are - each is needed once, by its own
-// particle - and the force pass reads them through src_sorted (12 bytes per particle less traffic here).
-template <bool STABLE, bool PAIRS, typename KEY>
-__global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, float4 *__restrict__ pt_out, int n, Grid g,
+// particle - and the force pass reads them through src_sorted.
+//
+// Two orders come out of this pass.  The COMPUTE order (where the record goes: sorted by fine bin, stable inside a bin)
+// is what the force pass walks; the REFERENCE order (ref_sorted: sorted by cell, stable inside a cell - exactly the
+// permutation of B/Physics.java:343-348) is where the force pass writes its result, so the particle array the caller
+// sees is the reference's.  Bins nest in cells, so both slots lie in the cell's own index range; with ks = 0 they coincide.
+// The record's type field is stored shifted (kTypeShift): it is the byte offset of a row of the force kernel's per-lane
+// matrix table, so staging candidates in shared memory is a plain bulk copy.
+template <bool STABLE, bool FINE, typename KEY>
+__global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, float4 *__restrict__ pt_out, DevInt n_, Grid g,
                                                        int first, KEY key, const int32_t *__restrict__ cell,
                                                        int32_t *__restrict__ cell_sorted, int32_t *__restrict__ src_sorted,
-                                                       const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm,
-                                                       const int32_t *__restrict__ pair_start, int32_t *__restrict__ pair_first)
+                                                       int32_t *__restrict__ ref_sorted, const int32_t *__restrict__ cell_end,
+                                                       const int32_t *__restrict__ perm)
 {
     // Two slots per thread: the kernel is a chain of four dependent memory round trips (perm -> record and cell ->
-    // cell offsets -> keys of the cell), so its speed is the number of chains in flight; two per thread instead of one.
+    // bin offsets -> keys of the cell), so its speed is the number of chains in flight; two per thread instead of one.
     constexpr int U = kGatherUnroll;
+    const int n = n_.get();
     const int d0 = blockIdx.x * (kThreads * U) + threadIdx.x;
+    if (blockIdx.x * (kThreads * U) >= n) return;
+    key.load();
     int src[U], cxy[U], c[U];
     float4 p[U];
 #pragma unroll
@@ -328,22 +327,37 @@ __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict_
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) c[u] = src[u] >= 0 ? container_of(cxy[u], g) : 0;
+    const int32_t *pp = perm - first;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (src[u] < 0) continue;
         const int d = d0 + u * kThreads;
-        const int dst = sorted_slot<STABLE, PAIRS, KEY>(d, src[u], c[u], cell_end, perm, first, key, pair_start, pair_first);
+        const int c0 = FINE ? (c[u] >> g.ks) << g.ks : c[u]; // first bin of the cell (bins per row is a multiple of K)
+        const int cs = __ldg(&cell_end[c0 - 1]);              // start of the cell
+        int dst, ref;
+        if (STABLE) {
+            const int ce = __ldg(&cell_end[c0 + (1 << g.ks) - 1]);
+            ref = cs + stable_rank(pp, cs, ce, src[u], first, key);
+            dst = ref;
+            if (FINE) {
+                const int bs = __ldg(&cell_end[c[u] - 1]), be = __ldg(&cell_end[c[u]]);
+                dst = bs + stable_rank(pp, bs, be, src[u], first, key);
+            }
+        } else { // PLIFE_FLAG_UNSTABLE_SORT: the cursor order is the order
+            dst = ref = d + first;
+        }
+        p[u].z = __int_as_float(__float_as_int(p[u].z) << kTypeShift);
         pt_out[dst] = p[u]; // sorted positions carry the ghost-below offset `first`; per-target arrays do not
         cell_sorted[dst - first] = cxy[u];
         src_sorted[dst - first] = src[u];
+        ref_sorted[dst - first] = ref - first;
     }
 }
 
 template <bool STABLE>
 __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out, int n, Grid g, const int32_t *__restrict__ cell,
                                                        int32_t *__restrict__ cell_sorted, const int32_t *__restrict__ cell_end,
-                                                       const int32_t *__restrict__ perm, const int32_t *__restrict__ pair_start,
-                                                       int32_t *__restrict__ pair_first)
+                                                       const int32_t *__restrict__ perm)
 {
     int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= n) return;
@@ -353,12 +367,38 @@ __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out
     int t = __ldg(&in.type[src]);
     uint32_t id = __ldg(&in.id[src]);
     int cxy = __ldg(&cell[src]);
-    int dst = sorted_slot<STABLE, false, IdentityKey>(d, src, container_of(cxy, g), cell_end, perm, 0, IdentityKey{}, pair_start, pair_first);
+    const int c = container_of(cxy, g);
+    const int s = __ldg(&cell_end[c - 1]);
+    int dst = d;
+    if (STABLE) dst = s + stable_rank(perm, s, __ldg(&cell_end[c]), src, 0, IdentityKey{});
     cell_sorted[dst] = cxy;
     out.pos[dst] = p;
     out.vel[dst] = v;
     out.type[dst] = t;
     out.id[dst] = id;
+}
+
+// After plife_debug_neighbors on an fp32 handle the sort becomes the visible state, like makeContainers' swap
+// (B/Physics.java:351-353): records go back to plain types at their reference slots, velocities follow them.
+__global__ void __launch_bounds__(kThreads) apply_sort_f32(const float4 *__restrict__ pt_sorted, const float2 *__restrict__ vel_in,
+                                                           const int32_t *__restrict__ src_sorted, const int32_t *__restrict__ ref_sorted,
+                                                           int n, float4 *__restrict__ pt_out, float2 *__restrict__ vel_out)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float4 p = __ldg(pt_sorted + i);
+    p.z = __int_as_float(__float_as_int(p.z) >> kTypeShift);
+    const int r = __ldg(ref_sorted + i);
+    pt_out[r] = p;
+    vel_out[r] = __ldg(vel_in + __ldg(src_sorted + i));
+}
+
+// END offset of every CELL = every K-th bin END offset (plife_get_containers)
+__global__ void __launch_bounds__(kThreads) containers_from_bins(const int32_t *__restrict__ cell_end, int64_t ncell, int ks,
+                                                                 int32_t *__restrict__ out)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c < ncell) out[c] = __ldg(cell_end + ((c + 1) << ks) - 1);
 }
 
 __global__ void __launch_bounds__(kThreads) type_hist_f32(const float4 *__restrict__ pt, int n, int m,
@@ -540,7 +580,6 @@ __global__ void __launch_bounds__(kThreads) snapshot_live_f32(const float4 *__re
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 inline int first_index(const plife_handle *h) { return h->slab.on ? (int)h->slab.halo_cap : 0; }
-inline int32_t *npairs_ptr(plife_handle *h) { return reinterpret_cast<int32_t *>(h->d_scalar + 7); }
 
 } // namespace
 
@@ -557,62 +596,81 @@ cudaError_t launch_bin(plife_handle *h, const Grid &g)
 
 cudaError_t launch_scan(plife_handle *h, const Grid &g)
 {
-    int64_t ncell = (int64_t)g.nx * g.nly;
+    int64_t ncell = (int64_t)g.nxk() * g.nly;
     int ntiles = (int)((ncell + kScanTile - 1) / kScanTile);
-    u64 *ts = reinterpret_cast<u64 *>(h->d_tile_sums);
+    int32_t *ts = reinterpret_cast<int32_t *>(h->d_tile_sums);
     scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts);
-    scan_sums<<<1, 1024, 0, h->stream>>>(ts, ntiles, first_index(h), h->d_cell_end, npairs_ptr(h));
-    if (h->flags & PLIFE_FLAG_PAIRS) scan_apply<true><<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts, h->d_cell_end, h->d_pair_start);
-    else scan_apply<false><<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts, h->d_cell_end, h->d_pair_start);
+    scan_sums<<<1, 1024, 0, h->stream>>>(ts, ntiles, first_index(h), h->d_cell_end);
+    scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts, h->d_cell_end);
     return cudaGetLastError();
 }
 
+// Slab mode with device-resident counts: the host sizes the grids by an upper bound (h->n_bound) and the kernels read
+// the true counts from SlabCounts; CTAs beyond the count exit at once.
 cudaError_t launch_scatter(plife_handle *h, const Grid &g)
 {
-    int n = (int)h->n_phys; // physical pre-sort length (dead slots included)
+    const bool dev = h->slab.on && h->slab.counts;
+    const int n = dev ? (int)h->slab.n_bound : (int)h->n_phys; // physical pre-sort length (dead slots included)
     if (n == 0) return cudaSuccess;
-    const double rho = (double)h->n / ((double)g.nx * (g.row_hi - g.row_lo));
-    if (rho >= 4.0) scatter_perm<true><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
-    else scatter_perm<false><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, n, g, first_index(h), h->d_cell_end, h->d_perm);
+    const DevInt np{(int)h->n_phys, dev ? &h->slab.counts->n_phys : nullptr};
+    const double rho = (double)h->n / ((double)g.nxk() * (g.row_hi - g.row_lo)); // particles per bin
+    if (rho >= 4.0) scatter_perm<true><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, np, g, first_index(h), h->d_cell_end, h->d_perm);
+    else scatter_perm<false><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, np, g, first_index(h), h->d_cell_end, h->d_perm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gather(plife_handle *h, const Grid &g)
 {
-    int n = (int)h->n;
+    const bool dev = h->slab.on && h->slab.counts;
+    const int n = dev ? (int)h->slab.n_bound : (int)h->n;
     if (n == 0) return cudaSuccess;
     int a = h->cur, b = h->cur ^ 1;
     bool stable = !(h->flags & PLIFE_FLAG_UNSTABLE_SORT);
     int nb = h->precision == PLIFE_F32 ? blocks_for(n, kThreads * kGatherUnroll) : blocks_for(n, kThreads);
-    int32_t *pf = (h->flags & PLIFE_FLAG_PAIRS) ? h->d_pair_first : nullptr; // only the opt-in pairs kernel needs it
-    StableKey key{0x7fffffff, 0, 0, 0, 0};
-    if (h->slab.on) {
-        const SlabState &S = h->slab;
-        const int no = (int)S.n_old, kb = (int)S.k_below, ka = (int)S.k_above;
-        const bool wrap = h->settings.wrap != 0 && S.world > 1;
-        if (wrap && S.rank == 0 && S.world > 1 && S.rank != S.world - 1) key = StableKey{no, kb, 0, no + ka, no}; // residents, above, below(seam)
-        else if (wrap && S.rank == S.world - 1) key = StableKey{no, kb, ka + kb, ka, 0};                          // above(seam), below, residents
-        else key = StableKey{no, kb, kb, 0, kb + no};                                                             // below, residents, above
-    }
     if (h->precision == PLIFE_F32) {
-#define PLIFE_GATHER(ST, PR, KT, KV)                                                                                      \
-    gather_f32<ST, PR, KT><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[b].pt, n, g, first_index(h), KV, h->d_cell,  \
-                                                           h->d_cell_sorted, h->d_src_sorted, h->d_cell_end, h->d_perm,     \
-                                                           h->d_pair_start, pf)
+        const DevInt nn{(int)h->n, dev ? &h->slab.counts->n : nullptr};
+        const bool fine = g.ks > 0;
+#define PLIFE_GATHER(ST, FN, KT, KV)                                                                                        \
+    gather_f32<ST, FN, KT><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[b].pt, nn, g, first_index(h), KV, h->d_cell, \
+                                                           h->d_cell_sorted, h->d_src_sorted, h->d_ref_sorted, h->d_cell_end, h->d_perm)
         if (h->slab.on) { // arrivals are ordered by their previous global position (StableKey)
-            if (stable) PLIFE_GATHER(true, false, StableKey, key);
+            const SlabState &S = h->slab;
+            const bool wrap = h->settings.wrap != 0 && S.world > 1;
+            int order = 0;
+            if (wrap && S.rank == 0 && S.rank != S.world - 1) order = 1;  // residents, above, below(seam)
+            else if (wrap && S.rank == S.world - 1) order = 2;            // above(seam), below, residents
+            StableKey key{S.counts, order, 0, 0, 0, 0, 0};
+            if (stable && fine) PLIFE_GATHER(true, true, StableKey, key);
+            else if (stable) PLIFE_GATHER(true, false, StableKey, key);
             else PLIFE_GATHER(false, false, StableKey, key);
-        } else if (stable && pf) PLIFE_GATHER(true, true, IdentityKey, IdentityKey{});
+        } else if (stable && fine) PLIFE_GATHER(true, true, IdentityKey, IdentityKey{});
         else if (stable) PLIFE_GATHER(true, false, IdentityKey, IdentityKey{});
-        else if (pf) PLIFE_GATHER(false, true, IdentityKey, IdentityKey{});
         else PLIFE_GATHER(false, false, IdentityKey, IdentityKey{});
 #undef PLIFE_GATHER
     } else {
         if (stable)
-            gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, nullptr);
+            gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
         else
-            gather_f64<false><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm, h->d_pair_start, nullptr);
+            gather_f64<false><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
     }
+    return cudaGetLastError();
+}
+
+// fp32: make the sorted scratch (compute order, shifted types) the visible state in reference order
+cudaError_t launch_apply_sort_f32(plife_handle *h)
+{
+    const int n = (int)h->n;
+    if (n == 0) return cudaSuccess;
+    const int a = h->cur, b = h->cur ^ 1;
+    apply_sort_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[b].pt, h->s32[a].vel, h->d_src_sorted, h->d_ref_sorted,
+                                                                      n, h->s32[a].pt, h->s32[b].vel);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_containers(plife_handle *h, const Grid &g, int32_t *d_out)
+{
+    const int64_t ncell = (int64_t)g.nx * g.nly;
+    containers_from_bins<<<blocks_for(ncell, kThreads), kThreads, 0, h->stream>>>(h->d_cell_end, ncell, g.ks, d_out);
     return cudaGetLastError();
 }
 

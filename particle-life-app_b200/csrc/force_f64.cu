@@ -15,7 +15,8 @@ cudaError_t launch_force_f64(plife_handle *h, const ForceParams<double> &p)
 {
     NextBin nb{nullptr, nullptr, {nullptr, nullptr}, 0};
     if (!(h->flags & PLIFE_FLAG_NO_FUSED_BIN)) nb = NextBin{h->d_cell, h->d_count, {nullptr, nullptr}, 0};
-    return dispatch_force<IOF64, false>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, (const double *)h->d_matrix_t, h->acc_kind, nb, h->stream);
+    return dispatch_force<IOF64, false>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, (p.n + kForceThreads - 1) / kForceThreads,
+                                        (const double *)h->d_matrix_t, h->acc_kind, nb, h->stream);
 }
 
 cudaError_t launch_neighbors_f64(plife_handle *h, const ForceParams<double> &p, int32_t *cnt, unsigned long long *hash)

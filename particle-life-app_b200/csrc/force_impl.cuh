@@ -27,15 +27,16 @@ struct Cand {
 // ---- state access policies -------------------------------------------------
 struct IOF32 {
     using R = float;
-    const float4 *__restrict__ pt;        // sorted records (candidates and own position)
+    const float4 *__restrict__ pt;        // sorted records in COMPUTE order (candidates and own position), type << kTypeShift
     const float2 *__restrict__ vel;       // velocities in PRE-sort order: the gather does not move them
     float4 *__restrict__ pt_out;
     float2 *__restrict__ vel_out;         // the other velocity buffer; the launcher swaps the two afterwards
     const int32_t *__restrict__ src;      // pre-sort slot of sorted particle i
+    const int32_t *__restrict__ ref;      // slot of sorted particle i in the reference's order: where its result goes
     __device__ __forceinline__ Cand<float> cand(int j) const
     {
         float4 q = __ldg(pt + j);
-        return Cand<float>{q.x, q.y, __float_as_int(q.z), __float_as_uint(q.w)};
+        return Cand<float>{q.x, q.y, __float_as_int(q.z) >> kTypeShift, __float_as_uint(q.w)};
     }
     __device__ __forceinline__ Cand<float> cand_pos(int j) const { return cand(j); } // one record: the type rides along
     __device__ __forceinline__ void cand_type(int, Cand<float> &) const {}
@@ -45,10 +46,11 @@ struct IOF32 {
         vx = v.x;
         vy = v.y;
     }
-    __device__ __forceinline__ void store(int i, float x, float y, float vx, float vy, int type, uint32_t id) const
+    __device__ __forceinline__ int out_slot(int i) const { return __ldg(ref + i); }
+    __device__ __forceinline__ void store(int o, float x, float y, float vx, float vy, int type, uint32_t id) const
     {
-        pt_out[i] = make_float4(x, y, __int_as_float(type), __uint_as_float(id));
-        vel_out[i] = make_float2(vx, vy);
+        pt_out[o] = make_float4(x, y, __int_as_float(type), __uint_as_float(id));
+        vel_out[o] = make_float2(vx, vy);
     }
 };
 
@@ -72,12 +74,13 @@ struct IOF64 {
         vx = v.x;
         vy = v.y;
     }
-    __device__ __forceinline__ void store(int i, double x, double y, double vx, double vy, int type, uint32_t id) const
+    __device__ __forceinline__ int out_slot(int i) const { return i; } // fp64: the sorted order IS the reference's
+    __device__ __forceinline__ void store(int o, double x, double y, double vx, double vy, int type, uint32_t id) const
     {
-        out.pos[i] = make_double2(x, y);
-        out.vel[i] = make_double2(vx, vy);
-        out.type[i] = type;
-        out.id[i] = id;
+        out.pos[o] = make_double2(x, y);
+        out.vel[o] = make_double2(vx, vy);
+        out.type[o] = type;
+        out.id[o] = id;
     }
 };
 
@@ -186,10 +189,7 @@ __device__ __forceinline__ void traverse_listed(const IO &io, const int32_t *__r
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         int j = 0, e = 0;
-        if (interior) {
-            j = __ldg(cell_end + base0 + r * g.nx - 2);
-            e = __ldg(cell_end + base0 + r * g.nx + 1);
-        }
+        if (interior) cell_span(cell_end, base0 + r * g.nx - 1, base0 + r * g.nx + 1, g.ks, j, e);
         int rb = j;
         if (r == 0) b0 = rb; else if (r == 1) b1 = rb; else b2 = rb;
         for (;;) {
@@ -216,13 +216,14 @@ __device__ __forceinline__ void traverse_listed(const IO &io, const int32_t *__r
 // wrapConnection is the identity) merge the three cells of a row into one
 // contiguous index range; the candidate j == i is NOT filtered there (its
 // d2 == 0 fails the in-range test).  All other lanes take the literal path.
+// (fp32 handles with fine bins: the candidates of a cell are the reference's, their order inside the cell is by bin.)
 template <typename IO, typename V>
 __device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict__ cell_end, const Grid &g, int wrap,
                                          int i, typename IO::R xi, typename IO::R yi, int cxy, V &v)
 {
     using R = typename IO::R;
     // :404-405 floor(x / containerSize) without the ==nx clamp: cached by the binning pass (cell_coords)
-    const int cx0 = cxy & 0xffff;
+    const int cx0 = (cxy & 0xffff) >> g.ks;
     const int cy0 = cxy >> 16;
     const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
     if constexpr (is_deferred<V>::value) {
@@ -233,8 +234,8 @@ __device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict
 #pragma unroll 1
         for (int oy = -1; oy <= 1; ++oy) {
             const int base = (cy0 + g.ly_shift + oy) * g.nx + cx0; // local cell of (cx0, cy0 + oy)
-            const int s = __ldg(cell_end + base - 2);               // cell_end[-1] is valid
-            const int e = __ldg(cell_end + base + 1);
+            int s, e;
+            cell_span(cell_end, base - 1, base + 1, g.ks, s, e);
 #pragma unroll 4
             for (int j = s; j < e; ++j) {
                 Cand<R> q = io.cand(j);
@@ -254,8 +255,8 @@ __device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict
                 continue; // :414-416
             }
             const int ci = cx + local_row(cy, g) * g.nx; // :418 (local cell index)
-            const int s = __ldg(cell_end + ci - 1);      // :420
-            const int e = __ldg(cell_end + ci);          // :421
+            int s, e;                                    // :420-421
+            cell_span(cell_end, ci, ci, g.ks, s, e);
             for (int j = s; j < e; ++j) {
                 if (j == i) continue; // :424
                 Cand<R> q = io.cand(j);
@@ -319,7 +320,6 @@ __device__ __forceinline__ void accelerate(R a, R px, R py, const R *prm, R &ox,
 constexpr int kMatGlobal = 0; // Mt in global memory (any m)
 constexpr int kMatShared = 1; // Mt copied to shared memory (m <= 64)
 constexpr int kMatLaneTab = 2; // per-lane copy of the lane's own matrix row (staged kernel, m <= 32)
-constexpr int kTabShift = 9;  // lane-table key = type << 9 = byte offset of row `type` (kForceThreads * 4 bytes per row)
 
 template <typename R, int MODE>
 struct MatrixView { // transposed matrix Mt[other][own]
@@ -338,7 +338,7 @@ struct MatrixView { // transposed matrix Mt[other][own]
             row = (uint32_t)__cvta_generic_to_shared(s + threadIdx.x);
         }
     }
-    // `key` is the candidate's type (MODE 0/1) or type << kTabShift (MODE 2)
+    // `key` is the candidate's type (MODE 0/1) or type << kTypeShift (MODE 2)
     __device__ __forceinline__ R get(int key) const
     {
         if (MODE == kMatShared) return lds(row + (uint32_t)key * mb); // one IMAD + one LDS
@@ -391,16 +391,16 @@ struct LiteralForce {
     }
 };
 
-// fp32 fast visitor for kind 0 (A/Main.java:275-280), branch-free, in absolute
-// distance units.  With b = beta*rmax, d0 = (1+beta)*rmax/2, h = (1-beta)*rmax/2
-// the reference force f(d/rmax) equals
+// fp32 fast visitor for kind 0 (A/Main.java:275-280), branch-free.  With b = beta*rmax, d0 = (1+beta)*rmax/2,
+// h = (1-beta)*rmax/2 (absolute distance units) the reference's f(d/rmax) is
 //     f = (1/b) * [ min(d - b, 0) + a' * max(h - |d - d0|, 0) ],  a' = a * 2*beta/(1-beta)
-// exactly: the first term is the repulsion (d < b), the second the triangular lobe
-// on [b, rmax], and both vanish beyond rmax, so the `d2 <= rmax^2` test
-// (B/Physics.java:432) is implied (f is continuous and 0 at the cutoff).  The
-// factor 1/b is folded into the final scale, a' into the shared-memory matrix.
-// Every constant is a direct constant-bank operand: no 3-register FFMA except
-// the three that must be (f and the two accumulators).
+// exactly: the first term is the repulsion (d < b), the second the triangular lobe on [b, rmax], and both vanish
+// beyond rmax, so the `d2 <= rmax^2` test (B/Physics.java:432) is implied (f is continuous and 0 at the cutoff).
+// The accumulated quantity is f*b/d (the acceleration is pos*(f/d), A/Main.java:279), computed straight from
+// u = 1/d = rsqrt(d2):
+//     f*b/d = min(1 - b*u, 0) + a' * max(h*u - |1 - d0*u|, 0)
+// which needs neither d nor a final multiplication by 1/d.  The factor 1/b is folded into the final scale
+// (fast_k), a' into the shared-memory matrix.
 template <int MODE>
 struct FastParticleLife32 {
     float ax, ay;
@@ -408,13 +408,13 @@ struct FastParticleLife32 {
     MatrixView<float, MODE> M;
     __device__ __forceinline__ void pair(int, const Cand<float> &q, float dx, float dy)
     {
-        float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
-        float rinv = rsqrt_fast(d2);
-        float d = d2 * rinv;
-        float a = M.get(q.type);
-        float rep = fminf(d - b, 0.0f);
-        float att = fmaxf(h - fabsf(d - d0), 0.0f);
-        float g = fmaf(a, att, rep) * rinv; // self / coincident: dx = dy = 0 kills the term
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
+        const float u = rsqrt_fast(d2);
+        const float a = M.get(q.type);
+        const float rep = fminf(fmaf(-b, u, 1.0f), 0.0f);
+        const float w = fmaf(-d0, u, 1.0f);
+        const float att = fmaxf(fmaf(h, u, -fabsf(w)), 0.0f);
+        const float g = fmaf(a, att, rep); // self / coincident: dx = dy = 0 kills the term
         ax = fmaf(g, dx, ax);
         ay = fmaf(g, dy, ay);
     }
@@ -455,8 +455,8 @@ struct PairCountVisitor {
 // message of that direction (two 16-byte records: {x,y,type,id}, {vx,vy,source slot,-}) and its
 // slot is marked dead; record 0 of a message is the header {count, far, -, -}.
 struct NextBin {
-    int32_t *cell;  // packed cell coords per particle, or nullptr: do not bin
-    int32_t *count; // per-cell histogram (zeroed by K_SCAN of this step)
+    int32_t *cell;  // bin word per particle, or nullptr: do not bin
+    int32_t *count; // per-bin histogram (zeroed by K_SCAN of this step)
     float4 *mig[2]; // migration messages [down, up] (slab mode) or nullptr
     int mig_cap;
     template <typename R>
@@ -493,6 +493,30 @@ struct NextBin {
     }
 };
 
+// The targets of a CTA.  Plain launch: CTA b owns sorted particles [128 b, 128 b + 128) below n.  Slab mode
+// splits the pass in two launches over device-resident index ranges (P.tr = {s0, e0, s1, e1}): the interior rows
+// while the halo is in flight, then the first and the last owned row.
+template <typename R>
+__device__ __forceinline__ bool cta_targets(const ForceParams<R> &P, int &i0, int &lim)
+{
+    const int b = blockIdx.x;
+    if (P.tr) {
+        const int s0 = P.tr[0], e0 = P.tr[1];
+        const int nb0 = (max(e0 - s0, 0) + kForceThreads - 1) / kForceThreads;
+        if (b < nb0) {
+            i0 = s0 + b * kForceThreads;
+            lim = e0;
+        } else {
+            i0 = P.tr[2] + (b - nb0) * kForceThreads;
+            lim = P.tr[3];
+        }
+    } else {
+        i0 = b * kForceThreads;
+        lim = P.n_dev ? *P.n_dev : P.n;
+    }
+    return i0 < lim;
+}
+
 // ---- kernels ---------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ void load_matrix_smem(R *sM, const R *__restrict__ gMt, int m, R scale)
@@ -510,11 +534,13 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
     using R = typename IO::R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *sM = reinterpret_cast<R *>(smem_raw);
+    int i0, lim;
+    if (!cta_targets(P, i0, lim)) return;
     const R mscale = FAST ? P.fast_a_scale : R(1);
     if (SMEM) load_matrix_smem(sM, gMt, P.m, mscale);
 
-    const int i = blockIdx.x * kForceThreads + threadIdx.x;
-    if (i >= P.n) return;
+    const int i = i0 + threadIdx.x;
+    if (i >= lim) return;
     const int si = P.first + i;
     const Cand<R> self = io.cand(si);
     const int cxy = __ldg(cell_sorted + i);
@@ -545,8 +571,9 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
         nx_ = range_clamp(nx_);
         ny_ = range_clamp(ny_);
     }
-    io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
-    nb.add(i, nx_, ny_, nvx, nvy, self.type, self.id, P.g);
+    const int o = io.out_slot(i);
+    io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
+    nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, P.g);
 }
 
 // The v2 kernels below exist ONLY in the fp32 translation unit.  force_f64.cu is compiled with
@@ -559,20 +586,24 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
 // address pattern, and the shared matrix lookup bank-conflicts between lanes of different cells
 // (profiles/r1_force_kernel.md); together they saturate L1TEX before the FP32 pipes.  Here each
 // CTA (128 consecutive sorted particles, about 8 cells) first copies the three index ranges that
-// cover the rows above / of / below its cells into shared memory - linear cell ids are
-// row-major, so [cellA + dy*nx - 1, cellB + dy*nx + 1] is ONE contiguous index range per dy -
-// and every lane copies its own matrix row into a [type][thread] table.  The inner loop then
-// issues one `LDS.128` (2.5 cycles with the 2-3 distinct addresses of a warp) and one
-// conflict-free `LDS.32` (bank = lane) per candidate.
+// cover the rows above / of / below its targets into shared memory - bin ids are row-major, so
+// [binA + dy*nxk - K, binB + dy*nxk + K] is ONE contiguous index range per dy - with three 1-D bulk copies
+// (cp.async.bulk + mbarrier, issued by one thread: no per-thread copy loop, no address arithmetic), and every lane
+// copies its own matrix row into a [type][thread] table.  The inner loop then issues one `LDS.128` (2.5 cycles with
+// the 2-3 distinct addresses of a warp) and one conflict-free `LDS.32` (bank = lane) per candidate.
+//
+// Fine bins: a lane walks the bins [own - K, own + K] of each row: every particle within rmax in x lies there
+// (bin = floor(K x / rmax) is monotone in x), and a row needs (2 + 1/K) cell widths of candidates instead of 3.
 //
 // Trip counts are rounded up to a multiple of 4 (no remainder loops): the extra candidates are
-// the first particles of cell cx0+2 or beyond, whose |dx| exceeds rmax for an interior lane, so
+// the first particles of the next bins, whose |dx| exceeds rmax for an interior lane, so
 // they contribute exactly zero; each staged range is followed by 3 far-away sentinels for the
 // case where the range itself ends.  Lanes on the domain seam walk global memory with the literal
 // 9-cell loop; CTAs whose ranges exceed the staging capacity (dense clusters) stream them through
 // it in chunks (traverse_chunked).
 constexpr int kTabMaxM = 32;
 constexpr int kStagePad = 3; // sentinels after each staged range
+static_assert(kForceThreads * 4 == (1 << kTypeShift), "lane-table row stride");
 
 __device__ __forceinline__ float4 lds128(uint32_t a)
 {
@@ -581,8 +612,37 @@ __device__ __forceinline__ float4 lds128(uint32_t a)
     return v;
 }
 
-// The literal 9-cell walk over global memory (seam lanes): B/Physics.java:412-437.
-template <int KEYSHIFT, typename V>
+// ---- mbarrier + 1-D bulk copy (TMA unit) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// size: multiple of 16 bytes, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// The literal 9-cell walk over global memory (seam lanes): B/Physics.java:412-437.  Records carry shifted types.
+template <typename V>
 __device__ __forceinline__ void traverse_global32(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g, int wrap,
                                                   int i, float xi, float yi, int cx0, int cy0, V &v)
 {
@@ -598,12 +658,12 @@ __device__ __forceinline__ void traverse_global32(const IOF32 &io, const int32_t
             continue;
         }
         const int ci = cx + local_row(cy, g) * g.nx;
-        const int s = __ldg(cell_end + ci - 1);
-        const int e = __ldg(cell_end + ci);
+        int s, e;
+        cell_span(cell_end, ci, ci, g.ks, s, e);
         for (int j = s; j < e; ++j) {
             if (j == i) continue;
-            Cand<float> q = io.cand(j);
-            q.type <<= KEYSHIFT;
+            const float4 r = __ldg(io.pt + j);
+            const Cand<float> q{r.x, r.y, __float_as_int(r.z), 0u}; // key = type << kTypeShift
             float dx, dy;
             if (wrap) {
                 dx = wrap_connection(xi, q.x);
@@ -617,32 +677,26 @@ __device__ __forceinline__ void traverse_global32(const IOF32 &io, const int32_t
     }
 }
 
-template <int KEYSHIFT = kTabShift, typename V>
-__device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g,
-                                                int wrap, int i, float xi, float yi, int cxy, bool staged_ok,
+// interior lane, staged ranges: 3 rows x bins [fb - K, fb + K]
+template <typename V>
+__device__ __forceinline__ void traverse_staged(const int32_t *__restrict__ cell_end, const Grid &g, float xi, float yi, int fb,
                                                 uint32_t stage_addr, int cap, const int *s_start, V &v)
 {
-    const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
-    const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
-    if (interior && staged_ok) {
-        const int base0 = (cy0 + g.ly_shift - 1) * g.nx + cx0;
+    const int K = 1 << g.ks, nxk = g.nxk();
 #pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
-            const int base = base0 + r * g.nx;
-            const int s = __ldg(cell_end + base - 2);
-            const int e = __ldg(cell_end + base + 1);
-            uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s - s_start[r]) * 16u;
-            const uint32_t a1 = a + (uint32_t)(e - s) * 16u;
-            for (; a < a1; a += 64u) { // 4 candidates per trip, padded (see above)
+    for (int r = 0; r < 3; ++r) {
+        const int base = fb + (r - 1) * nxk;
+        const int s = __ldg(cell_end + base - K - 1);
+        const int e = __ldg(cell_end + base + K);
+        uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s - s_start[r]) * 16u;
+        const uint32_t a1 = a + (uint32_t)(e - s) * 16u;
+        for (; a < a1; a += 64u) { // 4 candidates per trip, padded (see above)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 q = lds128(a + 16u * u);
-                    v.pair(-1, Cand<float>{q.x, q.y, __float_as_int(q.z), 0u}, q.x - xi, q.y - yi);
-                }
+            for (int u = 0; u < 4; ++u) {
+                const float4 q = lds128(a + 16u * u);
+                v.pair(-1, Cand<float>{q.x, q.y, __float_as_int(q.z), 0u}, q.x - xi, q.y - yi);
             }
         }
-    } else {
-        traverse_global32<KEYSHIFT>(io, cell_end, g, wrap, i, xi, yi, cx0, cy0, v);
     }
 }
 
@@ -654,20 +708,18 @@ __device__ __forceinline__ void traverse_staged(const IOF32 &io, const int32_t *
 // that runs off a chunk's end reads sentinels, never candidates the next chunk will deliver again.
 template <typename V>
 __device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g,
-                                                 int wrap, bool valid, int i, float xi, float yi, int cxy, float4 *stage,
+                                                 bool interior, float xi, float yi, int fb, float4 *stage,
                                                  uint32_t stage_addr, int chunk_cap, const int *s_start, const int *s_len, V &v)
 {
-    const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
-    const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
-    const int base0 = (cy0 + g.ly_shift - 1) * g.nx + cx0;
+    const int K = 1 << g.ks, nxk = g.nxk();
     const int tid = threadIdx.x;
 #pragma unroll 1
     for (int r = 0; r < 3; ++r) {
         int s = 0, e = 0;
         if (interior) {
-            const int base = base0 + r * g.nx;
-            s = __ldg(cell_end + base - 2);
-            e = __ldg(cell_end + base + 1);
+            const int base = fb + (r - 1) * nxk;
+            s = __ldg(cell_end + base - K - 1);
+            e = __ldg(cell_end + base + K);
         }
         const int row_lo = s_start[r], row_hi = row_lo + s_len[r];
 #pragma unroll 1
@@ -675,14 +727,8 @@ __device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t 
             const int clen = min(chunk_cap, row_hi - c0);
             __syncthreads(); // the previous chunk has been consumed
             const float4 *src = io.pt + c0;
-            for (int k = tid; k < clen + kStagePad; k += kForceThreads) {
-                float4 q = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
-                if (k < clen) {
-                    q = __ldg(src + k);
-                    q.z = __int_as_float(__float_as_int(q.z) << kTabShift);
-                }
-                stage[k] = q;
-            }
+            for (int k = tid; k < clen + kStagePad; k += kForceThreads)
+                stage[k] = k < clen ? __ldg(src + k) : make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
             __syncthreads();
             const int a0 = max(s, c0), a1 = min(e, c0 + clen);
             if (a0 < a1) {
@@ -698,34 +744,72 @@ __device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t 
             }
         }
     }
-    if (valid && !interior) traverse_global32<kTabShift>(io, cell_end, g, wrap, i, xi, yi, cx0, cy0, v);
 }
 
-// gM: row-major matrix [own][other] (for the vectorised row copy), gMt: transposed
+// gM: row-major matrix [own][other] (for the vectorised row copy)
 template <int KIND, bool FAST>
 __global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 io, const int32_t *__restrict__ cell_end,
                                                                     const int32_t *__restrict__ cell_sorted,
                                                                     ForceParams<float> P, const float *__restrict__ gM,
                                                                     int cap, NextBin nb)
 {
-    static_assert(kForceThreads * 4 == (1 << kTabShift), "lane-table row stride");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *stage = reinterpret_cast<float4 *>(smem_raw);                                      // [3][cap + kStagePad]
     float *tab = reinterpret_cast<float *>(smem_raw + (size_t)3 * (cap + kStagePad) * 16);      // [m][kForceThreads]
-    __shared__ int s_cell[2], s_start[3], s_len[3];
+    __shared__ int s_start[3], s_len[3];
+    __shared__ __align__(8) unsigned long long s_bar;
 
+    int i0, lim;
+    if (!cta_targets(P, i0, lim)) return;
     const int tid = threadIdx.x;
-    const int i = blockIdx.x * kForceThreads + tid;
-    const bool valid = i < P.n;
+    const int i = i0 + tid;
+    const bool valid = i < lim;
     const Grid g = P.g;
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+
+    // One thread finds the three row ranges of this CTA's targets and starts their copies; the others meanwhile
+    // load their own particle and fill the matrix table.
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        const int K = 1 << g.ks, nxk = g.nxk();
+        const int b0 = container_of(__ldg(cell_sorted + i0), g);
+        const int b1 = container_of(__ldg(cell_sorted + min(i0 + kForceThreads, lim) - 1), g);
+        int st[3], ln[3];
+        bool ok = true;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int lo = max(b0 + (r - 1) * nxk - K, P.bin_lo);
+            const int hi = min(b1 + (r - 1) * nxk + K, P.bin_hi);
+            st[r] = 0;
+            ln[r] = 0;
+            if (lo <= hi) {
+                st[r] = __ldg(cell_end + lo - 1);
+                ln[r] = __ldg(cell_end + hi) - st[r];
+            }
+            s_start[r] = st[r];
+            s_len[r] = ln[r];
+            ok = ok && ln[r] <= cap;
+        }
+        if (ok) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(ln[0] + ln[1] + ln[2]) * 16u);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float4 *dst = stage + r * (cap + kStagePad);
+                if (ln[r] > 0) bulk_g2s(stage_addr + (uint32_t)(r * (cap + kStagePad)) * 16u, io.pt + st[r], (uint32_t)ln[r] * 16u, bar);
+#pragma unroll
+                for (int k = 0; k < kStagePad; ++k) dst[ln[r] + k] = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f); // sentinel: far away, matrix key 0
+            }
+        }
+    }
     Cand<float> self{0.f, 0.f, 0, 0u};
     int cxy = 0;
     const int si = P.first + i; // index of this target in the sorted array (ghost rows precede it in slab mode)
+    float vx = 0.f, vy = 0.f;
     if (valid) {
         self = io.cand(si);
         cxy = __ldg(cell_sorted + i);
-        if (tid == 0) s_cell[0] = container_of(cxy, g);
-        if (tid == kForceThreads - 1 || i == P.n - 1) s_cell[1] = container_of(cxy, g);
+        io.self_vel(i, vx, vy);
     }
     // this lane's matrix row -> tab[other][tid] (bank = lane: conflict-free lookups)
     {
@@ -743,63 +827,36 @@ __global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 i
             for (int t = 0; t < P.m; ++t) tab[t * kForceThreads + tid] = __ldg(rowp + t) * mscale;
         }
     }
-    __syncthreads();
-    if (tid < 3) {
-        const int ncell = g.nx * g.nly;
-        int lo = s_cell[0] + (tid - 1) * g.nx - 1;
-        int hi = s_cell[1] + (tid - 1) * g.nx + 1;
-        lo = max(lo, 0);
-        hi = min(hi, ncell - 1);
-        int start = 0, len = 0;
-        if (lo <= hi) {
-            start = __ldg(cell_end + lo - 1);
-            len = __ldg(cell_end + hi) - start;
-        }
-        s_start[tid] = start;
-        s_len[tid] = len;
-    }
-    __syncthreads();
+    __syncthreads(); // s_start / s_len, the barrier's initialisation and the sentinels are visible
     const bool staged_ok = s_len[0] <= cap && s_len[1] <= cap && s_len[2] <= cap;
     if (staged_ok) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int len = s_len[r];
-            const float4 *src = io.pt + s_start[r];
-            float4 *dst = stage + r * (cap + kStagePad);
-            for (int k = tid; k < len + kStagePad; k += kForceThreads) {
-                float4 q = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f); // sentinel: far away, matrix key 0
-                if (k < len) {
-                    q = __ldg(src + k);
-                    q.z = __int_as_float(__float_as_int(q.z) << kTabShift); // matrix key = byte offset of row `type`
-                }
-                dst[k] = q;
-            }
-        }
+        if (!valid) return;   // (in chunked mode, CTA-uniform, every thread is needed at the barriers)
+        mbar_wait(bar, 0);    // the three ranges have landed
     }
-    __syncthreads();
-    if (!valid && staged_ok) return; // in chunked mode (CTA-uniform) every thread is needed at the barriers
 
-    float vx = 0.f, vy = 0.f;
-    if (valid) io.self_vel(i, vx, vy);
+    const int cx0 = (cxy & 0xffff) >> g.ks, cy0 = cxy >> 16;
+    const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
+    const int fb = (cxy & 0xffff) + (cy0 + g.ly_shift) * g.nxk(); // own bin (interior lanes: no clamp needed)
     MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, self.type, 1.0f, 0u, 0u};
     M.init();
-    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
     const int chunk_cap = 3 * (cap + kStagePad) - kStagePad; // the whole staging area as one buffer
     float nvx, nvy;
+    auto walk = [&](auto &v) {
+        if (staged_ok) {
+            if (interior) traverse_staged(cell_end, g, self.x, self.y, fb, stage_addr, cap, s_start, v);
+        } else {
+            traverse_chunked(io, cell_end, g, interior, self.x, self.y, fb, stage, stage_addr, chunk_cap, s_start, s_len, v);
+        }
+        if (valid && !interior) traverse_global32(io, cell_end, g, P.wrap, si, self.x, self.y, cx0, cy0, v);
+    };
     if constexpr (FAST) {
         FastParticleLife32<kMatLaneTab> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
-        if (staged_ok)
-            traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, true, stage_addr, cap, s_start, v);
-        else
-            traverse_chunked(io, cell_end, g, P.wrap, valid, si, self.x, self.y, cxy, stage, stage_addr, chunk_cap, s_start, s_len, v);
+        walk(v);
         nvx = fmaf(P.fast_k, v.ax, vx * P.mu);
         nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
     } else {
         LiteralForce<float, KIND, kMatLaneTab> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
-        if (staged_ok)
-            traverse_staged(io, cell_end, g, P.wrap, si, self.x, self.y, cxy, true, stage_addr, cap, s_start, v);
-        else
-            traverse_chunked(io, cell_end, g, P.wrap, valid, si, self.x, self.y, cxy, stage, stage_addr, chunk_cap, s_start, s_len, v);
+        walk(v);
         v.finish(nvx, nvy);
     }
     if (!valid) return;
@@ -812,16 +869,16 @@ __global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 i
         nx_ = range_clamp(nx_);
         ny_ = range_clamp(ny_);
     }
-    io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
-    nb.add(i, nx_, ny_, nvx, nvy, self.type, self.id, g);
+    const int o = io.out_slot(i);
+    io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
+    nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, g);
 }
 
 inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted,
-                                         const ForceParams<float> &P, const float *gM, int kind, int cap, NextBin nbin,
+                                         const ForceParams<float> &P, int nblocks, const float *gM, int kind, int cap, NextBin nbin,
                                          cudaStream_t stream)
 {
-    if (P.n == 0) return cudaSuccess;
-    const int nb = (P.n + kForceThreads - 1) / kForceThreads;
+    if (nblocks <= 0) return cudaSuccess;
     const size_t sbytes = (size_t)3 * (cap + kStagePad) * 16 + (size_t)P.m * kForceThreads * 4;
 #define PLIFE_LAUNCH_STAGED(KIND, FAST)                                                                          \
     do {                                                                                                         \
@@ -830,7 +887,7 @@ inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_en
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);  \
             if (e != cudaSuccess) return e;                                                                      \
         }                                                                                                        \
-        kfn<<<nb, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, P, gM, cap, nbin);                 \
+        kfn<<<nblocks, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, P, gM, cap, nbin);            \
     } while (0)
     switch (kind) {
     case PLIFE_ACC_PARTICLE_LIFE: PLIFE_LAUNCH_STAGED(PLIFE_ACC_PARTICLE_LIFE, true); break;
@@ -842,190 +899,6 @@ inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_en
     default: return cudaErrorInvalidValue;
     }
 #undef PLIFE_LAUNCH_STAGED
-    return cudaGetLastError();
-}
-
-// ---- v3: two targets per lane (fp32, accelerator kind 0) -----------------------------------
-// The v2 inner loop is limited by issue slots AND the L1 data pipe (LDS.128 + LDS.32 per pair
-// evaluation, profiles/r1_force_kernel.md).  Targets of one cell share their candidate list, so a
-// lane that owns TWO targets of the same cell amortises the candidate load, the address arithmetic
-// and the loop control over two pair evaluations, and fetches both matrix coefficients with one
-// conflict-free LDS.64 from a [type][thread] table of float2.  Pairs never straddle cells: the scan
-// produces pair_start[cell] = prefix of ceil(count/2) and the gather registers the even-ranked particle
-// of every pair (pair_first); an odd cell leaves the second slot of its last lane idle.
-constexpr int kPairShift = 10; // lane-table row stride: kForceThreads * sizeof(float2)
-
-__device__ __forceinline__ float2 lds64(uint32_t a)
-{
-    float2 v;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-    return v;
-}
-
-struct FastPair32 {
-    float ax0, ay0, ax1, ay1;
-    float x0, y0, x1, y1;
-    float b, d0, h;
-    uint32_t row; // shared address of tab2[0][thread]
-    __device__ __forceinline__ void one(float a, float dx, float dy, float &ax, float &ay) const
-    {
-        float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
-        float rinv = rsqrt_fast(d2);
-        float d = d2 * rinv;
-        float rep = fminf(d - b, 0.0f);
-        float att = fmaxf(h - fabsf(d - d0), 0.0f);
-        float g = fmaf(a, att, rep) * rinv;
-        ax = fmaf(g, dx, ax);
-        ay = fmaf(g, dy, ay);
-    }
-    __device__ __forceinline__ void cand(const float4 &q)
-    {
-        const float2 a = lds64(row + (uint32_t)__float_as_int(q.z));
-        one(a.x, q.x - x0, q.y - y0, ax0, ay0);
-        one(a.y, q.x - x1, q.y - y1, ax1, ay1);
-    }
-};
-
-__global__ void __launch_bounds__(kForceThreads) force_kernel_pairs(IOF32 io, const int32_t *__restrict__ cell_end,
-                                                                   const int32_t *__restrict__ cell_sorted,
-                                                                   const int32_t *__restrict__ pair_first,
-                                                                   const int32_t *__restrict__ npairs, ForceParams<float> P,
-                                                                   const float *__restrict__ gM, int cap, NextBin nb)
-{
-    static_assert(kForceThreads * 8 == (1 << kPairShift), "pair-table row stride");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                                 // [3][cap + kStagePad]
-    float2 *tab2 = reinterpret_cast<float2 *>(smem_raw + (size_t)3 * (cap + kStagePad) * 16); // [m][kForceThreads]
-    __shared__ int s_cell[2], s_start[3], s_len[3];
-
-    const int np = __ldg(npairs);
-    if ((int)(blockIdx.x * kForceThreads) >= np) return; // whole CTA beyond the last pair
-    const int tid = threadIdx.x;
-    const int t = blockIdx.x * kForceThreads + tid;
-    const bool valid = t < np;
-    const Grid g = P.g;
-    Cand<float> s0{0.f, 0.f, 0, 0u}, s1{0.f, 0.f, 0, 0u};
-    int i0 = 0, cxy = 0, cxy1 = 0;
-    bool has2 = false;
-    if (valid) {
-        i0 = __ldg(pair_first + t);
-        cxy = __ldg(cell_sorted + i0);
-        const int c = container_of(cxy, g);
-        has2 = P.first + i0 + 1 < __ldg(cell_end + c);
-        s0 = io.cand(P.first + i0);
-        s1 = has2 ? io.cand(P.first + i0 + 1) : s0;
-        // same container, but the un-clamped cell coords can differ in the fat last cell (x or y == nx*rmax..1)
-        cxy1 = has2 ? __ldg(cell_sorted + i0 + 1) : cxy;
-        if (tid == 0) s_cell[0] = c;
-        if (tid == kForceThreads - 1 || t == np - 1) s_cell[1] = c;
-    }
-    {
-        const float *r0 = gM + s0.type * P.m, *r1 = gM + s1.type * P.m;
-        for (int k = 0; k < P.m; ++k) tab2[k * kForceThreads + tid] = make_float2(__ldg(r0 + k) * P.fast_a_scale, __ldg(r1 + k) * P.fast_a_scale);
-    }
-    __syncthreads();
-    if (tid < 3) {
-        const int ncell = g.nx * g.nly;
-        int lo = s_cell[0] + (tid - 1) * g.nx - 1;
-        int hi = s_cell[1] + (tid - 1) * g.nx + 1;
-        lo = max(lo, 0);
-        hi = min(hi, ncell - 1);
-        int start = 0, len = 0;
-        if (lo <= hi) {
-            start = __ldg(cell_end + lo - 1);
-            len = __ldg(cell_end + hi) - start;
-        }
-        s_start[tid] = start;
-        s_len[tid] = len;
-    }
-    __syncthreads();
-    const bool staged_ok = s_len[0] <= cap && s_len[1] <= cap && s_len[2] <= cap;
-    if (staged_ok) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int len = s_len[r];
-            const float4 *src = io.pt + s_start[r];
-            float4 *dst = stage + r * (cap + kStagePad);
-            for (int k = tid; k < len + kStagePad; k += kForceThreads) {
-                float4 q = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
-                if (k < len) {
-                    q = __ldg(src + k);
-                    q.z = __int_as_float(__float_as_int(q.z) << kPairShift);
-                }
-                dst[k] = q;
-            }
-        }
-    }
-    __syncthreads();
-    if (!valid) return;
-
-    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
-    const uint32_t row = (uint32_t)__cvta_generic_to_shared(tab2 + tid);
-    const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
-    const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2 && cxy1 == cxy;
-    float ax0, ay0, ax1, ay1;
-    if (interior && staged_ok) {
-        FastPair32 v{0.f, 0.f, 0.f, 0.f, s0.x, s0.y, s1.x, s1.y, P.fast_b, P.fast_d0, P.fast_h, row};
-        const int base0 = (cy0 + g.ly_shift - 1) * g.nx + cx0;
-#pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
-            const int base = base0 + r * g.nx;
-            const int s = __ldg(cell_end + base - 2);
-            const int e = __ldg(cell_end + base + 1);
-            uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s - s_start[r]) * 16u;
-            const uint32_t a1 = a + (uint32_t)(e - s) * 16u;
-            for (; a < a1; a += 64u) { // 4 candidates per trip, padded like v2
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v.cand(lds128(a + 16u * u));
-            }
-        }
-        ax0 = v.ax0; ay0 = v.ay0; ax1 = v.ax1; ay1 = v.ay1;
-    } else { // seam lanes / oversized ranges: the literal walk, one target after the other
-        MatrixView<float, kMatLaneTab> M{nullptr, nullptr, P.m, 0, 1.0f, row, 0u};
-        FastParticleLife32<kMatLaneTab> v0{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
-        traverse_staged<kPairShift>(io, cell_end, g, P.wrap, P.first + i0, s0.x, s0.y, cxy, false, stage_addr, cap, s_start, v0);
-        ax0 = v0.ax; ay0 = v0.ay;
-        ax1 = ay1 = 0.f;
-        if (has2) {
-            M.row = row + 4u;
-            FastParticleLife32<kMatLaneTab> v1{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
-            traverse_staged<kPairShift>(io, cell_end, g, P.wrap, P.first + i0 + 1, s1.x, s1.y, cxy1, false, stage_addr, cap, s_start, v1);
-            ax1 = v1.ax; ay1 = v1.ay;
-        }
-    }
-    auto finish = [&](int i, const Cand<float> &self, float ax, float ay) {
-        float vx, vy;
-        io.self_vel(i, vx, vy);
-        const float nvx = fmaf(P.fast_k, ax, vx * P.mu);
-        const float nvy = fmaf(P.fast_k, ay, vy * P.mu);
-        float nx_ = fmaf(nvx, P.dt, self.x);
-        float ny_ = fmaf(nvy, P.dt, self.y);
-        if (P.wrap) {
-            nx_ = range_wrap(nx_);
-            ny_ = range_wrap(ny_);
-        } else {
-            nx_ = range_clamp(nx_);
-            ny_ = range_clamp(ny_);
-        }
-        io.store(i, nx_, ny_, nvx, nvy, self.type, self.id);
-        nb.add(i, nx_, ny_, nvx, nvy, self.type, self.id, g);
-    };
-    finish(i0, s0, ax0, ay0);
-    if (has2) finish(i0 + 1, s1, ax1, ay1);
-}
-
-inline cudaError_t launch_force_pairs(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted, const int32_t *pair_first,
-                                      const int32_t *npairs, int max_pairs, const ForceParams<float> &P, const float *gM, int cap,
-                                      NextBin nbin, cudaStream_t stream)
-{
-    if (P.n == 0) return cudaSuccess;
-    const int nb = (max_pairs + kForceThreads - 1) / kForceThreads;
-    const size_t sbytes = (size_t)3 * (cap + kStagePad) * 16 + (size_t)P.m * kForceThreads * 8;
-    if (sbytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(force_kernel_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
-        if (e != cudaSuccess) return e;
-    }
-    force_kernel_pairs<<<nb, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, pair_first, npairs, P, gM, cap, nbin);
     return cudaGetLastError();
 }
 
@@ -1043,8 +916,9 @@ __global__ void __launch_bounds__(kForceThreads) neighbors_kernel(IO io, const i
     const Cand<R> self = io.cand(P.first + i);
     NeighborVisitor<R> v{{0, 0ull}, P.r2};
     traverse(io, cell_end, P.g, P.wrap, P.first + i, self.x, self.y, __ldg(cell_sorted + i), v);
-    cnt[i] = v.d.count;
-    hash[i] = v.d.hash;
+    const int o = io.out_slot(i); // reported in the reference's particle order
+    cnt[o] = v.d.count;
+    hash[o] = v.d.hash;
 }
 
 template <typename IO>
@@ -1055,9 +929,11 @@ __global__ void __launch_bounds__(kForceThreads) pair_count_kernel(IO io, const 
 {
     using R = typename IO::R;
     __shared__ unsigned long long sh[kForceThreads / 32];
-    const int i = blockIdx.x * kForceThreads + threadIdx.x;
+    int i0 = 0, lim = 0;
+    cta_targets(P, i0, lim);
+    const int i = i0 + threadIdx.x;
     unsigned long long c = 0;
-    if (i < P.n) {
+    if (i < lim) {
         const Cand<R> self = io.cand(P.first + i);
         PairCountVisitor<R> v{P.first + i, 0ull};
         traverse(io, cell_end, P.g, P.wrap, P.first + i, self.x, self.y, __ldg(cell_sorted + i), v);
@@ -1077,12 +953,12 @@ __global__ void __launch_bounds__(kForceThreads) pair_count_kernel(IO io, const 
 // dispatch over accelerator kind / matrix placement
 template <typename IO, bool FAST_OK>
 cudaError_t dispatch_force(const IO &io, const int32_t *cell_end, const int32_t *cell_sorted,
-                           const ForceParams<typename IO::R> &P, const typename IO::R *gMt, int kind, NextBin nbin,
+                           const ForceParams<typename IO::R> &P, int nblocks, const typename IO::R *gMt, int kind, NextBin nbin,
                            cudaStream_t stream)
 {
     using R = typename IO::R;
-    if (P.n == 0) return cudaSuccess;
-    const int nb = (P.n + kForceThreads - 1) / kForceThreads;
+    if (nblocks <= 0) return cudaSuccess;
+    const int nb = nblocks;
     const bool smem = P.use_smem_matrix != 0;
     const size_t sbytes = smem ? sizeof(R) * (size_t)P.m * P.m : 0;
 #define PLIFE_LAUNCH(KIND, SM, FAST)                                                                            \

@@ -50,6 +50,9 @@ int cuda_fail(plife_handle *h, cudaError_t e, const char *what)
         if (e_ != cudaSuccess) return cuda_fail(h, e_, "cudaSetDevice");              \
     } while (0)
 
+constexpr int64_t kMaxCells = (int64_t)1 << 28;
+constexpr int kScanTile = 4096; // must match cells.cu
+
 template <typename T>
 cudaError_t dev_alloc(T **p, size_t count)
 {
@@ -72,8 +75,8 @@ void free_state(plife_handle *h)
     cudaFree(h->d_cell_sorted);
     cudaFree(h->d_src_sorted);
     cudaFree(h->d_perm);
-    cudaFree(h->d_pair_first);
-    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_pair_first = nullptr;
+    cudaFree(h->d_ref_sorted);
+    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_ref_sorted = nullptr;
     h->cap = 0;
     h->prebinned = false;
 }
@@ -101,7 +104,7 @@ int ensure_capacity(plife_handle *h, int64_t n)
     CU(h, dev_alloc(&h->d_cell_sorted, c));
     CU(h, dev_alloc(&h->d_src_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
-    CU(h, dev_alloc(&h->d_pair_first, c));
+    CU(h, dev_alloc(&h->d_ref_sorted, c));
     h->cap = n;
     return PLIFE_OK;
 }
@@ -155,21 +158,19 @@ int grow_preserve(plife_handle *h, int64_t cap)
     cudaFree(h->d_cell_sorted);
     cudaFree(h->d_src_sorted);
     cudaFree(h->d_perm);
-    cudaFree(h->d_pair_first);
-    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_pair_first = nullptr;
+    cudaFree(h->d_ref_sorted);
+    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_ref_sorted = nullptr;
     CU(h, dev_alloc(&h->d_cell, c));
     CU(h, dev_alloc(&h->d_cell_sorted, c));
     CU(h, dev_alloc(&h->d_src_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
-    CU(h, dev_alloc(&h->d_pair_first, c));
+    CU(h, dev_alloc(&h->d_ref_sorted, c));
     h->cap = cap;
     h->prebinned = false;
     h->has_sorted = false;
     return PLIFE_OK;
 }
 
-constexpr int64_t kMaxCells = (int64_t)1 << 28;
-constexpr int kScanTile = 4096; // must match cells.cu
 
 int ensure_cells(plife_handle *h, int64_t ncell)
 {
@@ -177,8 +178,7 @@ int ensure_cells(plife_handle *h, int64_t ncell)
     cudaFree(h->d_count);
     if (h->d_cell_end) cudaFree(h->d_cell_end - 4);
     cudaFree(h->d_tile_sums);
-    cudaFree(h->d_pair_start);
-    h->d_count = h->d_cell_end = h->d_pair_start = nullptr;
+    h->d_count = h->d_cell_end = nullptr;
     h->d_tile_sums = nullptr;
     h->cell_cap = 0;
     int64_t padded = (ncell + kScanTile - 1) / kScanTile * kScanTile;
@@ -189,12 +189,28 @@ int ensure_cells(plife_handle *h, int64_t ncell)
     CU(h, cudaMemsetAsync(raw, 0, 16, h->stream));
     h->d_cell_end = raw + 4;
     CU(h, cudaMalloc(&h->d_tile_sums, sizeof(unsigned long long) * (size_t)(padded / kScanTile)));
-    CU(h, dev_alloc(&h->d_pair_start, (size_t)padded));
     CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)padded, h->stream));
     h->cell_cap = padded;
     h->count_dirty = false;
     h->prebinned = false;
     return PLIFE_OK;
+}
+
+// Fine bins per cell along x (Grid::ks), fp32 handles only.  The gain is fewer candidates per target ((2 + 1/K) x 3
+// cell areas instead of 9); the cost is K times more bins to count and scan.  Worth it from a few particles per bin
+// on; the staged force kernel must be the one in use (m <= 32, >= 4 particles per cell).  PLIFE_BINS=K overrides.
+// Slab mode: every rank must pick the same K (the halo messages carry per-bin offsets), so the density estimate
+// comes from the halo capacity every rank was configured with, not from the rank's own particle count.
+int choose_ks(const plife_handle *h, const Grid &g)
+{
+    if (h->precision != PLIFE_F32 || (h->flags & PLIFE_FLAG_FORCE_V1) || h->m > 32) return 0;
+    double rho;
+    if (h->slab.on) rho = (double)h->slab.halo_cap / (1.5 * g.nx);
+    else rho = (double)h->n / ((double)g.nx * g.ny);
+    int ks = rho >= 12.0 ? 3 : (rho >= 6.0 ? 2 : (rho >= 4.0 ? 1 : 0));
+    if (h->bins_override >= 0) ks = h->bins_override;
+    while (ks > 0 && (((int64_t)(g.nx + 1) << ks) > 65535 || (((int64_t)g.nx * g.nly) << ks) > kMaxCells)) ks--;
+    return ks;
 }
 
 // B/Physics.java:82-85 with containerSize = rmax (:312)
@@ -213,6 +229,7 @@ int make_grid(plife_handle *h, Grid *g)
     g->nly = nx;
     g->rows_up = g->rows_dn = 0;
     g->ks = 0;
+    if (nx > 16384) return fail(h, PLIFE_ERR_INVALID, "rmax=%g gives nx=%d (max 16384)", rmax, nx);
     if (h->slab.on) {
         const int G = h->slab.world, r = h->slab.rank, ny = g->ny;
         if (ny < 4 * G) return fail(h, PLIFE_ERR_INVALID, "slab mode needs ny >= 4*world (ny=%d, world=%d)", ny, G);
@@ -225,6 +242,7 @@ int make_grid(plife_handle *h, Grid *g)
         g->rows_up = lo(up + 1) - lo(up);
         g->rows_dn = lo(dn + 1) - lo(dn);
     }
+    g->ks = choose_ks(h, *g);
     return PLIFE_OK;
 }
 
@@ -266,6 +284,10 @@ ForceParams<R> make_params(const plife_handle *h, const Grid &g, double dt)
     ForceParams<R> p{};
     p.n = (int)h->n;
     p.m = h->m;
+    p.n_dev = h->slab.on && h->slab.counts ? &h->slab.counts->n : nullptr;
+    p.tr = nullptr;
+    p.bin_lo = 0;
+    p.bin_hi = g.nxk() * g.nly - 1;
     p.first = h->slab.on ? (int)h->slab.halo_cap : 0;
     p.g = g;
     p.wrap = s.wrap ? 1 : 0;
@@ -324,13 +346,17 @@ int resolve_timings(plife_handle *h)
 // makeContainers (B/Physics.java:309-354): state buffer cur -> sorted into cur^1
 int sort_current(plife_handle *h, const Grid &g, StepTimer *tm, bool mark_gather_end = true)
 {
-    int rc = ensure_cells(h, (int64_t)g.nx * g.nly);
+    int rc = ensure_cells(h, (int64_t)g.nxk() * g.nly);
     if (rc) return rc;
     if (tm) CU(h, tm->mark(0));
     // the previous force pass already binned its output for this grid: skip K_BIN
-    const bool reuse = h->prebinned && h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs &&
+    const bool reuse = h->prebinned && h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs && h->prebinned_grid.ks == g.ks &&
                        h->prebinned_grid.row_lo == g.row_lo && h->prebinned_grid.row_hi == g.row_hi;
     if (!reuse) {
+        if (h->slab.on) { // binning from scratch is sized by the host: it needs the exact counts (rare: first step, rmax change)
+            rc = slab_refresh(h, true);
+            if (rc) return rc;
+        }
         if (h->count_dirty) CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)h->cell_cap, h->stream));
         CU(h, launch_bin(h, g));
     }
@@ -402,8 +428,8 @@ int slab_reset_capacity(plife_handle *h)
     free_state(h);
     return h->capacity_hint > 0 ? ensure_capacity(h, h->capacity_hint) : PLIFE_OK;
 }
-// Slab-mode profiling: event 4 is recorded right before the force kernel, so the K_GATHER bucket also holds the halo
-// pack / push / wait / unpack kernels that run between the gather and the force pass; K_FORCE is the kernel alone.
+// Slab-mode profiling: event 4 is recorded right before the first force launch, so the K_GATHER bucket also holds the
+// halo pack; K_FORCE spans both force launches and the halo wait + unpack between them.
 int slab_sort(plife_handle *h, const Grid &g)
 {
     int rc = sync_matrix(h);
@@ -414,13 +440,26 @@ int slab_sort(plife_handle *h, const Grid &g)
     h->slab_timing_on = tm.on && rc == PLIFE_OK;
     return rc;
 }
-cudaError_t slab_force(plife_handle *h, const Grid &g, double dt)
+// One of the two force launches of a slab step: targets = the device-resident ranges d_tr[0..3], staging clamped to
+// the bins [bin_lo, bin_hi] (the interior launch must not touch the ghost rows: they arrive later).
+cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_tr, int nblocks, int bin_lo, int bin_hi, bool first_part,
+                       bool last_part)
 {
     StepTimer tm(h);
     tm.t = h->slab_timing;
     tm.on = h->slab_timing_on;
-    cudaError_t e = tm.mark(4);
-    if (e == cudaSuccess) e = launch_force_f32(h, make_params<float>(h, g, dt));
+    cudaError_t e = cudaSuccess;
+    if (first_part) e = tm.mark(4);
+    ForceParams<float> p = make_params<float>(h, g, dt);
+    p.tr = d_tr;
+    p.bin_lo = bin_lo;
+    p.bin_hi = bin_hi;
+    if (e == cudaSuccess) e = launch_force_f32_part(h, p, nblocks);
+    if (!last_part) {
+        h->slab_timing = tm.t;
+        return e;
+    }
+    if (e == cudaSuccess) launch_force_f32_done(h);
     if (e == cudaSuccess) e = tm.mark(PLIFE_K_COUNT);
     if (tm.on && e == cudaSuccess) {
         h->pending.push_back(tm.t);
@@ -459,6 +498,7 @@ int plife_create(const plife_config *cfg, plife_handle **out)
     if (!cfg || !out) return PLIFE_ERR_INVALID;
     *out = nullptr;
     if (cfg->precision != PLIFE_F32 && cfg->precision != PLIFE_F64) return PLIFE_ERR_INVALID;
+    if (cfg->bins != 0 && cfg->bins != 1 && cfg->bins != 2 && cfg->bins != 4 && cfg->bins != 8) return PLIFE_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
@@ -488,6 +528,12 @@ int plife_create(const plife_config *cfg, plife_handle **out)
     cudaMemset(h->d_scalar, 0, (8 + 256) * sizeof(unsigned long long));
     h->d_hist = h->d_scalar + 8;
     h->capacity_hint = cfg->capacity;
+    {   // fine bins per cell along x: plife_config.bins, or the environment (for experiments), else from the density
+        int k = cfg->bins;
+        if (k == 0)
+            if (const char *ev = getenv("PLIFE_BINS")) k = atoi(ev);
+        if (k == 1 || k == 2 || k == 4 || k == 8) h->bins_override = k == 1 ? 0 : (k == 2 ? 1 : (k == 4 ? 2 : 3));
+    }
     if (cfg->capacity > 0) {
         int rc = ensure_capacity(h, cfg->capacity);
         if (rc) {
@@ -511,7 +557,6 @@ int plife_destroy(plife_handle *h)
     cudaFree(h->d_count);
     if (h->d_cell_end) cudaFree(h->d_cell_end - 4);
     cudaFree(h->d_tile_sums);
-    cudaFree(h->d_pair_start);
     cudaFree(h->d_matrix_t);
     cudaFree(h->d_snap);
     if (h->snap_init) {
@@ -666,14 +711,15 @@ int plife_upload(plife_handle *h, int64_t n, const double *pos_xy, const double 
     h->slab.k_below = h->slab.k_above = 0;
     h->max_type = max_type;
     h->next_id = id ? (n ? max_id + 1 : 0) : (uint32_t)n;
-    return PLIFE_OK;
+    return slab_set_counts(h);
 }
 
 int plife_download(plife_handle *h, double *pos_xy, double *vel_xy, int32_t *type, uint32_t *id)
 {
     CHECK_HANDLE(h);
-    int64_t n = h->n_phys;
     CU(h, cudaStreamSynchronize(h->stream));
+    if (int rcs = slab_refresh(h, true)) return rcs;
+    int64_t n = h->n_phys;
     if (n == 0) return PLIFE_OK;
     if (h->slab.on && h->slab.phase != PLIFE_SLAB_SORT) return fail(h, PLIFE_ERR_STATE, "download between slab phases");
     if (h->precision == PLIFE_F32) {
@@ -717,6 +763,7 @@ int plife_download(plife_handle *h, double *pos_xy, double *vel_xy, int32_t *typ
 int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type)
 {
     CHECK_HANDLE(h);
+    if (int rcs = slab_refresh(h, true)) return rcs;
     int64_t n = h->n;
     if (n == 0) return PLIFE_OK;
     if (h->snap_cap < n) { // sized by the handle's capacity: in slab mode n changes every step
@@ -744,6 +791,7 @@ int plife_download_f32(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *t
 static int snapshot_async_impl(plife_handle *h, float *pos_xy, float *vel_xy, int32_t *type, uint8_t *type8)
 {
     CHECK_HANDLE(h);
+    if (int rcs = slab_refresh(h, true)) return rcs; // slab mode: the copy sizes need the exact count
     const int64_t n = h->n;
     if (n == 0) return PLIFE_OK;
     if (!h->snap_init) {
@@ -831,7 +879,7 @@ int plife_init_uniform(plife_handle *h, int64_t n, uint64_t seed)
         h->slab.k_below = h->slab.k_above = 0;
         h->slab.phase = PLIFE_SLAB_SORT;
         h->max_type = kept > 0 ? h->m - 1 : -1;
-        return PLIFE_OK;
+        return slab_set_counts(h);
     }
     int rc = ensure_capacity(h, n);
     if (rc) return rc;
@@ -881,15 +929,24 @@ int plife_sync(plife_handle *h)
 {
     CHECK_HANDLE(h);
     CU(h, cudaStreamSynchronize(h->stream));
-    return PLIFE_OK;
+    return slab_refresh(h, true); // slab mode: errors the device found in the queued steps surface here
 }
 
-int64_t plife_count(const plife_handle *h) { return h ? h->n : PLIFE_ERR_INVALID; }
+int64_t plife_count(const plife_handle *h)
+{
+    if (!h) return PLIFE_ERR_INVALID;
+    if (h->slab.on && h->slab.counts && !h->poisoned) { // the count lives on the device: drain the queued steps and read it
+        plife_handle *m = const_cast<plife_handle *>(h);
+        if (cudaSetDevice(m->device) == cudaSuccess) slab_refresh(m, true);
+    }
+    return h->n;
+}
 
 int plife_type_histogram(plife_handle *h, int64_t *out_m)
 {
     CHECK_HANDLE(h);
     if (!out_m) return fail(h, PLIFE_ERR_INVALID, "out is NULL");
+    if (int rcs = slab_refresh(h, true)) return rcs;
     unsigned long long *d_hist = h->d_hist; // 256 counters, allocated with the handle
     cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256, h->stream);
     if (e == cudaSuccess) e = launch_type_histogram(h, d_hist);
@@ -916,8 +973,15 @@ int plife_get_containers(plife_handle *h, int32_t *out, int64_t capacity)
     if (!h->has_sorted) return fail(h, PLIFE_ERR_STATE, "no step has run since the last upload");
     int64_t ncell = (int64_t)h->last_grid.nx * h->last_grid.nly;
     if (!out || capacity < ncell) return fail(h, PLIFE_ERR_INVALID, "containers: capacity %lld < %lld", (long long)capacity, (long long)ncell);
-    CU(h, cudaMemcpyAsync(out, h->d_cell_end, sizeof(int32_t) * ncell, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    // the device array holds one END offset per fine bin; a cell's END offset is that of its last bin.  d_perm is
+    // scratch between steps and has at least one int per particle, which may be fewer than the cells
+    int32_t *d_tmp = nullptr;
+    CU(h, dev_alloc(&d_tmp, (size_t)ncell));
+    cudaError_t e = launch_containers(h, h->last_grid, d_tmp);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_tmp, sizeof(int32_t) * ncell, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) return cuda_fail(h, e, "containers");
     return PLIFE_OK;
 }
 
@@ -934,12 +998,18 @@ int plife_get_step_stats(plife_handle *h, plife_step_stats *out)
     auto pf = make_params<float>(h, g, 0.0);
     auto pd = make_params<double>(h, g, 0.0);
     pf.n = pd.n = (int)h->n_sorted;
+    pf.n_dev = nullptr;
+    if (h->slab.on && h->slab.d_tr) { // ... and the host may not know it: pack_halo left it on the device (d_tr[8..11] = {0, n, 0, 0})
+        pf.tr = h->slab.d_tr + 8;
+        pf.n = (int)h->cap;
+    }
     if (h->precision == PLIFE_F32) CU(h, launch_pair_count_f32(h, pf, h->d_scalar));
     else CU(h, launch_pair_count_f64(h, pd, h->d_scalar));
     unsigned long long total = 0;
     CU(h, cudaMemcpyAsync(&total, h->d_scalar, sizeof total, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    out->n = h->n_sorted;
+    if (int rcs = slab_refresh(h, true)) return rcs;
+    out->n = h->slab.on ? h->n : h->n_sorted;
     out->nx = g.nx;
     out->ny = g.ny;
     out->pair_evals = (int64_t)total;
@@ -971,8 +1041,17 @@ int plife_debug_neighbors(plife_handle *h, int32_t *count, uint64_t *hash)
     cudaFree(d_cnt);
     cudaFree(d_hash);
     if (e != cudaSuccess) return cuda_fail(h, e, "debug neighbors");
-    // like makeContainers, the sort is visible: the sorted copy becomes the current state
-    h->cur ^= 1;
+    // like makeContainers, the sort is visible: the sorted copy becomes the current state.  fp32: the scratch is in
+    // compute order with shifted types and the velocities never moved: write the reference order back into the
+    // current buffers (records cur^1 -> cur, velocities cur -> cur^1 and swap those two)
+    if (h->precision == PLIFE_F32) {
+        CU(h, launch_apply_sort_f32(h));
+        float2 *t = h->s32[0].vel;
+        h->s32[0].vel = h->s32[1].vel;
+        h->s32[1].vel = t;
+    } else {
+        h->cur ^= 1;
+    }
     h->has_sorted = false;
     h->prebinned = false;
     h->last_grid = g;

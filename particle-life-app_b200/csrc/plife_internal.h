@@ -13,6 +13,28 @@
 
 namespace plife {
 
+// fp32 compute-order records carry their type shifted left by kTypeShift: type << 9 is the byte offset of row `type` of
+// the force kernel's per-lane matrix table (128 threads x 4 bytes per row), so staging candidates is a plain copy.
+constexpr int kTypeShift = 9;
+
+// A count the host may not know when it queues a kernel: the host value, or (slab mode) a device-resident one.
+struct DevInt {
+    int v;
+    const int *dev;
+    __device__ __forceinline__ int get() const { return dev ? *dev : v; }
+};
+
+// Slab mode: particle counts of this rank, kept in device memory so that a step needs no host round trip
+// (slab.cu: finish kernel).  The pre-sort array is [residents 0..n_old) | arrivals from below | arrivals from above].
+struct SlabCounts {
+    int n;        // live particles
+    int n_phys;   // physical length of the pre-sort array (dead slots included)
+    int n_old, k_below, k_above;
+    int err;      // sticky error bits (kSlabErr*)
+    int sent_dn, sent_up;
+    unsigned long long seq; // last finished step
+};
+
 // Uniform grid of the reference: cell edge = rmax, nx = ny = floor(1/rmax)
 // (B/Physics.java:82-85, :312-313).  cs stays double: cell assignment is done
 // with IEEE double division in every precision mode.
@@ -79,6 +101,9 @@ __device__ __forceinline__ void cell_span(const int32_t *__restrict__ cell_end, 
 template <typename R>
 struct ForceParams {
     int n, m;
+    const int *n_dev; // slab mode: device-resident particle count (overrides n), or nullptr
+    const int *tr;    // slab mode: device-resident target ranges {s0, e0, s1, e1} of this launch, or nullptr: [0, n)
+    int bin_lo, bin_hi; // bins a CTA may stage (the interior launch of a slab step must keep off the ghost rows)
     int first; // sorted-array index of target 0 (ghost-below capacity in slab mode, else 0)
     Grid g;
     int wrap;
@@ -121,7 +146,7 @@ struct SlabState {
     int64_t halo_cap = 0, mig_cap = 0; // particles per halo row message / per migration message
     // exchange buffers (device pointers handed in by the host, 16-byte records); [0] = down, [1] = up
     float4 *halo_send[2]{}, *halo_recv[2]{}, *mig_send[2]{}, *mig_recv[2]{};
-    int64_t n_old = 0, k_below = 0, k_above = 0; // layout of the pre-sort array: residents | from below | from above
+    int64_t n_old = 0, k_below = 0, k_above = 0; // host copy (lagging): layout of the pre-sort array: residents | from below | from above
     int phase = 0;                  // next phase expected by plife_slab_phase
     // peer exchange (library-owned buffers, CUDA IPC)
     bool peer_mode = false;
@@ -132,13 +157,23 @@ struct SlabState {
     unsigned long long spin_ns = 30000000000ull; // device-side wait limit for a neighbour's message (PLIFE_SLAB_TIMEOUT_MS)
     float4 *peer_base[2]{};         // the neighbours' xbuf mapped into this process / device
     bool peer_ipc[2]{};
-    volatile int4 *h_hdr = nullptr; // mapped pinned: 4 migration headers + error word, written by finish_headers
+    // device-resident counts: a step needs no host synchronisation
+    SlabCounts *counts = nullptr;        // device
+    int *d_tr = nullptr;                 // device: target ranges of the force launches (pack_halo writes them), 12 ints
+    volatile SlabCounts *h_ring = nullptr; // mapped pinned: the counts after each of the last 8 steps (written by slab_finish)
+    cudaEvent_t step_done[4]{};          // recorded after each step's FINISH: bounds how far the host runs ahead
+    unsigned long long seq_known = 0;    // newest step whose counts the host has read
+    int64_t n_bound = 0;                 // upper bound of n_phys the host sizes grids with
+    int64_t max_arrivals = 0;            // largest number of arrivals seen in one step
+    int err_pending = 0, err_seen = 0;   // device error bits read from the ring / already reported
 };
 } // namespace plife
 
 struct plife_handle;
 namespace plife {
 void slab_destroy(plife_handle *h);
+int slab_refresh(plife_handle *h, bool block); // host view of the device-resident counts (block: drain the stream first)
+int slab_set_counts(plife_handle *h);          // host-known counts -> device (after upload / init)
 }
 
 struct plife_handle {
@@ -166,6 +201,7 @@ struct plife_handle {
     int64_t capacity_hint = 0;
     plife::SlabState slab;
     int max_type = -1;
+    int bins_override = -1; // PLIFE_BINS: log2 of the fine bins per cell, or -1: chosen from the density
     uint32_t next_id = 0; // id given to the next appended particle
     int cur = 0; // index of the buffer holding the current state
     plife::StateF32 s32[2]{};
@@ -173,9 +209,8 @@ struct plife_handle {
     int32_t *d_cell = nullptr;        // packed cell coords of particle i (pre-sort order)
     int32_t *d_cell_sorted = nullptr; // the same, permuted into sorted order
     int32_t *d_src_sorted = nullptr;  // fp32: pre-sort slot of every sorted particle (velocities are read through it)
+    int32_t *d_ref_sorted = nullptr;  // fp32: slot of every sorted particle in the reference's order (where its result is written)
     int32_t *d_perm = nullptr; // source index of sorted slot d
-    int32_t *d_pair_first = nullptr; // first target of every target pair (two-targets-per-lane force kernel)
-    int32_t *d_pair_start = nullptr; // first pair of every cell
     void *d_snap = nullptr;    // snapshot staging (download_f32)
     int64_t snap_cap = 0;
     // asynchronous, double-buffered snapshot (display-time handoff that overlaps the next steps)
@@ -224,6 +259,8 @@ cudaError_t launch_bin(plife_handle *h, const Grid &g);
 cudaError_t launch_scan(plife_handle *h, const Grid &g);
 cudaError_t launch_scatter(plife_handle *h, const Grid &g);
 cudaError_t launch_gather(plife_handle *h, const Grid &g);
+cudaError_t launch_apply_sort_f32(plife_handle *h);
+cudaError_t launch_containers(plife_handle *h, const Grid &g, int32_t *d_out);
 cudaError_t launch_type_histogram(plife_handle *h, unsigned long long *d_hist);
 cudaError_t launch_init_uniform(plife_handle *h, int64_t n, uint64_t seed);
 cudaError_t launch_init_uniform_owned(plife_handle *h, int64_t n_global, uint64_t seed, const Grid &g, int *d_counter);
@@ -231,6 +268,8 @@ cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32
 
 // force_f32.cu / force_f64.cu
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p);
+cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks); // slab mode: one of the two launches
+void launch_force_f32_done(plife_handle *h);                                                  // ... then swap the velocity buffers
 cudaError_t launch_force_f64(plife_handle *h, const ForceParams<double> &p);
 cudaError_t launch_neighbors_f32(plife_handle *h, const ForceParams<float> &p, int32_t *cnt, unsigned long long *hash);
 cudaError_t launch_neighbors_f64(plife_handle *h, const ForceParams<double> &p, int32_t *cnt, unsigned long long *hash);

@@ -2,24 +2,26 @@
 // grid rows [g*ny/G, (g+1)*ny/G).  The sorted order is row-major by cell, so a slab is one contiguous
 // index range and its first / last rows are contiguous sub-ranges: packing a halo is a plain copy.
 //
-// Per step (host drives the three phases and exchanges the messages between them, e.g. with
-// torch.distributed / NCCL send-recv; see plife/slab.py):
+// Per step, all on the handle's stream and WITHOUT a host synchronisation - the particle counts of a rank change
+// every step (migration) and live in device memory (SlabCounts); the host sizes grids by an upper bound and reads
+// the true counts back lazily, a few steps late, from a ring in mapped pinned memory:
 //   phase SORT    cell-list build of the owned particles; pack first and last owned row into the halo
-//                 messages {count | per-cell END offsets of the row | 16-byte particle records}
-//   (exchange)    halo_send[0] -> down neighbour's halo_recv[1], halo_send[1] -> up neighbour's halo_recv[0]
-//   phase FORCE   place the ghost rows around the owned block of the sorted array
-//                 [ghost below | owned | ghost above], run the force/integrate kernel over the owned
-//                 particles; its epilogue bins the new positions and appends particles whose new row
-//                 belongs to a neighbour to the migration messages
-//   (exchange)    mig_send[0] -> down neighbour's mig_recv[1], mig_send[1] -> up neighbour's mig_recv[0]
-//   phase FINISH  append the arrivals (binning them), update the particle count
+//                 messages {count | per-bin END offsets of the row | 16-byte particle records} - peer exchange:
+//                 written straight into the neighbours' receive slots over NVLink, then a flag is raised
+//   phase FORCE   force/integrate over the INTERIOR rows (they need no ghost row: the halo is in flight
+//                 meanwhile); wait for the neighbours' halo flags and place the ghost rows around the owned block
+//                 [ghost below | owned | ghost above]; force/integrate over the first and last owned row.  The
+//                 epilogue bins the new positions and appends particles whose new row belongs to a neighbour to
+//                 the migration messages, which are then pushed to the neighbours
+//   phase FINISH  wait for the neighbours' migration messages, validate, compute the new counts on the device,
+//                 append the arrivals (binning them)
 //
 // Two ways to move the messages:
 //   external  the host exchanges caller-provided buffers between the phases (torch.distributed/NCCL);
 //   peer      (default) the library owns the buffers, ranks map each other's receive slots with CUDA IPC
 //             and the kernels push a message straight into the neighbour's slot over NVLink, then raise a
-//             flag (sequence number) there; the consumer's stream spins on its own flag in a 1-thread
-//             kernel.  Slots are double-buffered by step parity: a rank can only be one message ahead of
+//             flag (sequence number) there; consumers spin on their own flag (bounded by wall time).
+//             Slots are double-buffered by step parity: a rank can only be one message ahead of
 //             its neighbour (it waits for the neighbour's flag of step k before it produces step k+1), so
 //             the slot of step k+1 was consumed by the neighbour before its step-k flag was raised.
 //
@@ -39,13 +41,26 @@ namespace plife {
 int slab_make_grid(plife_handle *h, Grid *g);
 int slab_sort(plife_handle *h, const Grid &g);
 int slab_fail(plife_handle *h, int code, const char *msg);
-cudaError_t slab_force(plife_handle *h, const Grid &g, double dt);
+cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_tr, int nblocks, int bin_lo, int bin_hi, bool first_part,
+                       bool last_part);
 int slab_reset_capacity(plife_handle *h);
 } // namespace plife
 
 namespace {
 
 constexpr int kThreads = 256;
+
+// sticky error bits of SlabCounts::err
+enum {
+    kErrHalo = 1,      // halo row did not fit / grid or bin mismatch between ranks
+    kErrTimeout = 2,   // a neighbour's message did not arrive within the wait limit
+    kErrFar = 4,       // a particle crossed more than one slab in one step
+    kErrClosed = 8,    // a particle left through a closed boundary
+    kErrMigCap = 16,   // migration message overflow
+    kErrCapacity = 32, // arrivals exceed the particle capacity
+    kErrOwner = 64,    // sender and receiver disagree about ownership
+    kErrBound = 128,   // the host's grid-size bound was below the true particle count
+};
 
 __device__ __forceinline__ int offsets_records(int nx) { return (nx + 3) >> 2; }
 
@@ -57,8 +72,18 @@ __device__ __forceinline__ unsigned long long wall_ns()
     return t;
 }
 
-// dir 0: first owned row (local row 1) -> becomes the down neighbour's top ghost row
-// dir 1: last owned row (local row nly-2) -> becomes the up neighbour's bottom ghost row
+// spin until *flag >= seq; false on timeout
+__device__ __forceinline__ bool wait_flag(const volatile unsigned long long *flag, unsigned long long seq, unsigned long long spin_ns)
+{
+    const unsigned long long t0 = wall_ns();
+    while (*flag < seq) {
+        if (wall_ns() - t0 > spin_ns) return false;
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    return true;
+}
+
 // Completion signal of a multi-CTA producer: every CTA fences its (remote) writes and takes a ticket; the CTA that draws
 // the last one publishes `seq` in the consumer's flag and resets the ticket for the next step.
 __device__ __forceinline__ void signal_when_all_done(unsigned int *ticket, volatile unsigned long long *flag, unsigned long long seq,
@@ -76,31 +101,47 @@ __device__ __forceinline__ void signal_when_all_done(unsigned int *ticket, volat
     }
 }
 
+// dir 0: first owned row (local row 1) -> becomes the down neighbour's top ghost row
+// dir 1: last owned row (local row nly-2) -> becomes the up neighbour's bottom ghost row
 // `msg0/msg1` are where the two messages are written: the local send buffers (external exchange), or - peer exchange -
 // straight into the neighbours' receive slots over NVLink, followed by the flag (flag0/flag1 non-NULL).
+// Block (0,0) also resets this step's migration cursors and writes the target ranges of the two force launches:
+//   tr[0..3] = interior rows {s, e, 0, 0}      tr[4..7] = first and last owned row {0, s, e, n}     tr[8..11] = all
 __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__ pt_sorted, const int32_t *__restrict__ cell_end,
-                                                      Grid g, int halo_cap, float4 *__restrict__ msg0, float4 *__restrict__ msg1,
-                                                      float4 *__restrict__ mig0, float4 *__restrict__ mig1,
+                                                      Grid g, int halo_cap, int first, const SlabCounts *__restrict__ cnt,
+                                                      float4 *__restrict__ msg0, float4 *__restrict__ msg1,
+                                                      float4 *__restrict__ mig0, float4 *__restrict__ mig1, int *__restrict__ tr,
                                                       volatile unsigned long long *flag0, volatile unsigned long long *flag1,
                                                       unsigned int *tickets, unsigned long long seq)
 {
     const int dir = blockIdx.y;
     float4 *msg = dir ? msg1 : msg0;
     volatile unsigned long long *flag = dir ? flag1 : flag0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) (dir ? mig1 : mig0)[0] = make_float4(0.f, 0.f, 0.f, 0.f); // this step's migration cursor
+    const int nxk = g.nxk(); // the message carries one END offset per fine bin of the row
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        (dir ? mig1 : mig0)[0] = make_float4(0.f, 0.f, 0.f, 0.f); // this step's migration cursor
+        if (dir == 0) {
+            const int n = cnt->n;
+            const int e1 = __ldg(cell_end + 2 * nxk - 1) - first;           // end of the first owned row
+            const int sl = __ldg(cell_end + (g.nly - 2) * nxk - 1) - first; // start of the last owned row
+            tr[0] = e1; tr[1] = sl; tr[2] = 0; tr[3] = 0;
+            tr[4] = 0; tr[5] = e1; tr[6] = sl; tr[7] = n;
+            tr[8] = 0; tr[9] = n; tr[10] = 0; tr[11] = 0; // the whole sorted block (plife_get_step_stats)
+        }
+    }
     const int row = dir ? g.nly - 2 : 1;
-    const int start = __ldg(cell_end + row * g.nx - 1);
-    const int end = __ldg(cell_end + (row + 1) * g.nx - 1);
+    const int start = __ldg(cell_end + row * nxk - 1);
+    const int end = __ldg(cell_end + (row + 1) * nxk - 1);
     const int count = end - start;
-    const int noff = offsets_records(g.nx);
+    const int noff = offsets_records(nxk);
     const int t = blockIdx.x * kThreads + threadIdx.x;
     if (t == 0) {
-        int4 hd = make_int4(count <= halo_cap ? count : -count, g.nx, 0, 0);
+        int4 hd = make_int4(count <= halo_cap ? count : -count - 1, nxk, 0, 0);
         msg[0] = *reinterpret_cast<float4 *>(&hd);
     }
-    if (count <= halo_cap) { // else overflow: reported by the receiver and by phase FINISH
+    if (count <= halo_cap) { // else overflow: reported by the receiver
         int32_t *off = reinterpret_cast<int32_t *>(msg + 1);
-        for (int c = t; c < 4 * noff; c += gridDim.x * kThreads) off[c] = c < g.nx ? __ldg(cell_end + row * g.nx + c) - start : 0;
+        for (int c = t; c < 4 * noff; c += gridDim.x * kThreads) off[c] = c < nxk ? __ldg(cell_end + row * nxk + c) - start : 0;
         for (int k = t; k < count; k += gridDim.x * kThreads) msg[1 + noff + k] = __ldg(pt_sorted + start + k);
     }
     if (flag) signal_when_all_done(tickets + dir, flag, seq, gridDim.x);
@@ -109,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__
 // which 0: ghost row below (local row 0), right-aligned before the owned block at `first`
 // which 1: ghost row above (local row nly-1), placed after the owned block
 __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_sorted, int32_t *__restrict__ cell_end, Grid g,
-                                                        int first, int n, const float4 *msg0, const float4 *msg1, int *__restrict__ err,
+                                                        int first, SlabCounts *__restrict__ cnt, const float4 *msg0, const float4 *msg1,
                                                         const volatile unsigned long long *flag0, const volatile unsigned long long *flag1,
                                                         unsigned long long seq, unsigned long long spin_ns)
 {
@@ -122,108 +163,124 @@ __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_
     const volatile unsigned long long *flag = which ? flag1 : flag0;
     if (flag) {
         __shared__ int s_timeout;
-        if (threadIdx.x == 0) {
-            s_timeout = 0;
-            const unsigned long long t0 = wall_ns();
-            while (*flag < seq) {
-                if (wall_ns() - t0 > spin_ns) {
-                    s_timeout = 1;
-                    break;
-                }
-                __nanosleep(100);
-            }
-            __threadfence_system();
-        }
+        if (threadIdx.x == 0) s_timeout = wait_flag(flag, seq, spin_ns) ? 0 : 1;
         __syncthreads();
         if (s_timeout) {
-            if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(err, 1 << 16);
+            if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&cnt->err, kErrTimeout);
             return;
         }
     }
     const int4 hd = __ldcg(reinterpret_cast<const int4 *>(msg));
     const int t = blockIdx.x * kThreads + threadIdx.x;
-    if (hd.x < 0 || hd.y != g.nx) {
-        if (t == 0) atomicAdd(err, 1);
+    const int nxk = g.nxk();
+    if (hd.x < 0 || hd.y != nxk) { // overflow at the sender, or the ranks disagree about the grid / the bins per cell
+        if (t == 0) atomicOr(&cnt->err, kErrHalo);
         return;
     }
+    const int n = cnt->n;
     const int count = hd.x;
-    const int noff = offsets_records(g.nx);
+    const int noff = offsets_records(nxk);
     const int base = which ? first + n : first - count;
     const int row = which ? g.nly - 1 : 0;
     const int32_t *off = reinterpret_cast<const int32_t *>(msg + 1);
-    for (int c = t; c < g.nx; c += gridDim.x * kThreads) cell_end[row * g.nx + c] = base + __ldcg(off + c);
+    for (int c = t; c < nxk; c += gridDim.x * kThreads) cell_end[row * nxk + c] = base + __ldcg(off + c);
     if (which == 0 && t == 0) cell_end[-1] = base;
     for (int k = t; k < count; k += gridDim.x * kThreads) pt_sorted[base + k] = __ldcg(msg + 1 + noff + k);
 }
 
+// copy the two migration messages (their used records only) into the neighbours' receive slots; blockIdx.y = direction
+__global__ void __launch_bounds__(kThreads) push_mig(const float4 *__restrict__ local0, const float4 *__restrict__ local1,
+                                                     float4 *__restrict__ peer0, float4 *__restrict__ peer1, int cap,
+                                                     volatile unsigned long long *flag0, volatile unsigned long long *flag1,
+                                                     unsigned int *tickets, unsigned long long seq)
+{
+    const int dir = blockIdx.y;
+    const float4 *local = dir ? local1 : local0;
+    float4 *peer = dir ? peer1 : peer0;
+    if (!peer) return;
+    const int count = *reinterpret_cast<const int *>(local);
+    const int nrec = 1 + 2 * min(count, cap);
+    for (int k = blockIdx.x * kThreads + threadIdx.x; k < nrec; k += gridDim.x * kThreads) peer[k] = local[k];
+    signal_when_all_done(tickets + dir, dir ? flag1 : flag0, seq, gridDim.x);
+}
+
+// Phase FINISH, one thread: wait for the neighbours' migration messages (peer mode), validate the four headers, compute
+// the counts of the next step and publish them where the host can read them later without a synchronisation.
+__global__ void slab_finish(const volatile unsigned long long *f0, const volatile unsigned long long *f1, unsigned long long seq,
+                            SlabCounts *cnt, const float4 *ms0, const float4 *ms1, const float4 *mi0, const float4 *mi1,
+                            int has_dn, int has_up, int mig_cap, int cap, int bound, volatile SlabCounts *ring, unsigned long long spin_ns)
+{
+    if (threadIdx.x != 0) return;
+    int err = cnt->err;
+    if (f0 && !wait_flag(f0, seq, spin_ns)) err |= kErrTimeout;
+    if (f1 && !wait_flag(f1, seq, spin_ns)) err |= kErrTimeout;
+    const volatile int *s0 = reinterpret_cast<const volatile int *>(ms0), *s1 = reinterpret_cast<const volatile int *>(ms1);
+    const int sent_dn = s0[0], sent_up = s1[0];
+    if (s0[1] || s1[1]) err |= kErrFar;
+    if ((!has_dn && sent_dn) || (!has_up && sent_up)) err |= kErrClosed;
+    int k_below = 0, k_above = 0;
+    if (!(err & kErrTimeout)) {
+        if (has_dn && mi0) k_below = reinterpret_cast<const volatile int *>(mi0)[0];
+        if (has_up && mi1) k_above = reinterpret_cast<const volatile int *>(mi1)[0];
+    }
+    if (sent_dn > mig_cap || sent_up > mig_cap || k_below > mig_cap || k_above > mig_cap) {
+        err |= kErrMigCap;
+        k_below = min(k_below, mig_cap);
+        k_above = min(k_above, mig_cap);
+    }
+    const int L = cnt->n; // residents before this step (the force pass wrote slots [0, L))
+    if (L + k_below + k_above > cap) {
+        err |= kErrCapacity;
+        k_below = k_above = 0;
+    }
+    if (L > bound || cnt->n_phys > bound) err |= kErrBound;
+    SlabCounts c;
+    c.n_old = L;
+    c.k_below = k_below;
+    c.k_above = k_above;
+    c.n_phys = L + k_below + k_above;
+    c.n = L - min(sent_dn, mig_cap) - min(sent_up, mig_cap) + k_below + k_above;
+    c.err = err;
+    c.sent_dn = sent_dn;
+    c.sent_up = sent_up;
+    c.seq = seq;
+    *cnt = c;
+    volatile SlabCounts *r = ring + (seq & 7);
+    r->seq = 0;
+    __threadfence_system();
+    r->n = c.n; r->n_phys = c.n_phys; r->n_old = c.n_old; r->k_below = c.k_below; r->k_above = c.k_above;
+    r->err = c.err; r->sent_dn = c.sent_dn; r->sent_up = c.sent_up;
+    __threadfence_system();
+    r->seq = seq;
+    __threadfence_system();
+}
+
 // Arrivals: message records {x,y,type,id},{vx,vy,source slot,-}.  Each is placed at
 // base + (rank of its source slot among the arrivals of the same message): the sender appended them
-// with an atomic cursor, the rank restores the sender's array order.
-__global__ void __launch_bounds__(kThreads) append_arrivals(const float4 *__restrict__ msg, int k, int base, Grid g,
+// with an atomic cursor, the rank restores the sender's array order.  blockIdx.y = 0: from below, 1: from above.
+__global__ void __launch_bounds__(kThreads) append_arrivals(const float4 *msg0, const float4 *msg1, SlabCounts *__restrict__ cnt, Grid g,
                                                             float4 *__restrict__ pt, float2 *__restrict__ vel,
-                                                            int32_t *__restrict__ cell, int32_t *__restrict__ count,
-                                                            int *__restrict__ err)
+                                                            int32_t *__restrict__ cell, int32_t *__restrict__ count)
 {
-    const int j = blockIdx.x * kThreads + threadIdx.x;
-    if (j >= k) return;
-    const float4 a = __ldg(msg + 1 + 2 * j), b = __ldg(msg + 2 + 2 * j);
-    const int src = __float_as_int(b.z);
-    int rank = 0;
-    for (int q = 0; q < k; ++q) rank += (__float_as_int(__ldg(msg + 2 + 2 * q).z) < src) ? 1 : 0;
-    const int dst = base + rank;
-    pt[dst] = a;
-    vel[dst] = make_float2(b.x, b.y);
-    const int cxy = cell_coords((double)a.x, (double)a.y, g);
-    const int c = container_of(cxy, g);
-    cell[dst] = c < 0 ? -1 : cxy;
-    if (c >= 0) atomicAdd(count + c, 1);
-    else atomicAdd(err, 1); // sender and receiver disagree about ownership
-}
-
-// copy a message (its used records only) into the neighbour's receive slot
-__global__ void __launch_bounds__(kThreads) push_msg(const float4 *__restrict__ local, float4 *__restrict__ peer, int is_halo, int nx,
-                                                     int cap, volatile unsigned long long *flag, unsigned int *ticket,
-                                                     unsigned long long seq)
-{
-    const int count = *reinterpret_cast<const int *>(local);
-    int nrec;
-    if (is_halo) nrec = count < 0 ? 1 : 1 + offsets_records(nx) + count;
-    else nrec = 1 + 2 * min(count, cap);
-    for (int k = blockIdx.x * kThreads + threadIdx.x; k < nrec; k += gridDim.x * kThreads) peer[k] = local[k];
-    if (flag) signal_when_all_done(ticket, flag, seq, gridDim.x);
-    else __threadfence_system();
-}
-
-// Phase FINISH: wait for the neighbours' migration messages (peer mode), then put the four message headers and the
-// error word where the host can read them after one stream synchronisation - mapped pinned memory, no copies.
-__global__ void finish_headers(const volatile unsigned long long *f0, const volatile unsigned long long *f1, unsigned long long seq,
-                               int *err, const float4 *ms0, const float4 *ms1, const float4 *mi0, const float4 *mi1,
-                               volatile int4 *out, unsigned long long spin_ns)
-{
-    const unsigned long long t0 = wall_ns();
-    for (int k = 0; k < 2; ++k) {
-        const volatile unsigned long long *f = k ? f1 : f0;
-        if (!f) continue;
-        while (*f < seq) {
-            if (wall_ns() - t0 > spin_ns) {
-                atomicAdd(err, 1 << 16);
-                break;
-            }
-            __nanosleep(200);
-        }
+    const int which = blockIdx.y;
+    const float4 *msg = which ? msg1 : msg0;
+    const int k = which ? cnt->k_above : cnt->k_below;
+    if (!msg || k == 0) return;
+    const int base = cnt->n_old + (which ? cnt->k_below : 0);
+    for (int j = blockIdx.x * kThreads + threadIdx.x; j < k; j += gridDim.x * kThreads) {
+        const float4 a = __ldcg(msg + 1 + 2 * j), b = __ldcg(msg + 2 + 2 * j);
+        const int src = __float_as_int(b.z);
+        int rank = 0;
+        for (int q = 0; q < k; ++q) rank += (__float_as_int(__ldcg(msg + 2 + 2 * q).z) < src) ? 1 : 0;
+        const int dst = base + rank;
+        pt[dst] = a;
+        vel[dst] = make_float2(b.x, b.y);
+        const int cxy = cell_coords((double)a.x, (double)a.y, g);
+        const int c = container_of(cxy, g);
+        cell[dst] = c < 0 ? -1 : cxy;
+        if (c >= 0) atomicAdd(count + c, 1);
+        else atomicOr(&cnt->err, kErrOwner); // sender and receiver disagree about ownership
     }
-    __threadfence_system();
-    const float4 *src[4] = {ms0, ms1, mi0, mi1};
-    for (int k = 0; k < 4; ++k) {
-        int4 v = make_int4(0, 0, 0, 0);
-        if (src[k]) {
-            const volatile int *p = reinterpret_cast<const volatile int *>(src[k]);
-            v = make_int4(p[0], p[1], p[2], p[3]);
-        }
-        out[k].x = v.x; out[k].y = v.y; out[k].z = v.z; out[k].w = v.w;
-    }
-    out[4].x = *reinterpret_cast<volatile int *>(err);
-    __threadfence_system();
 }
 
 int fail(plife_handle *h, int code, const char *msg) { return slab_fail(h, code, msg); }
@@ -236,6 +293,19 @@ int fail(plife_handle *h, int code, const char *msg) { return slab_fail(h, code,
             return fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e_));       \
         }                                                                 \
     } while (0)
+
+int report(plife_handle *h, int err)
+{
+    if (!err) return PLIFE_OK;
+    h->slab.err_seen = err;
+    if (err & kErrTimeout) return fail(h, PLIFE_ERR_STATE, "slab: timed out waiting for a neighbour's message");
+    if (err & kErrFar) return fail(h, PLIFE_ERR_STATE, "slab: a particle crossed more than one slab in one step");
+    if (err & kErrClosed) return fail(h, PLIFE_ERR_STATE, "slab: particle left through a closed boundary");
+    if (err & kErrMigCap) return fail(h, PLIFE_ERR_STATE, "slab: migration message overflow (raise mig_cap)");
+    if (err & kErrCapacity) return fail(h, PLIFE_ERR_OOM, "slab: particle capacity exceeded by arrivals");
+    if (err & kErrBound) return fail(h, PLIFE_ERR_STATE, "slab: particle count outran the host's launch bound (internal)");
+    return fail(h, PLIFE_ERR_STATE, "slab: halo overflow / grid mismatch between ranks / ownership mismatch (raise halo_cap)");
+}
 
 } // namespace
 
@@ -268,7 +338,11 @@ void slab_release(plife_handle *h)
         S.peer_base[d] = nullptr;
         S.peer_ipc[d] = false;
     }
-    if (S.h_hdr) cudaFreeHost((void *)S.h_hdr);
+    if (S.h_ring) cudaFreeHost((void *)S.h_ring);
+    cudaFree(S.counts);
+    cudaFree(S.d_tr);
+    for (int k = 0; k < 4; k++)
+        if (S.step_done[k]) cudaEventDestroy(S.step_done[k]);
     if (S.peer_mode) {
         cudaFree(S.xbuf);
         for (int d = 0; d < 2; d++) {
@@ -282,11 +356,74 @@ void slab_release(plife_handle *h)
 
 namespace plife {
 void slab_destroy(plife_handle *h) { slab_release(h); }
+
+// The host's view of the counts.  block = false: take the newest entry the finish kernels have published so far (the
+// host may be a few steps ahead of the device) and derive the launch bound from it; block = true: drain the stream
+// first, so the counts are exact (plife_count, download, snapshot, upload ...).
+int slab_refresh(plife_handle *h, bool block)
+{
+    SlabState &S = h->slab;
+    if (!S.on || !S.counts) return PLIFE_OK;
+    if (block) {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            h->poisoned = true;
+            return slab_fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    const unsigned long long done = S.seq - 1; // last step whose FINISH has been queued
+    for (unsigned long long s = done; s > S.seq_known && s + 8 > done; --s) {
+        volatile SlabCounts *r = S.h_ring + (s & 7);
+        if (r->seq != s) continue;
+        SlabCounts c;
+        c.n = r->n; c.n_phys = r->n_phys; c.n_old = r->n_old; c.k_below = r->k_below; c.k_above = r->k_above;
+        c.err = r->err; c.sent_dn = r->sent_dn; c.sent_up = r->sent_up;
+        if (r->seq != s) continue; // overwritten while reading (cannot happen with <= 4 steps in flight)
+        S.seq_known = s;
+        h->n = c.n;
+        h->n_phys = c.n_phys;
+        S.n_old = c.n_old;
+        S.k_below = c.k_below;
+        S.k_above = c.k_above;
+        S.max_arrivals = S.max_arrivals > c.k_below + c.k_above ? S.max_arrivals : c.k_below + c.k_above;
+        if (c.err && !S.err_seen) S.err_pending = c.err;
+        break;
+    }
+    // growth a step can bring: what has been seen, with a generous margin; the device reports kErrBound if it is ever wrong
+    const int64_t lag = (int64_t)(done - S.seq_known);
+    const int64_t per_step = 4 * S.max_arrivals + 4096;
+    int64_t b = h->n_phys + (lag + 1) * per_step;
+    S.n_bound = b < h->cap ? b : h->cap;
+    if (block && (S.err_pending || S.err_seen)) return report(h, S.err_pending | S.err_seen); // a synchronising call reports what the device found
+    return PLIFE_OK;
+}
+
+// counts known exactly on the host (after upload / init): write them to the device
+int slab_set_counts(plife_handle *h)
+{
+    SlabState &S = h->slab;
+    if (!S.on || !S.counts) return PLIFE_OK;
+    SlabCounts c{};
+    c.n = (int)h->n;
+    c.n_phys = (int)h->n_phys;
+    c.n_old = (int)h->n_phys;
+    c.seq = S.seq - 1;
+    cudaError_t e = cudaMemcpyAsync(S.counts, &c, sizeof c, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return slab_fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e));
+    S.seq_known = S.seq - 1;
+    S.n_old = h->n_phys;
+    S.k_below = S.k_above = 0;
+    S.n_bound = h->n_phys;
+    S.err_pending = S.err_seen = 0;
+    return PLIFE_OK;
+}
 } // namespace plife
 
 extern "C" {
 
-int64_t plife_slab_halo_records(int32_t nx, int64_t halo_cap) { return 1 + (nx + 3) / 4 + halo_cap; }
+// header + one END offset per fine bin of a row (at most 8 bins per cell) + the records
+int64_t plife_slab_halo_records(int32_t nx, int64_t halo_cap) { return 1 + (8 * (int64_t)nx + 3) / 4 + halo_cap; }
 int64_t plife_slab_migrate_records(int64_t mig_cap) { return 1 + 2 * mig_cap; }
 
 int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t halo_cap, int64_t mig_cap,
@@ -339,16 +476,23 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
             if (e == cudaSuccess) e = cudaMalloc((void **)&S.mig_send[d], (size_t)S.mrec * 16);
         }
         if (e == cudaSuccess) e = cudaMemset(S.xbuf, 0, (size_t)S.xrecords * 16);
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             slab_release(h);
             return fail(h, PLIFE_ERR_OOM, "slab_configure: allocating exchange buffers failed");
         }
     }
-    if (cudaHostAlloc((void **)&S.h_hdr, 5 * sizeof(int4), cudaHostAllocMapped) != cudaSuccess) {
+    cudaError_t e = cudaMalloc((void **)&S.counts, sizeof(SlabCounts));
+    if (e == cudaSuccess) e = cudaMemset(S.counts, 0, sizeof(SlabCounts));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&S.d_tr, 12 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(S.d_tr, 0, 12 * sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&S.h_ring, 8 * sizeof(SlabCounts), cudaHostAllocMapped);
+    for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&S.step_done[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
         slab_release(h);
-        return fail(h, PLIFE_ERR_OOM, "slab_configure: allocating the pinned header block failed");
+        return fail(h, PLIFE_ERR_OOM, "slab_configure: allocating the count blocks failed");
     }
+    memset((void *)S.h_ring, 0, 8 * sizeof(SlabCounts));
     S.phase = PLIFE_SLAB_SORT;
     h->prebinned = false;
     return slab_reset_capacity(h); // the particle buffers need room for the ghost rows
@@ -430,17 +574,17 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
     if (!h->slab.on) return fail(h, PLIFE_ERR_STATE, "plife_slab_configure has not been called");
     if (phase != h->slab.phase) return fail(h, PLIFE_ERR_STATE, "slab phases must run in order SORT, FORCE, FINISH");
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, PLIFE_ERR_CUDA, "cudaSetDevice");
+    SlabState &S = h->slab;
+    if (S.err_seen) return report(h, S.err_seen);
     Grid g;
     int rc = slab_make_grid(h, &g);
     if (rc) return rc;
-    SlabState &S = h->slab;
     if (g.nx > S.nx_cfg) return fail(h, PLIFE_ERR_STATE, "slab: rmax shrank since plife_slab_configure (halo messages would not fit): reconfigure");
     const bool wrap = h->settings.wrap != 0;
     const bool has_dn = S.world > 1 && (wrap || S.rank > 0);
     const bool has_up = S.world > 1 && (wrap || S.rank < S.world - 1);
     if (S.peer_mode && ((has_dn && !S.peer_base[0]) || (has_up && !S.peer_base[1])))
         return fail(h, PLIFE_ERR_STATE, "slab: neighbours not connected (plife_slab_connect_ipc / _local)");
-    int *d_err = reinterpret_cast<int *>(h->d_scalar + 4);
     const int first = (int)S.halo_cap;
     const int parity = (int)(S.seq & 1);
     float4 *dn = S.peer_base[0], *up = S.peer_base[1];
@@ -450,24 +594,29 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         halo_in[d] = S.peer_mode ? halo_slot(S.xbuf, S, parity, d) : S.halo_recv[d];
         mig_in[d] = S.peer_mode ? mig_slot(S.xbuf, S, parity, d) : S.mig_recv[d];
     }
+    unsigned int *tickets = S.peer_mode ? reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(S.xbuf) + F_TICKETS) : nullptr; // 4 local counters
 
     if (phase == PLIFE_SLAB_SORT) {
+        // no more than 3 steps queued ahead of the device: bounds the slack of the launch bound and the count ring
+        if (S.seq > 4) CUS(h, cudaEventSynchronize(S.step_done[(S.seq - 4) & 3]));
+        rc = slab_refresh(h, false);
+        if (rc) return rc;
+        if (S.err_pending) return report(h, S.err_pending);
         rc = slab_sort(h, g); // bin (if needed), scan, scatter, gather: owned block of the sorted array
         if (rc) return rc;
         const int sorted = h->cur ^ 1;
         dim3 grid(32, 2);
-        unsigned int *tickets = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(S.xbuf) + F_TICKETS); // 4 local counters
         if (S.peer_mode) {
             // my first row is the down neighbour's ghost row ABOVE its slab (its slot dir 1), and vice versa; the pack kernel
             // writes it there and raises the neighbour's flag when its last CTA is done
-            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap,
+            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, first, S.counts,
                                                         has_dn ? halo_slot(dn, S, parity, 1) : S.halo_send[0],
-                                                        has_up ? halo_slot(up, S, parity, 0) : S.halo_send[1], S.mig_send[0], S.mig_send[1],
+                                                        has_up ? halo_slot(up, S, parity, 0) : S.halo_send[1], S.mig_send[0], S.mig_send[1], S.d_tr,
                                                         has_dn ? flag_of(dn, F_HALO_UP) : nullptr, has_up ? flag_of(up, F_HALO_DN) : nullptr,
                                                         tickets, S.seq);
         } else {
-            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1],
-                                                        S.mig_send[0], S.mig_send[1], nullptr, nullptr, nullptr, 0ull);
+            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, first, S.counts, S.halo_send[0],
+                                                        S.halo_send[1], S.mig_send[0], S.mig_send[1], S.d_tr, nullptr, nullptr, nullptr, 0ull);
         }
         CUS(h, cudaGetLastError());
         S.phase = PLIFE_SLAB_FORCE;
@@ -475,63 +624,48 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
     }
     if (phase == PLIFE_SLAB_FORCE) {
         const int sorted = h->cur ^ 1;
-        dim3 grid(32, 2);
         const bool peer = S.peer_mode;
-        unpack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, first, (int)h->n,
-                                                      has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr, d_err,
+        const int nxk = g.nxk();
+        // interior rows first: they read owned rows only, so the halo may still be in flight (peer mode; with the external
+        // exchange the halo is already here and the split only costs a launch)
+        const int nb_all = (int)((S.n_bound + 127) / 128) + 1;
+        const int nb_edge = (int)((2 * S.halo_cap + 127) / 128) + 2;
+        CUS(h, slab_force(h, g, dt, S.d_tr, nb_all, nxk, (g.nly - 1) * nxk - 1, true, false));
+        dim3 grid(32, 2);
+        unpack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, first, S.counts,
+                                                      has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr,
                                                       peer && has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr,
                                                       peer && has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq, S.spin_ns);
         CUS(h, cudaGetLastError());
-        CUS(h, slab_force(h, g, dt));
-        if (S.peer_mode) {
-            unsigned int *tickets = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(S.xbuf) + F_TICKETS);
-            if (has_dn) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[0], mig_slot(dn, S, parity, 1), 0, g.nx, (int)S.mig_cap,
-                                                                flag_of(dn, F_MIG_UP), tickets + 2, S.seq);
-            if (has_up) push_msg<<<8, kThreads, 0, h->stream>>>(S.mig_send[1], mig_slot(up, S, parity, 0), 0, g.nx, (int)S.mig_cap,
-                                                                flag_of(up, F_MIG_DN), tickets + 3, S.seq);
+        CUS(h, slab_force(h, g, dt, S.d_tr + 4, nb_edge, 0, nxk * g.nly - 1, false, true));
+        if (S.peer_mode && (has_dn || has_up)) {
+            dim3 pg(8, 2);
+            push_mig<<<pg, kThreads, 0, h->stream>>>(S.mig_send[0], S.mig_send[1], has_dn ? mig_slot(dn, S, parity, 1) : nullptr,
+                                                     has_up ? mig_slot(up, S, parity, 0) : nullptr, (int)S.mig_cap,
+                                                     has_dn ? flag_of(dn, F_MIG_UP) : nullptr, has_up ? flag_of(up, F_MIG_DN) : nullptr,
+                                                     tickets + 2, S.seq);
             CUS(h, cudaGetLastError());
         }
         S.phase = PLIFE_SLAB_FINISH;
         return PLIFE_OK;
     }
-    // PLIFE_SLAB_FINISH: headers back to the host (the only synchronisation of the step)
+    // PLIFE_SLAB_FINISH
     {
-        const bool waits = S.peer_mode && (has_dn || has_up);
-        finish_headers<<<1, 1, 0, h->stream>>>(waits && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, waits && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr,
-                                               S.seq, d_err, S.mig_send[0], S.mig_send[1], has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr,
-                                               S.h_hdr, S.spin_ns);
+        const bool waits = S.peer_mode;
+        slab_finish<<<1, 32, 0, h->stream>>>(waits && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, waits && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr,
+                                             S.seq, S.counts, S.mig_send[0], S.mig_send[1], has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr,
+                                             has_dn ? 1 : 0, has_up ? 1 : 0, (int)S.mig_cap, (int)h->cap, (int)S.n_bound, S.h_ring, S.spin_ns);
+        CUS(h, cudaGetLastError());
+        if (has_dn || has_up) {
+            dim3 ag(16, 2);
+            append_arrivals<<<ag, kThreads, 0, h->stream>>>(has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr, S.counts, g, h->s32[h->cur].pt,
+                                                            h->s32[h->cur].vel, h->d_cell, h->d_count);
+            CUS(h, cudaGetLastError());
+        }
+        CUS(h, cudaEventRecord(S.step_done[S.seq & 3], h->stream));
     }
-    CUS(h, cudaGetLastError());
-    CUS(h, cudaStreamSynchronize(h->stream));
-    int4 hs[4];
-    for (int k = 0; k < 4; k++) hs[k] = make_int4(S.h_hdr[k].x, S.h_hdr[k].y, S.h_hdr[k].z, S.h_hdr[k].w);
-    const int err = S.h_hdr[4].x;
     S.phase = PLIFE_SLAB_SORT;
     S.seq++;
-    const int sent_dn = hs[0].x, sent_up = hs[1].x;
-    const int k_below = has_dn ? hs[2].x : 0, k_above = has_up ? hs[3].x : 0;
-    if (err >> 16) return fail(h, PLIFE_ERR_STATE, "slab: timed out waiting for a neighbour's message");
-    if (err) return fail(h, PLIFE_ERR_STATE, "slab: halo overflow / grid mismatch between ranks / ownership mismatch (raise halo_cap)");
-    if (hs[0].y || hs[1].y) return fail(h, PLIFE_ERR_STATE, "slab: a particle crossed more than one slab in one step");
-    if ((!has_dn && sent_dn) || (!has_up && sent_up)) return fail(h, PLIFE_ERR_STATE, "slab: particle left through a closed boundary");
-    if (sent_dn > S.mig_cap || sent_up > S.mig_cap || k_below > S.mig_cap || k_above > S.mig_cap)
-        return fail(h, PLIFE_ERR_STATE, "slab: migration message overflow (raise mig_cap)");
-    const int64_t L = h->n; // residents before this step (the force pass wrote slots [0, L))
-    if (L + k_below + k_above > h->cap) return fail(h, PLIFE_ERR_OOM, "slab: particle capacity exceeded by arrivals");
-    const int cur = h->cur;
-    CUS(h, cudaMemsetAsync(d_err, 0, sizeof(int), h->stream)); // errors raised from here on are reported by the next FINISH
-    if (k_below > 0)
-        append_arrivals<<<(k_below + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(mig_in[0], k_below, (int)L, g, h->s32[cur].pt,
-                                                                                      h->s32[cur].vel, h->d_cell, h->d_count, d_err);
-    if (k_above > 0)
-        append_arrivals<<<(k_above + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(mig_in[1], k_above, (int)L + k_below, g,
-                                                                                      h->s32[cur].pt, h->s32[cur].vel, h->d_cell, h->d_count, d_err);
-    CUS(h, cudaGetLastError());
-    S.n_old = L;
-    S.k_below = k_below;
-    S.k_above = k_above;
-    h->n_phys = L + k_below + k_above;
-    h->n = L - sent_dn - sent_up + k_below + k_above;
     h->steps++;
     return PLIFE_OK;
 }

@@ -50,9 +50,9 @@ public class NativePhysics extends Physics {
     private static final MethodHandle SNAPSHOT_ASYNC_U8 = fn("plife_snapshot_async_u8", FunctionDescriptor.of(I32, PTR, PTR, PTR, PTR));
     private static final MethodHandle SNAPSHOT_WAIT = fn("plife_snapshot_wait", FunctionDescriptor.of(I32, PTR));
 
-    /** struct plife_config { int32 device, precision; int64 capacity; int32 flags, reserved; void* stream; } */
+    /** struct plife_config { int32 device, precision; int64 capacity; int32 flags, bins; void* stream; } */
     private static final MemoryLayout CONFIG = MemoryLayout.structLayout(I32.withName("device"), I32.withName("precision"),
-            I64.withName("capacity"), I32.withName("flags"), I32.withName("reserved"), PTR.withName("stream"));
+            I64.withName("capacity"), I32.withName("flags"), I32.withName("bins"), PTR.withName("stream"));
     /** struct plife_settings { double rmax, friction, force; int32 wrap, reserved; } */
     private static final MemoryLayout SETTINGS = MemoryLayout.structLayout(F64.withName("rmax"), F64.withName("friction"),
             F64.withName("force"), I32.withName("wrap"), I32.withName("reserved"));

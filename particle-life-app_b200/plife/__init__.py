@@ -18,7 +18,7 @@ import numpy as np
 from . import _native as N
 from . import synth
 from ._native import (ACC_PARTICLE_LIFE, ACC_PARTICLE_LIFE_R, ACC_PARTICLE_LIFE_R2, ACC_PLANETS,
-                      ACC_ROTATOR_90, ACC_ROTATOR_ATTR, F32, F64, FLAG_FORCE_V1, FLAG_NO_FUSED_BIN, FLAG_PAIRS,
+                      ACC_ROTATOR_90, ACC_ROTATOR_ATTR, F32, F64, FLAG_FORCE_V1, FLAG_NO_FUSED_BIN,
                       FLAG_UNSTABLE_SORT, KERNEL_NAMES, PlifeError)
 
 __all__ = ["Physics", "PhysicsSettings", "NativePhysics", "Particles", "PlifeError",
@@ -40,9 +40,9 @@ class NativePhysics:
     """Thin object wrapper over the plife_* entry points (one handle)."""
 
     def __init__(self, device: int = 0, precision: int = F32, capacity: int = 0, flags: int = 0,
-                 stream: Optional[int] = None):
+                 stream: Optional[int] = None, bins: int = 0):
         self.L = N.lib()
-        cfg = N.Config(device=device, precision=precision, capacity=capacity, flags=flags, reserved=0,
+        cfg = N.Config(device=device, precision=precision, capacity=capacity, flags=flags, bins=bins,
                        stream=stream)
         h = C.c_void_p()
         rc = self.L.plife_create(C.byref(cfg), C.byref(h))

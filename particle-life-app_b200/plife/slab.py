@@ -117,10 +117,10 @@ class SlabPhysics:
     phases (`DistExchange`)."""
 
     def __init__(self, rank: int, world: int, rmax: float, *, device: int = 0, capacity: int, halo_cap: int,
-                 mig_cap: int, friction=0.85, force=1.0, wrap=True, stream=None, flags: int = 0, exchange: str = "peer"):
+                 mig_cap: int, friction=0.85, force=1.0, wrap=True, stream=None, flags: int = 0, exchange: str = "peer", bins: int = 0):
         from . import NativePhysics
         self.rank, self.world, self.wrap, self.exchange_mode = rank, world, wrap, exchange
-        self.native = NativePhysics(device=device, precision=N.F32, capacity=capacity, flags=flags, stream=stream)
+        self.native = NativePhysics(device=device, precision=N.F32, capacity=capacity, flags=flags, stream=stream, bins=bins)
         self.native.set_settings(rmax, friction, force, wrap)
         self.rmax = rmax
         L = self.native.L
@@ -203,10 +203,10 @@ class VirtualCluster:
     """`world` slabs driven in lockstep inside one process on one device."""
 
     def __init__(self, world: int, rmax: float, matrix, *, device: int = 0, capacity: int, halo_cap: int, mig_cap: int,
-                 wrap=True, friction=0.85, force=1.0, accelerator=(0, ()), exchange: str = "peer"):
+                 wrap=True, friction=0.85, force=1.0, accelerator=(0, ()), exchange: str = "peer", bins: int = 0):
         self.world, self.wrap, self.rmax, self.exchange_mode = world, wrap, rmax, exchange
         self.slabs = [SlabPhysics(r, world, rmax, device=device, capacity=capacity, halo_cap=halo_cap, mig_cap=mig_cap,
-                                  wrap=wrap, friction=friction, force=force, exchange=exchange) for r in range(world)]
+                                  wrap=wrap, friction=friction, force=force, exchange=exchange, bins=bins) for r in range(world)]
         for s in self.slabs:
             s.native.set_matrix(matrix)
             s.native.set_accelerator(accelerator[0], accelerator[1])

@@ -16,8 +16,8 @@ pytestmark = pytest.mark.gpu
 DT = 0.02
 
 
-def gpu_step(native_lib, precision, pos, vel, types, matrix, steps=1, accel=(0, (0.3,)), flags=0, **kw):
-    p = plife.NativePhysics(precision=precision, flags=flags)
+def gpu_step(native_lib, precision, pos, vel, types, matrix, steps=1, accel=(0, (0.3,)), flags=0, bins=0, **kw):
+    p = plife.NativePhysics(precision=precision, flags=flags, bins=bins)
     p.set_settings(kw.get("rmax", 0.02), kw.get("friction", 0.85), kw.get("force", 1.0), kw.get("wrap", True))
     p.set_matrix(matrix)
     p.set_accelerator(accel[0], accel[1])
@@ -244,11 +244,12 @@ def test_virtual_slabs_match_single_gpu(native_lib, world, wrap, exchange):
     from plife.slab import VirtualCluster
     n, m, rmax, steps = 60_000, 5, 0.02, 12
     pos, vel, types, matrix = make_state(n, m, seed=31 + world, vel_scale=0.3, f32=True)
-    single = plife.NativePhysics(precision=plife.F32)
+    # same fine-bin count on both sides: the fp32 summation order follows the internal cell list
+    single = plife.NativePhysics(precision=plife.F32, bins=4)
     single.set_settings(rmax, 0.85, 1.0, wrap)
     single.set_matrix(matrix)
     single.upload(pos, vel, types)
-    vc = VirtualCluster(world, rmax, matrix, capacity=n, halo_cap=4096, mig_cap=4096, wrap=wrap, exchange=exchange)
+    vc = VirtualCluster(world, rmax, matrix, capacity=n, halo_cap=4096, mig_cap=4096, wrap=wrap, exchange=exchange, bins=4)
     vc.upload(pos, vel, types)
     start_counts = vc.counts()
     assert sum(start_counts) == n
@@ -296,22 +297,25 @@ def test_slab_errors(native_lib):
     vc = VirtualCluster(2, 0.05, matrix, capacity=5000, halo_cap=8, mig_cap=512)  # halo row does not fit
     vc.upload(pos, vel, types)
     with pytest.raises(plife.PlifeError):
-        vc.step(DT, 1)
+        vc.step(DT, 1)  # a slab step never synchronises: the device's finding is returned by the next synchronising call
+        for s in vc.slabs:
+            s.native.sync()
     vc = VirtualCluster(2, 0.05, matrix, capacity=5000, halo_cap=2048, mig_cap=512)
     with pytest.raises(plife.PlifeError):  # single-GPU stepping is refused in slab mode
         vc.slabs[0].native.step(DT, 1)
 
 
-@pytest.mark.parametrize("flags", [plife.FLAG_FORCE_V1, plife.FLAG_PAIRS, plife.FLAG_NO_FUSED_BIN], ids=["v1", "pairs", "nofusedbin"])
+@pytest.mark.parametrize("flags,bins", [(plife.FLAG_FORCE_V1, 0), (plife.FLAG_NO_FUSED_BIN, 0), (0, 1), (0, 2), (0, 4), (0, 8), (plife.FLAG_NO_FUSED_BIN, 8)],
+                         ids=["v1", "nofusedbin", "bins1", "bins2", "bins4", "bins8", "nofusedbin_bins8"])
 @pytest.mark.parametrize("case", [dict(n=10_000, m=6, rmax=0.04, wrap=True), dict(n=5_000, m=3, rmax=0.065, wrap=True),
                                   dict(n=5_000, m=3, rmax=0.065, wrap=False), dict(n=40_000, m=16, rmax=0.02, wrap=True)],
                          ids=["c1", "fat_wrap", "fat_clamp", "m16"])
-def test_fp32_kernel_variants_match_oracle(native_lib, flags, case):
-    """The alternative fp32 force kernels (v1 global walk, two-targets-per-lane) and the unfused binning agree
-    with the oracle over several steps, fat last cell included."""
+def test_fp32_kernel_variants_match_oracle(native_lib, flags, bins, case):
+    """The alternative fp32 paths (v1 global walk, unfused binning, every fine-bin count of the internal cell list) agree
+    with the oracle over several steps - velocities within tolerance, particle order exact - fat last cell included."""
     pos, vel, types, matrix = make_state(case["n"], case["m"], seed=77, vel_scale=0.05, f32=True)
     ids = np.arange(case["n"], dtype=np.uint32)
-    p = plife.NativePhysics(precision=plife.F32, flags=flags)
+    p = plife.NativePhysics(precision=plife.F32, flags=flags, bins=bins)
     p.set_settings(case["rmax"], 0.85, 1.0, case["wrap"])
     p.set_matrix(matrix)
     pos[:20, 0] = 1.0  # the strip / wall: un-clamped cell coords differ from the container
@@ -552,13 +556,13 @@ def test_simulation_loop_and_snapshots(native_lib):
 
 
 @pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
-@pytest.mark.parametrize("flags", [0, plife.FLAG_PAIRS], ids=["default", "pairs"])
-def test_clustered_state(native_lib, precision, flags):
+@pytest.mark.parametrize("bins", [0, 1, 8], ids=["auto", "bins1", "bins8"])
+def test_clustered_state(native_lib, precision, bins):
     """Non-uniform occupancy: a tight gaussian blob puts hundreds of particles into a few cells and
     leaves most cells empty; staged ranges overflow their capacity (global-walk fallback) and the in-cell rank loop
     sees long cells.  Real Particle-Life states look like this, the benchmark state does not."""
-    if flags and precision == plife.F64:
-        pytest.skip("pairs kernel is fp32")
+    if bins and precision == plife.F64:
+        pytest.skip("fine bins are an fp32 feature")
     f32 = precision == plife.F32
     rng = np.random.default_rng(12)
     n, m, rmax = 30_000, 4, 0.02
@@ -574,7 +578,7 @@ def test_clustered_state(native_lib, precision, flags):
         o = oracle_step(pos, vel, types, matrix, rmax=rmax, wrap=wrap, dt=DT)
         opos, ovel, otyp, oid = o.get_particles()
         assert np.bincount(np.diff(np.concatenate([[0], o.containers()]))).size > 200  # some cell holds > 200 particles
-        g = gpu_step(native_lib, precision, pos, vel, types, matrix, flags=flags, rmax=rmax, wrap=wrap, dt=DT)
+        g = gpu_step(native_lib, precision, pos, vel, types, matrix, bins=bins, rmax=rmax, wrap=wrap, dt=DT)
         got = g.download()
         assert np.array_equal(got.id, oid) and np.array_equal(g.containers(), o.containers())
         assert g.step_stats()["pair_evals"] == o.pair_stats()[0]

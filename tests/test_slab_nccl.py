@@ -26,7 +26,7 @@ def _worker(rank, world, port, tmp, exchange):
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
             sp = SlabPhysics(rank, world, rmax, device=rank, capacity=n, halo_cap=8192, mig_cap=8192, stream=stream.cuda_stream,
-                             exchange=exchange)
+                             exchange=exchange, bins=8)
             if exchange == "peer":
                 sp.connect_dist()
             sp.native.set_matrix(matrix)
@@ -53,7 +53,7 @@ def test_two_gpu_slabs_match_single_gpu(native_lib, tmp_path, exchange):
     torch.multiprocessing.spawn(_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
     n, m, rmax, steps = 200_000, 6, 0.01, 15
     pos, vel, types, matrix = make_state(n, m, seed=99, vel_scale=0.3, f32=True)
-    single = plife.NativePhysics(precision=plife.F32)
+    single = plife.NativePhysics(precision=plife.F32, bins=8)  # same internal cell list => same fp32 summation order
     single.set_settings(rmax, 0.85, 1.0, True)
     single.set_matrix(matrix)
     single.upload(pos, vel, types)
