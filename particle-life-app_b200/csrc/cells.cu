@@ -218,96 +218,42 @@ __global__ void __launch_bounds__(kThreads) scatter_perm(const int32_t *__restri
     }
 }
 
-// Logical position of pre-sort slot `src`.  Single GPU: the identity.  Slab mode: the pre-sort array is
-// physically [residents 0..n_old) | arrivals from below (k_below) | arrivals from above]; the key puts the
-// three groups in the order of their previous GLOBAL array index, which is what the reference's stable
-// sort preserves: below < residents < above, except across the periodic seam, where rank 0's arrivals
-// from "below" come from the END of the global array and the last rank's arrivals from "above" from its
-// beginning.  The counts live in device memory (SlabCounts): the host does not know them when it queues the step.
-struct StableKey {
-    const SlabCounts *cnt;
-    int order; // 0: below, residents, above   1 (rank 0, periodic): residents, above, below   2 (last rank, periodic): above, below, residents
-    int n_old, k_below, base_res, base_below, base_above;
-    __device__ __forceinline__ void load()
-    {
-        n_old = cnt->n_old;
-        k_below = cnt->k_below;
-        const int ka = cnt->k_above;
-        if (order == 1) { base_res = 0; base_below = n_old + ka; base_above = n_old; }
-        else if (order == 2) { base_res = ka + k_below; base_below = ka; base_above = 0; }
-        else { base_res = k_below; base_below = 0; base_above = k_below + n_old; }
-    }
-    __device__ __forceinline__ int operator()(int src) const
-    {
-        if (src < n_old) return src + base_res;
-        src -= n_old;
-        return src < k_below ? src + base_below : src - k_below + base_above;
-    }
-    __device__ __forceinline__ bool mixed(int max_src) const { return max_src >= n_old; } // the range holds an arrival
-};
-
-struct IdentityKey { // single GPU: the pre-sort index is the previous array index
-    __device__ __forceinline__ void load() {}
-    __device__ __forceinline__ int operator()(int src) const { return src; }
-    __device__ __forceinline__ bool mixed(int) const { return false; }
-};
-
-// number of entries of pp[s, e) (pre-sort slots of one cell or bin) that precede `src` in the previous array order
-template <typename KEY>
-__device__ __forceinline__ int stable_rank(const int32_t *__restrict__ pp, int s, int e, int src, int align, const KEY &key)
-{
-    // Raw pre-sort indices order the residents exactly like their keys do, and almost every cell holds residents
-    // only, so rank on the raw indices (four per load: cells of an evolved state hold thousands of particles and
-    // this loop is O(count^2) per cell) and track the largest one; only cells that received migrants (slab mode)
-    // are ranked again through the key.
-    int rank = 0;
-    int mx = src;
-    int k = s;
-    for (; k < e && ((k - align) & 3); ++k) {
-        const int q = __ldg(pp + k);
-        rank += (q < src) ? 1 : 0;
-        mx = max(mx, q);
-    }
-    for (; k + 4 <= e; k += 4) {
-        const int4 q = __ldg(reinterpret_cast<const int4 *>(pp + k));
-        rank += ((q.x < src) ? 1 : 0) + ((q.y < src) ? 1 : 0) + ((q.z < src) ? 1 : 0) + ((q.w < src) ? 1 : 0);
-        mx = max(max(mx, q.x), max(q.y, max(q.z, q.w)));
-    }
-    for (; k < e; ++k) {
-        const int q = __ldg(pp + k);
-        rank += (q < src) ? 1 : 0;
-        mx = max(mx, q);
-    }
-    if (key.mixed(mx)) {
-        rank = 0;
-        const int ksrc = key(src);
-        for (k = s; k < e; ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
-    }
-    return rank;
-}
-
 constexpr int kGatherUnroll = 2; // measured: 1 -> 0.186 ms, 2 -> 0.166 ms, 4 -> 0.190 ms at 16M particles
 
 // fp32: only the 16-byte candidate record moves.  Velocities stay where they are - each is needed once, by its own
 // particle - and the force pass reads them through src_sorted.
 //
-// Two orders come out of this pass.  The COMPUTE order (where the record goes: sorted by fine bin, stable inside a bin)
-// is what the force pass walks; the REFERENCE order (ref_sorted: sorted by cell, stable inside a cell - exactly the
-// permutation of B/Physics.java:343-348) is where the force pass writes its result, so the particle array the caller
-// sees is the reference's.  Bins nest in cells, so both slots lie in the cell's own index range; with ks = 0 they coincide.
+// The record goes to its slot in the COMPUTE order: sorted by fine bin, stable inside a bin (deterministic, and the
+// same on one GPU and on slabs).  The REFERENCE order (sorted by cell, stable inside a cell - exactly the permutation
+// of B/Physics.java:343-348) is where the force pass writes its result; a particle's slot there is its rank among
+// the pre-sort slots of its CELL, which the force pass computes from src_sorted (reference_slot, plife_internal.h).
+// Bins nest in cells, so both slots lie in the cell's own index range; with ks = 0 they coincide.
 // The record's type field is stored shifted (kTypeShift): it is the byte offset of a row of the force kernel's per-lane
 // matrix table, so staging candidates in shared memory is a plain bulk copy.
-template <bool STABLE, bool FINE, typename KEY>
+// Block 0 also prepares the slab step (tr: target ranges of the two force launches; mig0/mig1: migration cursors).
+template <bool STABLE>
 __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, float4 *__restrict__ pt_out, DevInt n_, Grid g,
-                                                       int first, KEY key, const int32_t *__restrict__ cell,
+                                                       int first, StableKey key, const int32_t *__restrict__ cell,
                                                        int32_t *__restrict__ cell_sorted, int32_t *__restrict__ src_sorted,
-                                                       int32_t *__restrict__ ref_sorted, const int32_t *__restrict__ cell_end,
-                                                       const int32_t *__restrict__ perm)
+                                                       const int32_t *__restrict__ cell_end, const int32_t *__restrict__ perm,
+                                                       int *__restrict__ tr, float4 *__restrict__ mig0, float4 *__restrict__ mig1)
 {
     // Two slots per thread: the kernel is a chain of four dependent memory round trips (perm -> record and cell ->
-    // bin offsets -> keys of the cell), so its speed is the number of chains in flight; two per thread instead of one.
+    // bin offsets -> keys of the bin), so its speed is the number of chains in flight; two per thread instead of one.
     constexpr int U = kGatherUnroll;
     const int n = n_.get();
+    if (tr && blockIdx.x == 0 && threadIdx.x == 0) {
+        // slab step: rows 1 and nly-2 are the first / last owned row; the force pass runs over the interior rows while the
+        // halo is in flight, then over those two.  cell_end holds END offsets since the scatter.
+        const int nxk = g.nxk();
+        const int e1 = __ldg(cell_end + 2 * nxk - 1) - first;           // end of the first owned row
+        const int sl = __ldg(cell_end + (g.nly - 2) * nxk - 1) - first; // start of the last owned row
+        tr[0] = e1; tr[1] = sl; tr[2] = 0; tr[3] = 0;  // interior rows
+        tr[4] = 0; tr[5] = e1; tr[6] = sl; tr[7] = n;  // first and last owned row
+        tr[8] = 0; tr[9] = n; tr[10] = 0; tr[11] = 0;  // the whole sorted block (plife_get_step_stats)
+        mig0[0] = make_float4(0.f, 0.f, 0.f, 0.f);     // this step's migration cursors
+        mig1[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int d0 = blockIdx.x * (kThreads * U) + threadIdx.x;
     if (blockIdx.x * (kThreads * U) >= n) return;
     key.load();
@@ -331,26 +277,15 @@ __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict_
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (src[u] < 0) continue;
-        const int d = d0 + u * kThreads;
-        const int c0 = FINE ? (c[u] >> g.ks) << g.ks : c[u]; // first bin of the cell (bins per row is a multiple of K)
-        const int cs = __ldg(&cell_end[c0 - 1]);              // start of the cell
-        int dst, ref;
+        int dst = d0 + u * kThreads + first; // PLIFE_FLAG_UNSTABLE_SORT: the cursor order is the order
         if (STABLE) {
-            const int ce = __ldg(&cell_end[c0 + (1 << g.ks) - 1]);
-            ref = cs + stable_rank(pp, cs, ce, src[u], first, key);
-            dst = ref;
-            if (FINE) {
-                const int bs = __ldg(&cell_end[c[u] - 1]), be = __ldg(&cell_end[c[u]]);
-                dst = bs + stable_rank(pp, bs, be, src[u], first, key);
-            }
-        } else { // PLIFE_FLAG_UNSTABLE_SORT: the cursor order is the order
-            dst = ref = d + first;
+            const int bs = __ldg(&cell_end[c[u] - 1]), be = __ldg(&cell_end[c[u]]);
+            dst = bs + stable_rank(pp, bs, be, src[u], first, key);
         }
         p[u].z = __int_as_float(__float_as_int(p[u].z) << kTypeShift);
         pt_out[dst] = p[u]; // sorted positions carry the ghost-below offset `first`; per-target arrays do not
         cell_sorted[dst - first] = cxy[u];
         src_sorted[dst - first] = src[u];
-        ref_sorted[dst - first] = ref - first;
     }
 }
 
@@ -370,7 +305,7 @@ __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out
     const int c = container_of(cxy, g);
     const int s = __ldg(&cell_end[c - 1]);
     int dst = d;
-    if (STABLE) dst = s + stable_rank(perm, s, __ldg(&cell_end[c]), src, 0, IdentityKey{});
+    if (STABLE) dst = s + stable_rank(perm, s, __ldg(&cell_end[c]), src, 0, StableKey{});
     cell_sorted[dst] = cxy;
     out.pos[dst] = p;
     out.vel[dst] = v;
@@ -381,14 +316,15 @@ __global__ void __launch_bounds__(kThreads) gather_f64(StateF64 in, StateF64 out
 // After plife_debug_neighbors on an fp32 handle the sort becomes the visible state, like makeContainers' swap
 // (B/Physics.java:351-353): records go back to plain types at their reference slots, velocities follow them.
 __global__ void __launch_bounds__(kThreads) apply_sort_f32(const float4 *__restrict__ pt_sorted, const float2 *__restrict__ vel_in,
-                                                           const int32_t *__restrict__ src_sorted, const int32_t *__restrict__ ref_sorted,
-                                                           int n, float4 *__restrict__ pt_out, float2 *__restrict__ vel_out)
+                                                           const int32_t *__restrict__ src_sorted, const int32_t *__restrict__ cell_sorted,
+                                                           const int32_t *__restrict__ cell_end, Grid g, int stable, int n,
+                                                           float4 *__restrict__ pt_out, float2 *__restrict__ vel_out)
 {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     float4 p = __ldg(pt_sorted + i);
     p.z = __int_as_float(__float_as_int(p.z) >> kTypeShift);
-    const int r = __ldg(ref_sorted + i);
+    const int r = stable ? reference_slot(i, __ldg(cell_sorted + i), src_sorted, cell_end, g, 0, StableKey{}) : i;
     pt_out[r] = p;
     vel_out[r] = __ldg(vel_in + __ldg(src_sorted + i));
 }
@@ -629,24 +565,14 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
     int nb = h->precision == PLIFE_F32 ? blocks_for(n, kThreads * kGatherUnroll) : blocks_for(n, kThreads);
     if (h->precision == PLIFE_F32) {
         const DevInt nn{(int)h->n, dev ? &h->slab.counts->n : nullptr};
-        const bool fine = g.ks > 0;
-#define PLIFE_GATHER(ST, FN, KT, KV)                                                                                        \
-    gather_f32<ST, FN, KT><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[b].pt, nn, g, first_index(h), KV, h->d_cell, \
-                                                           h->d_cell_sorted, h->d_src_sorted, h->d_ref_sorted, h->d_cell_end, h->d_perm)
-        if (h->slab.on) { // arrivals are ordered by their previous global position (StableKey)
-            const SlabState &S = h->slab;
-            const bool wrap = h->settings.wrap != 0 && S.world > 1;
-            int order = 0;
-            if (wrap && S.rank == 0 && S.rank != S.world - 1) order = 1;  // residents, above, below(seam)
-            else if (wrap && S.rank == S.world - 1) order = 2;            // above(seam), below, residents
-            StableKey key{S.counts, order, 0, 0, 0, 0, 0};
-            if (stable && fine) PLIFE_GATHER(true, true, StableKey, key);
-            else if (stable) PLIFE_GATHER(true, false, StableKey, key);
-            else PLIFE_GATHER(false, false, StableKey, key);
-        } else if (stable && fine) PLIFE_GATHER(true, true, IdentityKey, IdentityKey{});
-        else if (stable) PLIFE_GATHER(true, false, IdentityKey, IdentityKey{});
-        else PLIFE_GATHER(false, false, IdentityKey, IdentityKey{});
-#undef PLIFE_GATHER
+        const StableKey key = stable_key_of(h); // slabs: arrivals are ordered by their previous global position
+        int *tr = h->slab.on ? h->slab.d_tr : nullptr;
+        if (stable)
+            gather_f32<true><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[b].pt, nn, g, first_index(h), key, h->d_cell, h->d_cell_sorted,
+                                                             h->d_src_sorted, h->d_cell_end, h->d_perm, tr, h->slab.mig_send[0], h->slab.mig_send[1]);
+        else
+            gather_f32<false><<<nb, kThreads, 0, h->stream>>>(h->s32[a].pt, h->s32[b].pt, nn, g, first_index(h), key, h->d_cell, h->d_cell_sorted,
+                                                              h->d_src_sorted, h->d_cell_end, h->d_perm, tr, h->slab.mig_send[0], h->slab.mig_send[1]);
     } else {
         if (stable)
             gather_f64<true><<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], n, g, h->d_cell, h->d_cell_sorted, h->d_cell_end, h->d_perm);
@@ -657,13 +583,27 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
 }
 
 // fp32: make the sorted scratch (compute order, shifted types) the visible state in reference order
-cudaError_t launch_apply_sort_f32(plife_handle *h)
+StableKey stable_key_of(const plife_handle *h)
+{
+    StableKey key;
+    if (h->slab.on) {
+        const SlabState &S = h->slab;
+        const bool wrap = h->settings.wrap != 0 && S.world > 1;
+        key.cnt = S.counts;
+        if (wrap && S.rank == 0 && S.rank != S.world - 1) key.order = 1;  // residents, above, below(seam)
+        else if (wrap && S.rank == S.world - 1) key.order = 2;            // above(seam), below, residents
+    }
+    return key;
+}
+
+cudaError_t launch_apply_sort_f32(plife_handle *h, const Grid &g)
 {
     const int n = (int)h->n;
     if (n == 0) return cudaSuccess;
     const int a = h->cur, b = h->cur ^ 1;
-    apply_sort_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[b].pt, h->s32[a].vel, h->d_src_sorted, h->d_ref_sorted,
-                                                                      n, h->s32[a].pt, h->s32[b].vel);
+    apply_sort_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[b].pt, h->s32[a].vel, h->d_src_sorted, h->d_cell_sorted, h->d_cell_end,
+                                                                      g, (h->flags & PLIFE_FLAG_UNSTABLE_SORT) ? 0 : 1, n, h->s32[a].pt,
+                                                                      h->s32[b].vel);
     return cudaGetLastError();
 }
 

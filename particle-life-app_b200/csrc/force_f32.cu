@@ -11,7 +11,8 @@ static IOF32 make_io(plife_handle *h)
     const int src = h->cur ^ 1, dst = h->cur; // sorted scratch -> current
     // velocities: read from the current buffer (pre-sort order, through d_src_sorted), written to the scratch one;
     // launch_force_f32 swaps the two pointers afterwards so that s32[cur] is again the complete new state
-    return IOF32{h->s32[src].pt, h->s32[dst].vel, h->s32[dst].pt, h->s32[src].vel, h->d_src_sorted, h->d_ref_sorted};
+    return IOF32{h->s32[src].pt, h->s32[dst].vel, h->s32[dst].pt, h->s32[src].vel, h->d_src_sorted, h->slab.on ? (int)h->slab.halo_cap : 0,
+                 (h->flags & PLIFE_FLAG_UNSTABLE_SORT) ? 0 : 1, stable_key_of(h)};
 }
 
 static NextBin next_bin(plife_handle *h)
@@ -24,7 +25,7 @@ static NextBin next_bin(plife_handle *h)
 // The kernels read the old velocities from s32[cur].vel and write the new ones into s32[cur ^ 1].vel; swapping the two
 // pointers (launch_force_f32_done) makes s32[cur] = {new positions, new velocities} again for every other entry point.
 // `nblocks` CTAs of 128 targets; p.tr / p.n_dev select device-resident target ranges (slab mode).
-cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks)
+cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks, cudaStream_t stream)
 {
     const float *mt = (const float *)h->d_matrix_t;
     const float *mrow = mt + (size_t)p.m * p.m; // row-major copy follows the transposed one
@@ -37,9 +38,9 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
         int cap = (int)(kForceThreads + over + 8.0 * sqrt(rho + 1.0) + 32.0);
         cap = (cap + 31) / 32 * 32;
         if (cap > 1536) cap = 1536;
-        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h), h->stream);
+        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h), stream);
     }
-    return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mt, h->acc_kind, next_bin(h), h->stream);
+    return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mt, h->acc_kind, next_bin(h), stream);
 }
 
 void launch_force_f32_done(plife_handle *h)
@@ -52,7 +53,7 @@ void launch_force_f32_done(plife_handle *h)
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p)
 {
     if (p.n == 0) return cudaSuccess;
-    const cudaError_t e = launch_force_f32_part(h, p, (p.n + kForceThreads - 1) / kForceThreads);
+    const cudaError_t e = launch_force_f32_part(h, p, (p.n + kForceThreads - 1) / kForceThreads, h->stream);
     if (e == cudaSuccess) launch_force_f32_done(h);
     return e;
 }

@@ -32,7 +32,9 @@ struct IOF32 {
     float4 *__restrict__ pt_out;
     float2 *__restrict__ vel_out;         // the other velocity buffer; the launcher swaps the two afterwards
     const int32_t *__restrict__ src;      // pre-sort slot of sorted particle i
-    const int32_t *__restrict__ ref;      // slot of sorted particle i in the reference's order: where its result goes
+    int first;                            // sorted-array index of target 0
+    int stable;                           // 0: PLIFE_FLAG_UNSTABLE_SORT (results stay at the compute slot)
+    StableKey key;                        // previous-array-order key (slab mode: arrivals; else the identity)
     __device__ __forceinline__ Cand<float> cand(int j) const
     {
         float4 q = __ldg(pt + j);
@@ -46,7 +48,13 @@ struct IOF32 {
         vx = v.x;
         vy = v.y;
     }
-    __device__ __forceinline__ int out_slot(int i) const { return __ldg(ref + i); }
+    // where particle i's result goes: its slot in the reference's order (cells.cu: gather_f32)
+    __device__ __forceinline__ int out_slot(int i, int cxy, const int32_t *__restrict__ cell_end, const Grid &g)
+    {
+        if (!stable || g.ks == 0) return i;
+        key.load();
+        return reference_slot(i, cxy, src, cell_end, g, first, key);
+    }
     __device__ __forceinline__ void store(int o, float x, float y, float vx, float vy, int type, uint32_t id) const
     {
         pt_out[o] = make_float4(x, y, __int_as_float(type), __uint_as_float(id));
@@ -74,7 +82,7 @@ struct IOF64 {
         vx = v.x;
         vy = v.y;
     }
-    __device__ __forceinline__ int out_slot(int i) const { return i; } // fp64: the sorted order IS the reference's
+    __device__ __forceinline__ int out_slot(int i, int, const int32_t *, const Grid &) const { return i; } // fp64: the sorted order IS the reference's
     __device__ __forceinline__ void store(int o, double x, double y, double vx, double vy, int type, uint32_t id) const
     {
         out.pos[o] = make_double2(x, y);
@@ -571,7 +579,7 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
         nx_ = range_clamp(nx_);
         ny_ = range_clamp(ny_);
     }
-    const int o = io.out_slot(i);
+    const int o = io.out_slot(i, cxy, cell_end, P.g);
     io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
     nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, P.g);
 }
@@ -869,7 +877,7 @@ __global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 i
         nx_ = range_clamp(nx_);
         ny_ = range_clamp(ny_);
     }
-    const int o = io.out_slot(i);
+    const int o = io.out_slot(i, cxy, cell_end, g);
     io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
     nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, g);
 }
@@ -915,8 +923,9 @@ __global__ void __launch_bounds__(kForceThreads) neighbors_kernel(IO io, const i
     if (i >= P.n) return;
     const Cand<R> self = io.cand(P.first + i);
     NeighborVisitor<R> v{{0, 0ull}, P.r2};
-    traverse(io, cell_end, P.g, P.wrap, P.first + i, self.x, self.y, __ldg(cell_sorted + i), v);
-    const int o = io.out_slot(i); // reported in the reference's particle order
+    const int cxy = __ldg(cell_sorted + i);
+    traverse(io, cell_end, P.g, P.wrap, P.first + i, self.x, self.y, cxy, v);
+    const int o = io.out_slot(i, cxy, cell_end, P.g); // reported in the reference's particle order
     cnt[o] = v.d.count;
     hash[o] = v.d.hash;
 }

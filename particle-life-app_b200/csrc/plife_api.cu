@@ -75,8 +75,7 @@ void free_state(plife_handle *h)
     cudaFree(h->d_cell_sorted);
     cudaFree(h->d_src_sorted);
     cudaFree(h->d_perm);
-    cudaFree(h->d_ref_sorted);
-    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_ref_sorted = nullptr;
+    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = nullptr;
     h->cap = 0;
     h->prebinned = false;
 }
@@ -104,7 +103,6 @@ int ensure_capacity(plife_handle *h, int64_t n)
     CU(h, dev_alloc(&h->d_cell_sorted, c));
     CU(h, dev_alloc(&h->d_src_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
-    CU(h, dev_alloc(&h->d_ref_sorted, c));
     h->cap = n;
     return PLIFE_OK;
 }
@@ -158,13 +156,11 @@ int grow_preserve(plife_handle *h, int64_t cap)
     cudaFree(h->d_cell_sorted);
     cudaFree(h->d_src_sorted);
     cudaFree(h->d_perm);
-    cudaFree(h->d_ref_sorted);
-    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = h->d_ref_sorted = nullptr;
+    h->d_cell = h->d_cell_sorted = h->d_src_sorted = h->d_perm = nullptr;
     CU(h, dev_alloc(&h->d_cell, c));
     CU(h, dev_alloc(&h->d_cell_sorted, c));
     CU(h, dev_alloc(&h->d_src_sorted, c));
     CU(h, dev_alloc(&h->d_perm, c));
-    CU(h, dev_alloc(&h->d_ref_sorted, c));
     h->cap = cap;
     h->prebinned = false;
     h->has_sorted = false;
@@ -442,28 +438,39 @@ int slab_sort(plife_handle *h, const Grid &g)
 }
 // One of the two force launches of a slab step: targets = the device-resident ranges d_tr[0..3], staging clamped to
 // the bins [bin_lo, bin_hi] (the interior launch must not touch the ghost rows: they arrive later).
-cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_tr, int nblocks, int bin_lo, int bin_hi, bool first_part,
-                       bool last_part)
+cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_tr, int nblocks, int bin_lo, int bin_hi, cudaStream_t stream,
+                       bool first_part, bool last_part)
 {
-    StepTimer tm(h);
-    tm.t = h->slab_timing;
-    tm.on = h->slab_timing_on;
+    (void)last_part;
     cudaError_t e = cudaSuccess;
-    if (first_part) e = tm.mark(4);
+    if (first_part && h->slab_timing_on) { // profiling: event 4 = start of the force pass (main stream)
+        StepTimer tm(h);
+        tm.t = h->slab_timing;
+        tm.on = true;
+        e = tm.mark(4);
+        h->slab_timing = tm.t;
+    }
     ForceParams<float> p = make_params<float>(h, g, dt);
     p.tr = d_tr;
     p.bin_lo = bin_lo;
     p.bin_hi = bin_hi;
-    if (e == cudaSuccess) e = launch_force_f32_part(h, p, nblocks);
-    if (!last_part) {
-        h->slab_timing = tm.t;
-        return e;
-    }
-    if (e == cudaSuccess) launch_force_f32_done(h);
-    if (e == cudaSuccess) e = tm.mark(PLIFE_K_COUNT);
-    if (tm.on && e == cudaSuccess) {
-        h->pending.push_back(tm.t);
-        if (h->pending.size() >= 256 && resolve_timings(h) != PLIFE_OK) e = cudaErrorUnknown;
+    if (e == cudaSuccess) e = launch_force_f32_part(h, p, nblocks, stream);
+    return e;
+}
+// both launches are queued (and the main stream waits for the edge launch): the new state is the current one
+cudaError_t slab_force_done(plife_handle *h, const Grid &g)
+{
+    cudaError_t e = cudaSuccess;
+    launch_force_f32_done(h);
+    if (h->slab_timing_on) {
+        StepTimer tm(h);
+        tm.t = h->slab_timing;
+        tm.on = true;
+        e = tm.mark(PLIFE_K_COUNT);
+        if (e == cudaSuccess) {
+            h->pending.push_back(tm.t);
+            if (h->pending.size() >= 256 && resolve_timings(h) != PLIFE_OK) e = cudaErrorUnknown;
+        }
     }
     h->slab_timing_on = false;
     h->prebinned = true; // the epilogue binned the stayers; arrivals are binned by phase FINISH
@@ -1045,7 +1052,7 @@ int plife_debug_neighbors(plife_handle *h, int32_t *count, uint64_t *hash)
     // compute order with shifted types and the velocities never moved: write the reference order back into the
     // current buffers (records cur^1 -> cur, velocities cur -> cur^1 and swap those two)
     if (h->precision == PLIFE_F32) {
-        CU(h, launch_apply_sort_f32(h));
+        CU(h, launch_apply_sort_f32(h, g));
         float2 *t = h->s32[0].vel;
         h->s32[0].vel = h->s32[1].vel;
         h->s32[1].vel = t;

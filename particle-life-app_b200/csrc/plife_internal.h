@@ -96,6 +96,81 @@ __device__ __forceinline__ void cell_span(const int32_t *__restrict__ cell_end, 
     e = __ldg(cell_end + ((c_hi + 1) << ks) - 1);
 }
 
+// Logical position of pre-sort slot `src`.  Single GPU (cnt == nullptr): the identity.  Slab mode: the pre-sort array is
+// physically [residents 0..n_old) | arrivals from below (k_below) | arrivals from above]; the key puts the
+// three groups in the order of their previous GLOBAL array index, which is what the reference's stable
+// sort preserves: below < residents < above, except across the periodic seam, where rank 0's arrivals
+// from "below" come from the END of the global array and the last rank's arrivals from "above" from its
+// beginning.  The counts live in device memory (SlabCounts): the host does not know them when it queues the step.
+struct StableKey {
+    const SlabCounts *cnt = nullptr;
+    int order = 0; // 0: below, residents, above   1 (rank 0, periodic): residents, above, below   2 (last rank, periodic): above, below, residents
+    int n_old = 0x7fffffff, k_below = 0, base_res = 0, base_below = 0, base_above = 0;
+    __device__ __forceinline__ void load()
+    {
+        if (!cnt) return;
+        n_old = cnt->n_old;
+        k_below = cnt->k_below;
+        const int ka = cnt->k_above;
+        if (order == 1) { base_res = 0; base_below = n_old + ka; base_above = n_old; }
+        else if (order == 2) { base_res = ka + k_below; base_below = ka; base_above = 0; }
+        else { base_res = k_below; base_below = 0; base_above = k_below + n_old; }
+    }
+    __device__ __forceinline__ int operator()(int src) const
+    {
+        if (src < n_old) return src + base_res;
+        src -= n_old;
+        return src < k_below ? src + base_below : src - k_below + base_above;
+    }
+    __device__ __forceinline__ bool mixed(int max_src) const { return max_src >= n_old; } // the range holds an arrival
+};
+
+// number of entries of pp[s, e) (pre-sort slots of one cell or bin) that precede `src` in the previous array order;
+// pp + k is 16-byte aligned where (k - align) % 4 == 0
+__device__ __forceinline__ int stable_rank(const int32_t *__restrict__ pp, int s, int e, int src, int align, const StableKey &key)
+{
+    // Raw pre-sort indices order the residents exactly like their keys do, and almost every cell holds residents
+    // only, so rank on the raw indices (four per load: cells of an evolved state hold thousands of particles and
+    // this loop is O(count^2) per cell) and track the largest one; only cells that received migrants (slab mode)
+    // are ranked again through the key.
+    int rank = 0;
+    int mx = src;
+    int k = s;
+    for (; k < e && ((k - align) & 3); ++k) {
+        const int q = __ldg(pp + k);
+        rank += (q < src) ? 1 : 0;
+        mx = max(mx, q);
+    }
+    for (; k + 4 <= e; k += 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(pp + k));
+        rank += ((q.x < src) ? 1 : 0) + ((q.y < src) ? 1 : 0) + ((q.z < src) ? 1 : 0) + ((q.w < src) ? 1 : 0);
+        mx = max(max(mx, q.x), max(q.y, max(q.z, q.w)));
+    }
+    for (; k < e; ++k) {
+        const int q = __ldg(pp + k);
+        rank += (q < src) ? 1 : 0;
+        mx = max(mx, q);
+    }
+    if (key.mixed(mx)) {
+        rank = 0;
+        const int ksrc = key(src);
+        for (k = s; k < e; ++k) rank += (key(__ldg(pp + k)) < ksrc) ? 1 : 0;
+    }
+    return rank;
+}
+
+// Slot of sorted (compute-order) particle i in the REFERENCE order: its cell's start + its rank among the pre-sort slots
+// of the cell (B/Physics.java:343-348 is a stable scatter: inside a cell the previous array order is kept).  Per-target
+// numbering (no ghost-row offset); `key` must be loaded.  With ks == 0 the compute order is the reference order.
+__device__ __forceinline__ int reference_slot(int i, int cxy, const int32_t *__restrict__ src_sorted, const int32_t *__restrict__ cell_end,
+                                              const Grid &g, int first, const StableKey &key)
+{
+    if (g.ks == 0) return i;
+    const int c0 = (container_of(cxy, g) >> g.ks) << g.ks; // first bin of the cell (bins per row is a multiple of K)
+    const int cs = __ldg(cell_end + c0 - 1), ce = __ldg(cell_end + c0 + (1 << g.ks) - 1);
+    return cs - first + stable_rank(src_sorted - first, cs, ce, __ldg(src_sorted + i), first, key);
+}
+
 // Kernel parameters of the force/integrate pass for one step, in the
 // arithmetic type R of the handle.
 template <typename R>
@@ -162,6 +237,8 @@ struct SlabState {
     int *d_tr = nullptr;                 // device: target ranges of the force launches (pack_halo writes them), 12 ints
     volatile SlabCounts *h_ring = nullptr; // mapped pinned: the counts after each of the last 8 steps (written by slab_finish)
     cudaEvent_t step_done[4]{};          // recorded after each step's FINISH: bounds how far the host runs ahead
+    cudaStream_t side = nullptr;         // peer mode: high-priority stream for the halo traffic and the edge rows
+    cudaEvent_t ev_sorted = nullptr, ev_edge = nullptr;
     unsigned long long seq_known = 0;    // newest step whose counts the host has read
     int64_t n_bound = 0;                 // upper bound of n_phys the host sizes grids with
     int64_t max_arrivals = 0;            // largest number of arrivals seen in one step
@@ -209,7 +286,6 @@ struct plife_handle {
     int32_t *d_cell = nullptr;        // packed cell coords of particle i (pre-sort order)
     int32_t *d_cell_sorted = nullptr; // the same, permuted into sorted order
     int32_t *d_src_sorted = nullptr;  // fp32: pre-sort slot of every sorted particle (velocities are read through it)
-    int32_t *d_ref_sorted = nullptr;  // fp32: slot of every sorted particle in the reference's order (where its result is written)
     int32_t *d_perm = nullptr; // source index of sorted slot d
     void *d_snap = nullptr;    // snapshot staging (download_f32)
     int64_t snap_cap = 0;
@@ -259,7 +335,8 @@ cudaError_t launch_bin(plife_handle *h, const Grid &g);
 cudaError_t launch_scan(plife_handle *h, const Grid &g);
 cudaError_t launch_scatter(plife_handle *h, const Grid &g);
 cudaError_t launch_gather(plife_handle *h, const Grid &g);
-cudaError_t launch_apply_sort_f32(plife_handle *h);
+cudaError_t launch_apply_sort_f32(plife_handle *h, const Grid &g);
+StableKey stable_key_of(const plife_handle *h);
 cudaError_t launch_containers(plife_handle *h, const Grid &g, int32_t *d_out);
 cudaError_t launch_type_histogram(plife_handle *h, unsigned long long *d_hist);
 cudaError_t launch_init_uniform(plife_handle *h, int64_t n, uint64_t seed);
@@ -268,7 +345,7 @@ cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32
 
 // force_f32.cu / force_f64.cu
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p);
-cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks); // slab mode: one of the two launches
+cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks, cudaStream_t stream); // slab mode: one of the two launches
 void launch_force_f32_done(plife_handle *h);                                                  // ... then swap the velocity buffers
 cudaError_t launch_force_f64(plife_handle *h, const ForceParams<double> &p);
 cudaError_t launch_neighbors_f32(plife_handle *h, const ForceParams<float> &p, int32_t *cnt, unsigned long long *hash);

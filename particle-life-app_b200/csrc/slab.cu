@@ -41,8 +41,9 @@ namespace plife {
 int slab_make_grid(plife_handle *h, Grid *g);
 int slab_sort(plife_handle *h, const Grid &g);
 int slab_fail(plife_handle *h, int code, const char *msg);
-cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_tr, int nblocks, int bin_lo, int bin_hi, bool first_part,
-                       bool last_part);
+cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_tr, int nblocks, int bin_lo, int bin_hi, cudaStream_t stream,
+                       bool first_part, bool last_part);
+cudaError_t slab_force_done(plife_handle *h, const Grid &g);
 int slab_reset_capacity(plife_handle *h);
 } // namespace plife
 
@@ -105,12 +106,9 @@ __device__ __forceinline__ void signal_when_all_done(unsigned int *ticket, volat
 // dir 1: last owned row (local row nly-2) -> becomes the up neighbour's bottom ghost row
 // `msg0/msg1` are where the two messages are written: the local send buffers (external exchange), or - peer exchange -
 // straight into the neighbours' receive slots over NVLink, followed by the flag (flag0/flag1 non-NULL).
-// Block (0,0) also resets this step's migration cursors and writes the target ranges of the two force launches:
-//   tr[0..3] = interior rows {s, e, 0, 0}      tr[4..7] = first and last owned row {0, s, e, n}     tr[8..11] = all
+// (The target ranges of the force launches and the migration cursors are prepared by the gather kernel, cells.cu.)
 __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__ pt_sorted, const int32_t *__restrict__ cell_end,
-                                                      Grid g, int halo_cap, int first, const SlabCounts *__restrict__ cnt,
-                                                      float4 *__restrict__ msg0, float4 *__restrict__ msg1,
-                                                      float4 *__restrict__ mig0, float4 *__restrict__ mig1, int *__restrict__ tr,
+                                                      Grid g, int halo_cap, float4 *__restrict__ msg0, float4 *__restrict__ msg1,
                                                       volatile unsigned long long *flag0, volatile unsigned long long *flag1,
                                                       unsigned int *tickets, unsigned long long seq)
 {
@@ -118,17 +116,6 @@ __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__
     float4 *msg = dir ? msg1 : msg0;
     volatile unsigned long long *flag = dir ? flag1 : flag0;
     const int nxk = g.nxk(); // the message carries one END offset per fine bin of the row
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        (dir ? mig1 : mig0)[0] = make_float4(0.f, 0.f, 0.f, 0.f); // this step's migration cursor
-        if (dir == 0) {
-            const int n = cnt->n;
-            const int e1 = __ldg(cell_end + 2 * nxk - 1) - first;           // end of the first owned row
-            const int sl = __ldg(cell_end + (g.nly - 2) * nxk - 1) - first; // start of the last owned row
-            tr[0] = e1; tr[1] = sl; tr[2] = 0; tr[3] = 0;
-            tr[4] = 0; tr[5] = e1; tr[6] = sl; tr[7] = n;
-            tr[8] = 0; tr[9] = n; tr[10] = 0; tr[11] = 0; // the whole sorted block (plife_get_step_stats)
-        }
-    }
     const int row = dir ? g.nly - 2 : 1;
     const int start = __ldg(cell_end + row * nxk - 1);
     const int end = __ldg(cell_end + (row + 1) * nxk - 1);
@@ -343,6 +330,9 @@ void slab_release(plife_handle *h)
     cudaFree(S.d_tr);
     for (int k = 0; k < 4; k++)
         if (S.step_done[k]) cudaEventDestroy(S.step_done[k]);
+    if (S.ev_sorted) cudaEventDestroy(S.ev_sorted);
+    if (S.ev_edge) cudaEventDestroy(S.ev_edge);
+    if (S.side) cudaStreamDestroy(S.side);
     if (S.peer_mode) {
         cudaFree(S.xbuf);
         for (int d = 0; d < 2; d++) {
@@ -487,6 +477,13 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
     if (e == cudaSuccess) e = cudaMemset(S.d_tr, 0, 12 * sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&S.h_ring, 8 * sizeof(SlabCounts), cudaHostAllocMapped);
     for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&S.step_done[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev_sorted, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev_edge, cudaEventDisableTiming);
+    if (e == cudaSuccess && S.peer_mode) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi); // hi = greatest priority (numerically lowest)
+        e = cudaStreamCreateWithPriority(&S.side, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         slab_release(h);
@@ -596,6 +593,12 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
     }
     unsigned int *tickets = S.peer_mode ? reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(S.xbuf) + F_TICKETS) : nullptr; // 4 local counters
 
+    // Peer exchange: the halo traffic and the two edge rows run on a second, high-priority stream next to the interior
+    // force launch, so neither the wait for the neighbours nor the tail of the small edge launch is on the critical path:
+    //   main:  scan, scatter, gather -> [sorted]      force(interior) ................ wait [edge] -> push migrants, finish
+    //   side:              wait [sorted] -> pack halo (push + signal), wait + unpack halo, force(edge rows) -> [edge]
+    // External exchange (the host moves the messages between the phases): everything stays on the main stream.
+    cudaStream_t side = S.peer_mode ? S.side : h->stream;
     if (phase == PLIFE_SLAB_SORT) {
         // no more than 3 steps queued ahead of the device: bounds the slack of the launch bound and the count ring
         if (S.seq > 4) CUS(h, cudaEventSynchronize(S.step_done[(S.seq - 4) & 3]));
@@ -607,16 +610,17 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         const int sorted = h->cur ^ 1;
         dim3 grid(32, 2);
         if (S.peer_mode) {
+            CUS(h, cudaEventRecord(S.ev_sorted, h->stream));
+            CUS(h, cudaStreamWaitEvent(side, S.ev_sorted, 0));
             // my first row is the down neighbour's ghost row ABOVE its slab (its slot dir 1), and vice versa; the pack kernel
             // writes it there and raises the neighbour's flag when its last CTA is done
-            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, first, S.counts,
-                                                        has_dn ? halo_slot(dn, S, parity, 1) : S.halo_send[0],
-                                                        has_up ? halo_slot(up, S, parity, 0) : S.halo_send[1], S.mig_send[0], S.mig_send[1], S.d_tr,
-                                                        has_dn ? flag_of(dn, F_HALO_UP) : nullptr, has_up ? flag_of(up, F_HALO_DN) : nullptr,
-                                                        tickets, S.seq);
+            pack_halo<<<grid, kThreads, 0, side>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap,
+                                                   has_dn ? halo_slot(dn, S, parity, 1) : S.halo_send[0],
+                                                   has_up ? halo_slot(up, S, parity, 0) : S.halo_send[1],
+                                                   has_dn ? flag_of(dn, F_HALO_UP) : nullptr, has_up ? flag_of(up, F_HALO_DN) : nullptr, tickets, S.seq);
         } else {
-            pack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, first, S.counts, S.halo_send[0],
-                                                        S.halo_send[1], S.mig_send[0], S.mig_send[1], S.d_tr, nullptr, nullptr, nullptr, 0ull);
+            pack_halo<<<grid, kThreads, 0, side>>>(h->s32[sorted].pt, h->d_cell_end, g, (int)S.halo_cap, S.halo_send[0], S.halo_send[1], nullptr,
+                                                   nullptr, nullptr, 0ull);
         }
         CUS(h, cudaGetLastError());
         S.phase = PLIFE_SLAB_FORCE;
@@ -626,18 +630,22 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         const int sorted = h->cur ^ 1;
         const bool peer = S.peer_mode;
         const int nxk = g.nxk();
-        // interior rows first: they read owned rows only, so the halo may still be in flight (peer mode; with the external
-        // exchange the halo is already here and the split only costs a launch)
+        // interior rows: they read owned rows only, so the halo may still be in flight
         const int nb_all = (int)((S.n_bound + 127) / 128) + 1;
         const int nb_edge = (int)((2 * S.halo_cap + 127) / 128) + 2;
-        CUS(h, slab_force(h, g, dt, S.d_tr, nb_all, nxk, (g.nly - 1) * nxk - 1, true, false));
+        CUS(h, slab_force(h, g, dt, S.d_tr, nb_all, nxk, (g.nly - 1) * nxk - 1, h->stream, true, false));
         dim3 grid(32, 2);
-        unpack_halo<<<grid, kThreads, 0, h->stream>>>(h->s32[sorted].pt, h->d_cell_end, g, first, S.counts,
-                                                      has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr,
-                                                      peer && has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr,
-                                                      peer && has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq, S.spin_ns);
+        unpack_halo<<<grid, kThreads, 0, side>>>(h->s32[sorted].pt, h->d_cell_end, g, first, S.counts,
+                                                 has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr,
+                                                 peer && has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr,
+                                                 peer && has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq, S.spin_ns);
         CUS(h, cudaGetLastError());
-        CUS(h, slab_force(h, g, dt, S.d_tr + 4, nb_edge, 0, nxk * g.nly - 1, false, true));
+        CUS(h, slab_force(h, g, dt, S.d_tr + 4, nb_edge, 0, nxk * g.nly - 1, side, false, true));
+        if (S.peer_mode) {
+            CUS(h, cudaEventRecord(S.ev_edge, side));
+            CUS(h, cudaStreamWaitEvent(h->stream, S.ev_edge, 0));
+        }
+        CUS(h, slab_force_done(h, g));
         if (S.peer_mode && (has_dn || has_up)) {
             dim3 pg(8, 2);
             push_mig<<<pg, kThreads, 0, h->stream>>>(S.mig_send[0], S.mig_send[1], has_dn ? mig_slot(dn, S, parity, 1) : nullptr,
