@@ -694,10 +694,10 @@ def run_ours(args):
 
 
 def launches_per_step(world, exchange):
-    # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add the halo pack
-    # (writes into the neighbours' memory and signals), the halo wait + unpack, 2 migration pushes (with signal) and the
-    # wait-and-collect of phase FINISH; arrival appends are not counted
-    return 6 if world == 1 else (11 if exchange == "peer" else 9)
+    # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add the halo pack (written into
+    # the neighbours' memory, then a flag), the halo wait + unpack, a second force launch (interior rows / edge rows) and ONE
+    # kernel for phase FINISH (push migrants + wait + new counts + append arrivals)
+    return 6 if world == 1 else 10
 
 
 def main():

@@ -234,7 +234,8 @@ struct SlabState {
     bool peer_ipc[2]{};
     // device-resident counts: a step needs no host synchronisation
     SlabCounts *counts = nullptr;        // device
-    int *d_tr = nullptr;                 // device: target ranges of the force launches (pack_halo writes them), 12 ints
+    int *d_tr = nullptr;                 // device: target ranges of the force launches (the gather kernel writes them), 12 ints
+    volatile unsigned long long *d_go = nullptr; // device: the finish CTA releases the append CTAs of the same launch
     volatile SlabCounts *h_ring = nullptr; // mapped pinned: the counts after each of the last 8 steps (written by slab_finish)
     cudaEvent_t step_done[4]{};          // recorded after each step's FINISH: bounds how far the host runs ahead
     cudaStream_t side = nullptr;         // peer mode: high-priority stream for the halo traffic and the edge rows

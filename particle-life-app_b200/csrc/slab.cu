@@ -175,85 +175,97 @@ __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_
     for (int k = t; k < count; k += gridDim.x * kThreads) pt_sorted[base + k] = __ldcg(msg + 1 + noff + k);
 }
 
-// copy the two migration messages (their used records only) into the neighbours' receive slots; blockIdx.y = direction
-__global__ void __launch_bounds__(kThreads) push_mig(const float4 *__restrict__ local0, const float4 *__restrict__ local1,
-                                                     float4 *__restrict__ peer0, float4 *__restrict__ peer1, int cap,
-                                                     volatile unsigned long long *flag0, volatile unsigned long long *flag1,
-                                                     unsigned int *tickets, unsigned long long seq)
+// Phase FINISH as ONE kernel of a few co-resident CTAs (gridDim = (kMigCtas, 2), blockIdx.y = direction):
+//   push    every CTA copies its share of the two migration messages (their used records only) into the neighbours'
+//           receive slots over NVLink; the last CTA per direction raises the neighbour's flag (peer mode)
+//   finish  CTA (0,0): wait for the neighbours' messages, validate the four headers, compute the counts of the next
+//           step, publish them (device struct + the host's ring in mapped pinned memory), then release the other CTAs
+//   append  every CTA places its share of the arrivals.  Message records {x,y,type,id},{vx,vy,source slot,-}: each
+//           goes to base + (rank of its source slot among the arrivals of the same message) - the sender appended them
+//           with an atomic cursor, the rank restores the sender's array order - and is binned.
+// The CTAs wait for each other inside the kernel, so all of them must be resident: the grid is 16 CTAs.
+constexpr int kMigCtas = 8;
+
+__global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restrict__ ms0, const float4 *__restrict__ ms1, float4 *peer0, float4 *peer1,
+                                                         volatile unsigned long long *pflag0, volatile unsigned long long *pflag1,
+                                                         unsigned int *tickets, const volatile unsigned long long *f0,
+                                                         const volatile unsigned long long *f1, unsigned long long seq, SlabCounts *cnt,
+                                                         const float4 *mi0, const float4 *mi1, int has_dn, int has_up, int mig_cap, int cap, int bound,
+                                                         volatile SlabCounts *ring, volatile unsigned long long *go, unsigned long long spin_ns, Grid g,
+                                                         float4 *__restrict__ pt, float2 *__restrict__ vel, int32_t *__restrict__ cell,
+                                                         int32_t *__restrict__ count)
 {
     const int dir = blockIdx.y;
-    const float4 *local = dir ? local1 : local0;
-    float4 *peer = dir ? peer1 : peer0;
-    if (!peer) return;
-    const int count = *reinterpret_cast<const int *>(local);
-    const int nrec = 1 + 2 * min(count, cap);
-    for (int k = blockIdx.x * kThreads + threadIdx.x; k < nrec; k += gridDim.x * kThreads) peer[k] = local[k];
-    signal_when_all_done(tickets + dir, dir ? flag1 : flag0, seq, gridDim.x);
-}
-
-// Phase FINISH, one thread: wait for the neighbours' migration messages (peer mode), validate the four headers, compute
-// the counts of the next step and publish them where the host can read them later without a synchronisation.
-__global__ void slab_finish(const volatile unsigned long long *f0, const volatile unsigned long long *f1, unsigned long long seq,
-                            SlabCounts *cnt, const float4 *ms0, const float4 *ms1, const float4 *mi0, const float4 *mi1,
-                            int has_dn, int has_up, int mig_cap, int cap, int bound, volatile SlabCounts *ring, unsigned long long spin_ns)
-{
-    if (threadIdx.x != 0) return;
-    int err = cnt->err;
-    if (f0 && !wait_flag(f0, seq, spin_ns)) err |= kErrTimeout;
-    if (f1 && !wait_flag(f1, seq, spin_ns)) err |= kErrTimeout;
-    const volatile int *s0 = reinterpret_cast<const volatile int *>(ms0), *s1 = reinterpret_cast<const volatile int *>(ms1);
-    const int sent_dn = s0[0], sent_up = s1[0];
-    if (s0[1] || s1[1]) err |= kErrFar;
-    if ((!has_dn && sent_dn) || (!has_up && sent_up)) err |= kErrClosed;
-    int k_below = 0, k_above = 0;
-    if (!(err & kErrTimeout)) {
-        if (has_dn && mi0) k_below = reinterpret_cast<const volatile int *>(mi0)[0];
-        if (has_up && mi1) k_above = reinterpret_cast<const volatile int *>(mi1)[0];
+    // ---- push ----
+    {
+        const float4 *local = dir ? ms1 : ms0;
+        float4 *peer = dir ? peer1 : peer0;
+        if (peer) {
+            const int c = *reinterpret_cast<const int *>(local);
+            const int nrec = 1 + 2 * min(c, mig_cap);
+            for (int k = blockIdx.x * kThreads + threadIdx.x; k < nrec; k += gridDim.x * kThreads) peer[k] = local[k];
+            signal_when_all_done(tickets + dir, dir ? pflag1 : pflag0, seq, gridDim.x);
+        }
     }
-    if (sent_dn > mig_cap || sent_up > mig_cap || k_below > mig_cap || k_above > mig_cap) {
-        err |= kErrMigCap;
-        k_below = min(k_below, mig_cap);
-        k_above = min(k_above, mig_cap);
+    // ---- finish ----
+    if (blockIdx.x == 0 && dir == 0) {
+        if (threadIdx.x == 0) {
+            int err = cnt->err;
+            if (f0 && !wait_flag(f0, seq, spin_ns)) err |= kErrTimeout;
+            if (f1 && !wait_flag(f1, seq, spin_ns)) err |= kErrTimeout;
+            const volatile int *s0 = reinterpret_cast<const volatile int *>(ms0), *s1 = reinterpret_cast<const volatile int *>(ms1);
+            const int sent_dn = s0[0], sent_up = s1[0];
+            if (s0[1] || s1[1]) err |= kErrFar;
+            if ((!has_dn && sent_dn) || (!has_up && sent_up)) err |= kErrClosed;
+            int k_below = 0, k_above = 0;
+            if (!(err & kErrTimeout)) {
+                if (has_dn && mi0) k_below = reinterpret_cast<const volatile int *>(mi0)[0];
+                if (has_up && mi1) k_above = reinterpret_cast<const volatile int *>(mi1)[0];
+            }
+            if (sent_dn > mig_cap || sent_up > mig_cap || k_below > mig_cap || k_above > mig_cap) {
+                err |= kErrMigCap;
+                k_below = min(k_below, mig_cap);
+                k_above = min(k_above, mig_cap);
+            }
+            const int L = cnt->n; // residents before this step (the force pass wrote slots [0, L))
+            if (L + k_below + k_above > cap) {
+                err |= kErrCapacity;
+                k_below = k_above = 0;
+            }
+            if (L > bound || cnt->n_phys > bound) err |= kErrBound;
+            SlabCounts c;
+            c.n_old = L;
+            c.k_below = k_below;
+            c.k_above = k_above;
+            c.n_phys = L + k_below + k_above;
+            c.n = L - min(sent_dn, mig_cap) - min(sent_up, mig_cap) + k_below + k_above;
+            c.err = err;
+            c.sent_dn = sent_dn;
+            c.sent_up = sent_up;
+            c.seq = seq;
+            *cnt = c;
+            volatile SlabCounts *r = ring + (seq & 7);
+            r->seq = 0;
+            __threadfence_system();
+            r->n = c.n; r->n_phys = c.n_phys; r->n_old = c.n_old; r->k_below = c.k_below; r->k_above = c.k_above;
+            r->err = c.err; r->sent_dn = c.sent_dn; r->sent_up = c.sent_up;
+            __threadfence_system();
+            r->seq = seq;
+            __threadfence();
+            *go = seq; // release the other CTAs of this kernel
+        }
+    } else if (threadIdx.x == 0) {
+        const unsigned long long t0 = wall_ns();
+        while (*go < seq && wall_ns() - t0 < 2 * spin_ns) __nanosleep(50);
+        __threadfence();
     }
-    const int L = cnt->n; // residents before this step (the force pass wrote slots [0, L))
-    if (L + k_below + k_above > cap) {
-        err |= kErrCapacity;
-        k_below = k_above = 0;
-    }
-    if (L > bound || cnt->n_phys > bound) err |= kErrBound;
-    SlabCounts c;
-    c.n_old = L;
-    c.k_below = k_below;
-    c.k_above = k_above;
-    c.n_phys = L + k_below + k_above;
-    c.n = L - min(sent_dn, mig_cap) - min(sent_up, mig_cap) + k_below + k_above;
-    c.err = err;
-    c.sent_dn = sent_dn;
-    c.sent_up = sent_up;
-    c.seq = seq;
-    *cnt = c;
-    volatile SlabCounts *r = ring + (seq & 7);
-    r->seq = 0;
-    __threadfence_system();
-    r->n = c.n; r->n_phys = c.n_phys; r->n_old = c.n_old; r->k_below = c.k_below; r->k_above = c.k_above;
-    r->err = c.err; r->sent_dn = c.sent_dn; r->sent_up = c.sent_up;
-    __threadfence_system();
-    r->seq = seq;
-    __threadfence_system();
-}
-
-// Arrivals: message records {x,y,type,id},{vx,vy,source slot,-}.  Each is placed at
-// base + (rank of its source slot among the arrivals of the same message): the sender appended them
-// with an atomic cursor, the rank restores the sender's array order.  blockIdx.y = 0: from below, 1: from above.
-__global__ void __launch_bounds__(kThreads) append_arrivals(const float4 *msg0, const float4 *msg1, SlabCounts *__restrict__ cnt, Grid g,
-                                                            float4 *__restrict__ pt, float2 *__restrict__ vel,
-                                                            int32_t *__restrict__ cell, int32_t *__restrict__ count)
-{
-    const int which = blockIdx.y;
-    const float4 *msg = which ? msg1 : msg0;
-    const int k = which ? cnt->k_above : cnt->k_below;
+    __syncthreads();
+    // ---- append ----
+    const float4 *msg = dir ? mi1 : mi0;
+    const volatile SlabCounts *vc = cnt;
+    const int k = dir ? vc->k_above : vc->k_below;
     if (!msg || k == 0) return;
-    const int base = cnt->n_old + (which ? cnt->k_below : 0);
+    const int base = vc->n_old + (dir ? vc->k_below : 0);
     for (int j = blockIdx.x * kThreads + threadIdx.x; j < k; j += gridDim.x * kThreads) {
         const float4 a = __ldcg(msg + 1 + 2 * j), b = __ldcg(msg + 2 + 2 * j);
         const int src = __float_as_int(b.z);
@@ -328,6 +340,7 @@ void slab_release(plife_handle *h)
     if (S.h_ring) cudaFreeHost((void *)S.h_ring);
     cudaFree(S.counts);
     cudaFree(S.d_tr);
+    cudaFree((void *)S.d_go);
     for (int k = 0; k < 4; k++)
         if (S.step_done[k]) cudaEventDestroy(S.step_done[k]);
     if (S.ev_sorted) cudaEventDestroy(S.ev_sorted);
@@ -473,6 +486,8 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
     }
     cudaError_t e = cudaMalloc((void **)&S.counts, sizeof(SlabCounts));
     if (e == cudaSuccess) e = cudaMemset(S.counts, 0, sizeof(SlabCounts));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&S.d_go, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset((void *)S.d_go, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc((void **)&S.d_tr, 12 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(S.d_tr, 0, 12 * sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&S.h_ring, 8 * sizeof(SlabCounts), cudaHostAllocMapped);
@@ -646,30 +661,20 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
             CUS(h, cudaStreamWaitEvent(h->stream, S.ev_edge, 0));
         }
         CUS(h, slab_force_done(h, g));
-        if (S.peer_mode && (has_dn || has_up)) {
-            dim3 pg(8, 2);
-            push_mig<<<pg, kThreads, 0, h->stream>>>(S.mig_send[0], S.mig_send[1], has_dn ? mig_slot(dn, S, parity, 1) : nullptr,
-                                                     has_up ? mig_slot(up, S, parity, 0) : nullptr, (int)S.mig_cap,
-                                                     has_dn ? flag_of(dn, F_MIG_UP) : nullptr, has_up ? flag_of(up, F_MIG_DN) : nullptr,
-                                                     tickets + 2, S.seq);
-            CUS(h, cudaGetLastError());
-        }
         S.phase = PLIFE_SLAB_FINISH;
         return PLIFE_OK;
     }
-    // PLIFE_SLAB_FINISH
+    // PLIFE_SLAB_FINISH: push the migrants, wait for the neighbours', new counts, append the arrivals - one launch
     {
-        const bool waits = S.peer_mode;
-        slab_finish<<<1, 32, 0, h->stream>>>(waits && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, waits && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr,
-                                             S.seq, S.counts, S.mig_send[0], S.mig_send[1], has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr,
-                                             has_dn ? 1 : 0, has_up ? 1 : 0, (int)S.mig_cap, (int)h->cap, (int)S.n_bound, S.h_ring, S.spin_ns);
+        const bool peer = S.peer_mode;
+        dim3 mg(kMigCtas, 2);
+        slab_migrate<<<mg, kThreads, 0, h->stream>>>(
+            S.mig_send[0], S.mig_send[1], peer && has_dn ? mig_slot(dn, S, parity, 1) : nullptr, peer && has_up ? mig_slot(up, S, parity, 0) : nullptr,
+            peer && has_dn ? flag_of(dn, F_MIG_UP) : nullptr, peer && has_up ? flag_of(up, F_MIG_DN) : nullptr, peer ? tickets + 2 : nullptr,
+            peer && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, peer && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr, S.seq, S.counts,
+            has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr, has_dn ? 1 : 0, has_up ? 1 : 0, (int)S.mig_cap, (int)h->cap, (int)S.n_bound,
+            S.h_ring, S.d_go, S.spin_ns, g, h->s32[h->cur].pt, h->s32[h->cur].vel, h->d_cell, h->d_count);
         CUS(h, cudaGetLastError());
-        if (has_dn || has_up) {
-            dim3 ag(16, 2);
-            append_arrivals<<<ag, kThreads, 0, h->stream>>>(has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr, S.counts, g, h->s32[h->cur].pt,
-                                                            h->s32[h->cur].vel, h->d_cell, h->d_count);
-            CUS(h, cudaGetLastError());
-        }
         CUS(h, cudaEventRecord(S.step_done[S.seq & 3], h->stream));
     }
     S.phase = PLIFE_SLAB_SORT;
