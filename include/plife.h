@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PLIFE_VERSION 100 /* 0.1.0 */
+#define PLIFE_VERSION 200 /* 0.2.0: plife_config.bins, plife_step_stats.graph_steps, plife_rebuild, host-free slab steps */
 
 /* status codes */
 #define PLIFE_OK 0
@@ -46,7 +46,8 @@ extern "C" {
 
 /* plife_config.flags */
 #define PLIFE_FLAG_UNSTABLE_SORT 1 /* skip the in-cell stable ordering (faster; order in a cell arbitrary) */
-#define PLIFE_FLAG_NO_GRAPH 2      /* reserved: this version never captures the step into a CUDA graph */
+#define PLIFE_FLAG_NO_GRAPH 2      /* never replay the step as a CUDA graph (default: captured below 262144 particles, once the
+                                      settings have been stable for two steps; any change of dt, settings or particles re-captures) */
 /* 16 was PLIFE_FLAG_PAIRS (round 1's experimental two-targets-per-lane kernel, removed); the bit is ignored */
 #define PLIFE_FLAG_NO_FUSED_BIN 8  /* do not fuse the next step's binning into the force pass */
 #define PLIFE_FLAG_FORCE_V1 4      /* fp32: use the global-memory force kernel instead of the shared-memory staged one */
@@ -89,6 +90,7 @@ typedef struct plife_step_stats {
     int32_t nx, ny;     /* grid, B/Physics.java:82-85 */
     int64_t pair_evals; /* candidate pairs (i,j), j != i, in the 3x3 cells: B/Physics.java:423-439 */
     int64_t steps;      /* steps executed by this handle so far */
+    int64_t graph_steps; /* ... of which replayed from a captured CUDA graph (launch-bound regime, see PLIFE_FLAG_NO_GRAPH) */
 } plife_step_stats;
 
 /* slots of plife_kernel_times() */
@@ -220,6 +222,17 @@ int plife_cursor_delete(plife_handle *h, const plife_cursor *c, int64_t *removed
 /* cursor action BRUSH / growing setParticleCount (A/Main.java:550-566, B/Physics.java:212-220): appends k particles
  * sampled by the caller's setters; ids continue after the largest id seen; vel_xy may be NULL */
 int plife_append(plife_handle *h, int64_t k, const double *pos_xy, const double *vel_xy, const int32_t *type);
+
+/* Physics.setParticleCount incl. its shuffle-before-shrink (B/Physics.java:190-223, :278-280), ensureTypes (:266-272), setTypes
+ * (:509-511), ExtendedPhysics.setTypeCount / setTypeCountEqual (A/ExtendedPhysics.java:28-130) all rearrange, retype, drop or
+ * create particles by rules that depend on the TYPES only (plus the host-side setter plugins for new positions).  The host
+ * plans the new array from the types (plife_download_f32 with only `type`: 4 bytes per particle) and the device applies it:
+ *   new particle k = old particle src[k] (src[k] >= 0; its id, position and velocity are kept) or a new one (src[k] < 0);
+ *   type[k] is its type; if place[k] >= 0 (place may be NULL: nobody is placed) its position becomes placed_xy[place[k]] and
+ *   its velocity zero, as Physics.setPosition does (B/Physics.java:297-303).  New particles must be placed; they get the ids
+ *   next_id + place[k].  n_placed = number of (x, y) pairs in placed_xy. */
+int plife_rebuild(plife_handle *h, int64_t n_new, const int32_t *src, const int32_t *type, const int32_t *place, int64_t n_placed,
+                  const double *placed_xy);
 
 /* ---- multi-GPU slab decomposition (one process per GPU) ----
  * Rank g owns grid rows [g*ny/G, (g+1)*ny/G).  The library packs / unpacks the halo and migration

@@ -172,6 +172,47 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
     }
 }
 
+// ---- small grids: histogram, scan and cursor scatter in ONE CTA ----
+// Up to kSmallBins bins and kSmallN particles (BASELINE config 1: 10 000 particles, 25 x 25 cells) the step is bound by
+// launch latency, not by work: the five launches of K_BIN's consumers (3 scan + scatter) become one.  The histogram lives
+// in shared memory and is rebuilt from the cached bin words, so the force pass does not count in this mode.
+constexpr int kSmallThreads = 1024;
+
+__global__ void __launch_bounds__(kSmallThreads) small_sort(const int32_t *__restrict__ cell, int n_phys, Grid g, int nbins,
+                                                            int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
+{
+    extern __shared__ int s_cnt[]; // [nbins]
+    __shared__ int sm[33];
+    const int tid = threadIdx.x;
+    for (int b = tid; b < nbins; b += kSmallThreads) s_cnt[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_phys; i += kSmallThreads) {
+        const int c = container_of(__ldg(&cell[i]), g);
+        if (c >= 0) atomicAdd(&s_cnt[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan: thread t owns the bins [t*B, (t+1)*B)
+    const int B = (nbins + kSmallThreads - 1) / kSmallThreads;
+    const int b0 = tid * B, b1 = min(b0 + B, nbins);
+    int local = 0;
+    for (int b = b0; b < b1; ++b) local += s_cnt[b];
+    int total;
+    int ex = block_exclusive_scan(local, total, sm);
+    for (int b = b0; b < b1; ++b) {
+        const int c = s_cnt[b];
+        s_cnt[b] = ex; // cursor = start of the bin
+        ex += c;
+    }
+    if (tid == 0) cell_end[-1] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_phys; i += kSmallThreads) { // B/Physics.java:343-348 (order inside a bin is fixed by K_GATHER)
+        const int c = container_of(__ldg(&cell[i]), g);
+        if (c >= 0) perm[atomicAdd(&s_cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    for (int b = tid; b < nbins; b += kSmallThreads) cell_end[b] = s_cnt[b]; // END offsets, like `containers`
+}
+
 // B/Physics.java:343-348: `i = containers[ci]; buffer[i] = p; containers[ci]++`.
 // Afterwards cell_end[b] is the END offset of bin b, as in the reference (per cell: every K-th entry).
 constexpr int kScatterUnroll = 4; // measured: 1 -> 0.078 ms, 4 -> 0.056 ms at 16M particles
@@ -527,6 +568,13 @@ cudaError_t launch_bin(plife_handle *h, const Grid &g)
         bin_f32<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s32[h->cur].pt, n, g, h->d_cell, h->d_count);
     else
         bin_f64<<<blocks_for(n, kThreads), kThreads, 0, h->stream>>>(h->s64[h->cur].pos, n, g, h->d_cell, h->d_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_small_sort(plife_handle *h, const Grid &g)
+{
+    const int nbins = g.nxk() * g.nly;
+    small_sort<<<1, kSmallThreads, sizeof(int) * nbins, h->stream>>>(h->d_cell, (int)h->n_phys, g, nbins, h->d_cell_end, h->d_perm);
     return cudaGetLastError();
 }
 

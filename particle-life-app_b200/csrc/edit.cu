@@ -220,6 +220,58 @@ int make_cursor(plife_handle *h, const plife_cursor *c, CursorArgs *a)
     return PLIFE_OK;
 }
 
+// plife_rebuild: new particle k = old particle src[k] (src[k] >= 0) or a new one; its type is type[k]; where place[k] >= 0 the
+// position is placed[place[k]] and the velocity zero (Physics.setPosition, B/Physics.java:297-303)
+__global__ void __launch_bounds__(kThreads) rebuild_f32(StateF32 in, StateF32 out, int n_new, const int32_t *__restrict__ src,
+                                                        const int32_t *__restrict__ type, const int32_t *__restrict__ place,
+                                                        const double2 *__restrict__ placed, uint32_t next_id)
+{
+    const int k = blockIdx.x * kThreads + threadIdx.x;
+    if (k >= n_new) return;
+    const int s = src[k], pl = place ? place[k] : -1;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 v = make_float2(0.f, 0.f);
+    if (s >= 0) {
+        p = in.pt[s];
+        v = in.vel[s];
+    } else {
+        p.w = __uint_as_float(next_id + (uint32_t)pl);
+    }
+    p.z = __int_as_float(type[k]);
+    if (pl >= 0) {
+        const double2 q = placed[pl];
+        p.x = (float)q.x;
+        p.y = (float)q.y;
+        v = make_float2(0.f, 0.f);
+    }
+    out.pt[k] = p;
+    out.vel[k] = v;
+}
+
+__global__ void __launch_bounds__(kThreads) rebuild_f64(StateF64 in, StateF64 out, int n_new, const int32_t *__restrict__ src,
+                                                        const int32_t *__restrict__ type, const int32_t *__restrict__ place,
+                                                        const double2 *__restrict__ placed, uint32_t next_id)
+{
+    const int k = blockIdx.x * kThreads + threadIdx.x;
+    if (k >= n_new) return;
+    const int s = src[k], pl = place ? place[k] : -1;
+    double2 p = make_double2(0, 0), v = make_double2(0, 0);
+    uint32_t id = next_id + (uint32_t)(pl < 0 ? 0 : pl);
+    if (s >= 0) {
+        p = in.pos[s];
+        v = in.vel[s];
+        id = in.id[s];
+    }
+    if (pl >= 0) {
+        p = placed[pl];
+        v = make_double2(0, 0);
+    }
+    out.pos[k] = p;
+    out.vel[k] = v;
+    out.type[k] = type[k];
+    out.id[k] = id;
+}
+
 int check(plife_handle *h)
 {
     if (!h) return PLIFE_ERR_INVALID;
@@ -366,6 +418,69 @@ int plife_append(plife_handle *h, int64_t k, const double *pos_xy, const double 
     }
     h->n = h->n_phys = n + k;
     h->slab.n_old = h->n;
+    h->max_type = max_type;
+    h->prebinned = false;
+    h->has_sorted = false;
+    return PLIFE_OK;
+}
+
+// Physics.setParticleCount (shuffle-before-shrink, B/Physics.java:190-223, :278-280), ensureTypes (:266-272), setTypes (:509-511),
+// ExtendedPhysics.setTypeCount / setTypeCountEqual (A/ExtendedPhysics.java:28-130): the caller plans the new array on the
+// host - from the types alone, 4 bytes per particle - and the device applies the plan; particles never leave the GPU.
+int plife_rebuild(plife_handle *h, int64_t n_new, const int32_t *src, const int32_t *type, const int32_t *place, int64_t n_placed,
+                  const double *placed_xy)
+{
+    int rc = check(h);
+    if (rc) return rc;
+    if (n_new < 0 || n_placed < 0 || (n_new > 0 && (!src || !type)) || (n_placed > 0 && (!place || !placed_xy)))
+        return edit_fail(h, PLIFE_ERR_INVALID, "rebuild: bad arguments");
+    const int64_t n_old = h->n;
+    int max_type = -1;
+    for (int64_t k = 0; k < n_new; k++) {
+        if (src[k] >= n_old) return edit_fail(h, PLIFE_ERR_INVALID, "rebuild: src index beyond the particle count");
+        if (type[k] < 0 || type[k] >= h->m) return edit_fail(h, PLIFE_ERR_INVALID, "rebuild: type outside [0,m)");
+        const int pl = place ? place[k] : -1;
+        if (pl >= n_placed) return edit_fail(h, PLIFE_ERR_INVALID, "rebuild: place index beyond the placed positions");
+        if (src[k] < 0 && pl < 0) return edit_fail(h, PLIFE_ERR_INVALID, "rebuild: a new particle needs a position");
+        if (type[k] > max_type) max_type = type[k];
+    }
+    for (int64_t q = 0; q < n_placed; q++) {
+        const double x = placed_xy[2 * q], y = placed_xy[2 * q + 1];
+        if (!(x >= 0 && x <= 1 && y >= 0 && y <= 1)) return edit_fail(h, PLIFE_ERR_INVALID, "rebuild: position outside [0,1]^2");
+    }
+    if (n_new > h->cap) {
+        rc = edit_grow(h, n_new + n_new / 4);
+        if (rc) return rc;
+    }
+    int32_t *d_plan = nullptr;
+    double2 *d_placed = nullptr;
+    const size_t np = (size_t)(n_new ? n_new : 1);
+    CUE(h, cudaMalloc((void **)&d_plan, sizeof(int32_t) * 3 * np));
+    cudaError_t e = cudaMalloc((void **)&d_placed, sizeof(double2) * (size_t)(n_placed ? n_placed : 1));
+    if (e == cudaSuccess && n_new) e = cudaMemcpyAsync(d_plan, src, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && n_new) e = cudaMemcpyAsync(d_plan + np, type, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && n_new && place) e = cudaMemcpyAsync(d_plan + 2 * np, place, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && n_placed) e = cudaMemcpyAsync(d_placed, placed_xy, sizeof(double2) * n_placed, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && n_new) {
+        const int nb = (int)((n_new + kThreads - 1) / kThreads);
+        const int a = h->cur, b = h->cur ^ 1;
+        if (h->precision == PLIFE_F32)
+            rebuild_f32<<<nb, kThreads, 0, h->stream>>>(h->s32[a], h->s32[b], (int)n_new, d_plan, d_plan + np, place ? d_plan + 2 * np : nullptr, d_placed, h->next_id);
+        else
+            rebuild_f64<<<nb, kThreads, 0, h->stream>>>(h->s64[a], h->s64[b], (int)n_new, d_plan, d_plan + np, place ? d_plan + 2 * np : nullptr, d_placed, h->next_id);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_plan);
+    cudaFree(d_placed);
+    if (e != cudaSuccess) {
+        h->poisoned = true;
+        return edit_fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    h->cur ^= 1;
+    h->n = h->n_phys = n_new;
+    h->slab.n_old = n_new;
+    h->next_id += (uint32_t)n_placed;
     h->max_type = max_type;
     h->prebinned = false;
     h->has_sorted = false;

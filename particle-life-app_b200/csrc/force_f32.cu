@@ -18,7 +18,7 @@ static IOF32 make_io(plife_handle *h)
 static NextBin next_bin(plife_handle *h)
 {
     if (h->flags & PLIFE_FLAG_NO_FUSED_BIN) return NextBin{nullptr, nullptr, {nullptr, nullptr}, 0};
-    NextBin nb{h->d_cell, h->d_count, {h->slab.on ? h->slab.mig_send[0] : nullptr, h->slab.on ? h->slab.mig_send[1] : nullptr}, (int)h->slab.mig_cap};
+    NextBin nb{h->d_cell, h->small_step ? nullptr : h->d_count, {h->slab.on ? h->slab.mig_send[0] : nullptr, h->slab.on ? h->slab.mig_send[1] : nullptr}, (int)h->slab.mig_cap};
     return nb;
 }
 

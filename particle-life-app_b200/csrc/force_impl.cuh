@@ -475,7 +475,7 @@ struct NextBin {
         const int c = container_of(cxy, g);
         if (c >= 0) {
             cell[i] = cxy;
-            atomicAdd(count + c, 1);
+            if (count) atomicAdd(count + c, 1); // (small mode: small_sort rebuilds the histogram from the bin words)
             return;
         }
         cell[i] = -1; // leaves this slab

@@ -340,14 +340,23 @@ int resolve_timings(plife_handle *h)
 }
 
 // makeContainers (B/Physics.java:309-354): state buffer cur -> sorted into cur^1
+// small grids: one CTA does histogram + scan + scatter (cells.cu: small_sort), and the force pass skips the histogram
+bool small_mode(const plife_handle *h, const Grid &g)
+{
+    return !h->slab.on && (int64_t)g.nxk() * g.nly <= kSmallBins && h->n_phys <= kSmallN && !(h->flags & PLIFE_FLAG_NO_FUSED_BIN);
+}
+
 int sort_current(plife_handle *h, const Grid &g, StepTimer *tm, bool mark_gather_end = true)
 {
     int rc = ensure_cells(h, (int64_t)g.nxk() * g.nly);
     if (rc) return rc;
     if (tm) CU(h, tm->mark(0));
-    // the previous force pass already binned its output for this grid: skip K_BIN
-    const bool reuse = h->prebinned && h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs && h->prebinned_grid.ks == g.ks &&
-                       h->prebinned_grid.row_lo == g.row_lo && h->prebinned_grid.row_hi == g.row_hi;
+    const bool small = small_mode(h, g);
+    h->small_step = small;
+    // the previous force pass already binned its output for this grid: skip K_BIN (the bin words; the big path also needs
+    // the histogram, which a small-mode step does not leave behind)
+    const bool reuse = h->prebinned && (small || h->prebinned_counts) && h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs &&
+                       h->prebinned_grid.ks == g.ks && h->prebinned_grid.row_lo == g.row_lo && h->prebinned_grid.row_hi == g.row_hi;
     if (!reuse) {
         if (h->slab.on) { // binning from scratch is sized by the host: it needs the exact counts (rare: first step, rmax change)
             rc = slab_refresh(h, true);
@@ -355,18 +364,40 @@ int sort_current(plife_handle *h, const Grid &g, StepTimer *tm, bool mark_gather
         }
         if (h->count_dirty) CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)h->cell_cap, h->stream));
         CU(h, launch_bin(h, g));
+        h->count_dirty = true;
     }
     h->prebinned = false;
-    h->count_dirty = false; // K_SCAN zeroes the histogram after reading it
+    h->prebinned_counts = false;
     if (tm) CU(h, tm->mark(1));
-    CU(h, launch_scan(h, g));
-    if (tm) CU(h, tm->mark(2));
-    CU(h, launch_scatter(h, g));
+    if (small) {
+        CU(h, launch_small_sort(h, g));
+        if (tm) CU(h, tm->mark(2));
+    } else {
+        CU(h, launch_scan(h, g));
+        h->count_dirty = false; // K_SCAN zeroes the histogram after reading it
+        if (tm) CU(h, tm->mark(2));
+        CU(h, launch_scatter(h, g));
+    }
     if (tm) CU(h, tm->mark(3));
     CU(h, launch_gather(h, g));
     h->n_sorted = h->n;
     if (tm && mark_gather_end) CU(h, tm->mark(4));
     return PLIFE_OK;
+}
+
+// host-side bookkeeping of a finished (queued) step; the graph replay path runs only this
+void step_done_host(plife_handle *h, const Grid &g)
+{
+    // the force pass binned the new positions into d_cell (and, unless in small mode, d_count) for the same grid
+    h->prebinned = !(h->flags & PLIFE_FLAG_NO_FUSED_BIN);
+    h->prebinned_counts = h->prebinned && !h->small_step;
+    h->prebinned_grid = g;
+    if (h->prebinned_counts) h->count_dirty = true;
+    h->n_phys = h->n;
+    h->n_sorted = h->n;
+    h->last_grid = g;
+    h->has_sorted = true;
+    h->steps++;
 }
 
 int run_step(plife_handle *h, double dt)
@@ -381,10 +412,6 @@ int run_step(plife_handle *h, double dt)
     if (rc) return rc;
     if (h->precision == PLIFE_F32) CU(h, launch_force_f32(h, make_params<float>(h, g, dt)));
     else CU(h, launch_force_f64(h, make_params<double>(h, g, dt)));
-    // the force pass binned the new positions into d_cell / d_count for the same grid
-    h->prebinned = !(h->flags & PLIFE_FLAG_NO_FUSED_BIN);
-    h->prebinned_grid = g;
-    h->count_dirty = h->prebinned;
     if (tm.on) {
         CU(h, tm.mark(PLIFE_K_COUNT));
         h->pending.push_back(tm.t);
@@ -393,10 +420,106 @@ int run_step(plife_handle *h, double dt)
             if (rc) return rc;
         }
     }
-    h->n_phys = h->n;
-    h->last_grid = g;
-    h->has_sorted = true;
-    h->steps++;
+    step_done_host(h, g);
+    return PLIFE_OK;
+}
+
+// ---- launch-bound regime: replay the step as a CUDA graph ----
+// Below kGraphMaxN particles a step is a handful of microsecond kernels and the host cannot launch them as fast as the
+// device runs them.  Once the settings have been stable for two steps the step is captured (once per velocity-buffer
+// parity: the fp32 force pass ping-pongs the two velocity arrays) and replayed with one cudaGraphLaunch.  Everything a
+// captured launch depends on is in the key; any change re-captures.  PLIFE_FLAG_NO_GRAPH turns this off.
+constexpr int64_t kGraphMaxN = 262144;
+
+plife_handle::GraphKey graph_key(const plife_handle *h, double dt, const Grid &g)
+{
+    plife_handle::GraphKey k;
+    memset(&k, 0, sizeof k);
+    k.dt = dt;
+    k.rmax = h->settings.rmax;
+    k.friction = h->settings.friction;
+    k.force = h->settings.force;
+    for (int i = 0; i < 4; i++) k.accp[i] = h->acc_params[i];
+    k.wrap = h->settings.wrap;
+    k.acc_kind = h->acc_kind;
+    k.m = h->m;
+    k.flags = h->flags;
+    k.ks = g.ks;
+    k.n = h->n;
+    k.matrix_version = h->matrix_version;
+    if (h->precision == PLIFE_F32) {
+        k.pt0 = h->s32[0].pt; k.pt1 = h->s32[1].pt; k.vel0 = h->s32[0].vel; k.vel1 = h->s32[1].vel;
+    } else {
+        k.pt0 = h->s64[0].pos; k.pt1 = h->s64[1].pos; k.vel0 = h->s64[0].vel; k.vel1 = h->s64[1].vel;
+    }
+    k.cell_end = h->d_cell_end;
+    k.cur = h->cur;
+    return k;
+}
+
+bool graph_eligible(const plife_handle *h)
+{
+    return !(h->flags & PLIFE_FLAG_NO_GRAPH) && !h->slab.on && !h->profiling && h->n > 0 && h->n <= kGraphMaxN && h->has_sorted &&
+           h->prebinned && !h->matrix_dirty && h->n_phys == h->n;
+}
+
+int step_maybe_graph(plife_handle *h, double dt)
+{
+    if (!graph_eligible(h)) {
+        h->stable_steps = 0;
+        return run_step(h, dt);
+    }
+    Grid g;
+    int rc = make_grid(h, &g);
+    if (rc) return rc;
+    const bool reuse = h->prebinned_grid.nx == g.nx && h->prebinned_grid.cs == g.cs && h->prebinned_grid.ks == g.ks &&
+                       (small_mode(h, g) || h->prebinned_counts);
+    if (!reuse) { // this step re-bins first: not the steady-state launch sequence
+        h->stable_steps = 0;
+        return run_step(h, dt);
+    }
+    const plife_handle::GraphKey key = graph_key(h, dt, g);
+    for (auto &slot : h->graphs) {
+        if (slot.valid && memcmp(&slot.key, &key, sizeof key) == 0) {
+            CU(h, cudaGraphLaunch(slot.exec, h->stream));
+            if (h->precision == PLIFE_F32) launch_force_f32_done(h);
+            h->small_step = small_mode(h, g);
+            step_done_host(h, g);
+            h->graph_launches++;
+            return PLIFE_OK;
+        }
+    }
+    // stability: the key without the alternating velocity pointers
+    plife_handle::GraphKey stable = key;
+    stable.vel0 = stable.vel1 = nullptr;
+    if (memcmp(&stable, &h->last_key, sizeof stable) == 0) h->stable_steps++;
+    else h->stable_steps = 0;
+    h->last_key = stable;
+    if (h->stable_steps < 2) return run_step(h, dt);
+    // capture this step
+    plife_handle::GraphSlot &slot = h->graphs[key.vel0 < key.vel1 ? 0 : 1];
+    if (slot.valid) {
+        cudaGraphExecDestroy(slot.exec);
+        slot.valid = false;
+    }
+    CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    rc = run_step(h, dt);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc;
+    }
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&slot.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaGraphInstantiate");
+    slot.key = key;
+    slot.valid = true;
+    h->graph_captures++;
+    CU(h, cudaGraphLaunch(slot.exec, h->stream)); // the capture queued nothing: run the step now
+    h->graph_launches++;
     return PLIFE_OK;
 }
 
@@ -559,6 +682,8 @@ int plife_destroy(plife_handle *h)
     cudaStreamSynchronize(h->stream);
     for (auto &p : h->pending)
         for (int k = 0; k <= PLIFE_K_COUNT; k++) cudaEventDestroy(p.ev[k]);
+    for (auto &slot : h->graphs)
+        if (slot.valid) cudaGraphExecDestroy(slot.exec);
     slab_destroy(h);
     free_state(h);
     cudaFree(h->d_count);
@@ -610,6 +735,7 @@ int plife_set_matrix(plife_handle *h, int32_t m, const double *row_major)
     h->m = m;
     h->matrix.assign(row_major, row_major + (size_t)m * m);
     h->matrix_dirty = true;
+    h->matrix_version++;
     return PLIFE_OK;
 }
 
@@ -619,6 +745,7 @@ int plife_set_matrix_entry(plife_handle *h, int32_t i, int32_t j, double v)
     if (i < 0 || j < 0 || i >= h->m || j >= h->m || !isfinite(v)) return fail(h, PLIFE_ERR_INVALID, "matrix entry (%d,%d) out of range for size %d", i, j, h->m);
     h->matrix[(size_t)i * h->m + j] = v;
     h->matrix_dirty = true;
+    h->matrix_version++;
     return PLIFE_OK;
 }
 
@@ -926,7 +1053,7 @@ int plife_step(plife_handle *h, double dt, int32_t nsteps)
     if (h->slab.on) return fail(h, PLIFE_ERR_STATE, "slab mode: drive the step with plife_slab_phase");
     for (int s = 0; s < nsteps; s++) {
         if (h->stop_requested.exchange(0)) return fail(h, PLIFE_ERR_STOPPED, "stopped after %d of %d steps", s, nsteps);
-        int rc = run_step(h, dt);
+        int rc = step_maybe_graph(h, dt);
         if (rc) return rc;
     }
     return PLIFE_OK;
@@ -1021,6 +1148,7 @@ int plife_get_step_stats(plife_handle *h, plife_step_stats *out)
     out->ny = g.ny;
     out->pair_evals = (int64_t)total;
     out->steps = h->steps;
+    out->graph_steps = h->graph_launches;
     return PLIFE_OK;
 }
 

@@ -308,6 +308,25 @@ struct plife_handle {
 
     plife::Grid last_grid{0, 0, 0.0};
     bool prebinned = false;   // d_cell / d_count already hold the binning of the current state (fused into the last force pass)
+    bool small_step = false;       // the current / last step ran in small mode
+    bool prebinned_counts = false; // ... including the histogram d_count (not in small mode: small_sort recounts in shared memory)
+    // launch-bound regime: the step replays a captured CUDA graph (one per velocity-buffer parity)
+    struct GraphKey {
+        double dt, rmax, friction, force, accp[4];
+        int wrap, acc_kind, m, flags, ks;
+        long long n, matrix_version;
+        const void *pt0, *pt1, *vel0, *vel1, *cell_end;
+        int cur;
+    };
+    struct GraphSlot {
+        GraphKey key;
+        cudaGraphExec_t exec;
+        bool valid;
+    } graphs[2]{};
+    long long matrix_version = 0;
+    int stable_steps = 0; // consecutive steps with an unchanged key
+    GraphKey last_key{};
+    long long graph_launches = 0, graph_captures = 0;
     plife::Grid prebinned_grid{0, 0, 0.0};
     bool count_dirty = false; // d_count is not all-zero
     bool has_sorted = false; // buffer cur^1 holds the sorted pre-step state of the last step
@@ -334,6 +353,9 @@ namespace plife {
 // cells.cu
 cudaError_t launch_bin(plife_handle *h, const Grid &g);
 cudaError_t launch_scan(plife_handle *h, const Grid &g);
+cudaError_t launch_small_sort(plife_handle *h, const Grid &g); // histogram + scan + scatter in one CTA (small grids)
+constexpr int kSmallBins = 8192;  // small_sort: the histogram must fit the CTA's shared memory
+constexpr int kSmallN = 65536;
 cudaError_t launch_scatter(plife_handle *h, const Grid &g);
 cudaError_t launch_gather(plife_handle *h, const Grid &g);
 cudaError_t launch_apply_sort_f32(plife_handle *h, const Grid &g);

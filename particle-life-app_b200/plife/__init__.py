@@ -180,6 +180,23 @@ class NativePhysics:
         types = np.ascontiguousarray(types, dtype=np.int32).reshape(k)
         self._check(self.L.plife_append(self.h, k, _ptr(pos), _ptr(vel), _ptr(types)))
 
+    def types(self) -> np.ndarray:
+        """Only the types, in array order (4 bytes per particle over PCIe): what the type-count planners need."""
+        t = np.empty(self.count, np.int32)
+        if t.size:
+            self._check(self.L.plife_download_f32(self.h, None, None, t.ctypes.data))
+        return t
+
+    def rebuild(self, src, types, place=None, placed=None):
+        """Device-side apply of a host-planned rearrangement (plife_rebuild): new particle k = old particle src[k] (or a new
+        one for src[k] < 0) with type types[k]; where place[k] >= 0 it is put at placed[place[k]] with zero velocity."""
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        types = np.ascontiguousarray(types, dtype=np.int32).reshape(src.shape[0])
+        place = None if place is None else np.ascontiguousarray(place, dtype=np.int32).reshape(src.shape[0])
+        placed = np.zeros((0, 2)) if placed is None else np.ascontiguousarray(placed, dtype=np.float64).reshape(-1, 2)
+        self._check(self.L.plife_rebuild(self.h, src.shape[0], _ptr(src), _ptr(types), _ptr(place), placed.shape[0],
+                                         _ptr(placed) if placed.shape[0] else None))
+
     # -- stepping --
     def step(self, dt, nsteps=1):
         self._check(self.L.plife_step(self.h, dt, nsteps))
@@ -207,7 +224,7 @@ class NativePhysics:
     def step_stats(self, pairs=True):
         s = N.StepStats()
         self._check(self.L.plife_get_step_stats(self.h, C.byref(s)))
-        return dict(n=s.n, nx=s.nx, ny=s.ny, pair_evals=s.pair_evals, steps=s.steps)
+        return dict(n=s.n, nx=s.nx, ny=s.ny, pair_evals=s.pair_evals, steps=s.steps, graph_steps=s.graph_steps)
 
     def debug_neighbors(self):
         n = self.count
@@ -240,6 +257,7 @@ class DefaultPositionSetter:
 
 class DefaultTypeSetter:
     """B/DefaultTypeSetter.java:8-10: floor(random * nTypes)."""
+    uses_state = False  # ignores position / velocity: nothing has to come back from the device for it
 
     def get_type(self, position, velocity, types, n_types: int, rng: np.random.Generator) -> np.ndarray:
         return np.floor(rng.random(types.shape[0]) * n_types).astype(np.int32)
@@ -336,7 +354,8 @@ class Physics:
         return pos, zeros.copy(), types
 
     def set_particle_count(self, n: int):
-        """B/Physics.java:190-223."""
+        """B/Physics.java:190-223.  Planned on the host from the types, applied on the device (plife_rebuild): the
+        particles never leave the GPU."""
         cur = self.native.count
         if n == cur and cur > 0:
             return
@@ -344,38 +363,53 @@ class Physics:
             pos, vel, types = self._generate(n)
             self.set_particles(pos, vel, types)
             return
-        p = self.native.download()
-        if n < cur:  # shuffle first, then keep the first n (:201-210)
+        self._push_settings()
+        old_types = self.native.types()
+        if n < cur:  # shuffle first, then keep the first n (:201-210, :278-280)
             keep = self.rng.permutation(cur)[:n]
-            self.set_particles(p.position[keep], p.velocity[keep], p.type[keep], p.id[keep])
+            self.native.rebuild(keep, old_types[keep])
         else:
-            pos, vel, types = self._generate(n - cur)
-            ids = np.concatenate([p.id, np.arange(cur, n, dtype=np.uint32)])
-            self.set_particles(np.concatenate([p.position, pos]), np.concatenate([p.velocity, vel]),
-                               np.concatenate([p.type, types]), ids)
+            pos, _, types = self._generate(n - cur)
+            src = np.concatenate([np.arange(cur), np.full(n - cur, -1)])
+            place = np.concatenate([np.full(cur, -1), np.arange(n - cur)])
+            self.native.rebuild(src, np.concatenate([old_types, types]), place, pos)
 
     def set_positions(self):
-        """B/Physics.java:166-168."""
+        """B/Physics.java:166-168: every particle gets a new position (velocity zero); types and ids stay."""
+        self._push_settings()
+        types = self.native.types()
+        pos = self.ensure_position(self.position_setter.set(types, self.settings.matrix.shape[0], self.rng))
+        n = len(types)
+        self.native.rebuild(np.arange(n), types, np.arange(n), pos)
+
+    def _setter_state(self, idx):
+        """Positions / velocities for a TypeSetter that looks at them (B/TypeSetter.java:14); the default one does not."""
+        if not getattr(self.type_setter, "uses_state", True):
+            z = np.zeros((len(idx), 2))
+            return z, z
         p = self.native.download()
-        pos = self.ensure_position(self.position_setter.set(p.type, self.settings.matrix.shape[0], self.rng))
-        self.set_particles(pos, np.zeros_like(p.velocity), p.type, p.id)
+        return p.position[idx], p.velocity[idx]
 
     def set_types(self):
         """B/Physics.java:509-511."""
-        p = self.native.download()
-        t = self.type_setter.get_type(p.position, p.velocity, p.type, self.settings.matrix.shape[0], self.rng)
-        self.set_particles(p.position, p.velocity, t.astype(np.int32), p.id)
+        self._push_settings()
+        types = self.native.types()
+        idx = np.arange(len(types))
+        pos, vel = self._setter_state(idx)
+        t = self.type_setter.get_type(pos, vel, types, self.settings.matrix.shape[0], self.rng)
+        self.native.rebuild(idx, np.asarray(t, np.int32))
 
     def ensure_types(self):
-        """B/Physics.java:266-272."""
-        p = self.native.download()
+        """B/Physics.java:266-272: particles whose type no longer exists get a new one from the TypeSetter.  Runs against the
+        OLD (larger) matrix on the device, so call it before the smaller matrix is pushed (set_matrix_size does)."""
+        types = self.native.types()
         m = self.settings.matrix.shape[0]
-        bad = p.type >= m
-        if bad.any():
-            t = p.type.copy()
-            t[bad] = self.type_setter.get_type(p.position[bad], p.velocity[bad], p.type[bad], m, self.rng)
-            # upload against the OLD (larger) matrix is still valid; push the new matrix afterwards
-            self.native.upload(p.position, p.velocity, t, p.id)
+        bad = np.nonzero(types >= m)[0]
+        if len(bad):
+            pos, vel = self._setter_state(bad)
+            t = types.copy()
+            t[bad] = self.type_setter.get_type(pos, vel, types[bad], m, self.rng)
+            self.native.rebuild(np.arange(len(types)), t)
 
     # -- matrix --
     def generate_matrix(self):
@@ -401,26 +435,21 @@ class Physics:
         return self.native.type_histogram()
 
     def set_type_count(self, type_count):
-        """A/ExtendedPhysics.java:40-118 (planned on the host for the whole array, see setters.plan_type_count)."""
+        """A/ExtendedPhysics.java:40-118: planned on the host for the whole array at once from the types alone
+        (setters.plan_type_count), applied on the device (plife_rebuild)."""
         from .setters import plan_type_count
         m = self.settings.matrix.shape[0]
         want = np.asarray(type_count, np.int64).reshape(-1)
         if want.shape[0] != m:
             raise ValueError(f"Got array of length {want.shape[0]}, but current matrix size is {m}. "
                              "Maybe you should change the matrix size before doing this.")
-        p = self.native.download()
-        src, types, fresh = plan_type_count(p.type, want, self.rng)
-        old = src >= 0
-        pos = np.zeros((len(src), 2))
-        vel = np.zeros((len(src), 2))
-        pos[old], vel[old] = p.position[src[old]], p.velocity[src[old]]
-        if fresh.any():
-            pos[fresh] = self.ensure_position(self.position_setter.set(types[fresh], m, self.rng))
-        ids = np.zeros(len(src), np.uint32)
-        ids[old] = p.id[src[old]]
-        first_new = int(p.id.max()) + 1 if len(p.id) else 0
-        ids[~old] = np.arange(first_new, first_new + int((~old).sum()), dtype=np.uint32)
-        self.set_particles(pos, vel, types, ids)
+        self._push_settings()
+        src, types, fresh = plan_type_count(self.native.types(), want, self.rng)
+        place = np.full(len(src), -1, np.int64)
+        place[fresh] = np.arange(int(fresh.sum()))
+        # setPosition of every particle that could not be reused or is new (:92-97): new position, zero velocity
+        pos = self.ensure_position(self.position_setter.set(types[fresh], m, self.rng)) if fresh.any() else None
+        self.native.rebuild(src, types, place, pos)
 
     def set_type_count_equal(self):
         """A/ExtendedPhysics.java:28-38."""

@@ -30,7 +30,7 @@ class Settings(C.Structure):
 
 class StepStats(C.Structure):
     _fields_ = [("n", C.c_int64), ("nx", C.c_int32), ("ny", C.c_int32), ("pair_evals", C.c_int64),
-                ("steps", C.c_int64)]
+                ("steps", C.c_int64), ("graph_steps", C.c_int64)]
 
 
 class Cursor(C.Structure):
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
         "plife_cursor_move": (C.c_int, [vp, C.POINTER(Cursor), dbl, dbl]),
         "plife_cursor_delete": (C.c_int, [vp, C.POINTER(Cursor), C.POINTER(i64)]),
         "plife_append": (C.c_int, [vp, i64, vp, vp, vp]),
+        "plife_rebuild": (C.c_int, [vp, i64, vp, vp, vp, i64, vp]),
         "plife_slab_halo_records": (i64, [i32, i64]),
         "plife_slab_migrate_records": (i64, [i64]),
         "plife_slab_configure": (C.c_int, [vp, i32, i32, i64, i64, C.POINTER(SlabBuffers)]),

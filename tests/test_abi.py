@@ -26,7 +26,7 @@ def test_header_declares_the_reference_surface():
 def test_library_exports_every_declared_symbol(native_lib):
     for s in declared_symbols():
         assert hasattr(native_lib, s), f"libplife.so does not export {s}"
-    assert native_lib.plife_version() == 100
+    assert native_lib.plife_version() == 200
 
 
 def test_product_library_does_not_link_the_oracle(native_lib):
@@ -60,7 +60,7 @@ def test_no_gpu_means_loud_failure(native_lib):
 
 def test_struct_layouts_match_header():
     from plife import _native as N
-    assert C.sizeof(N.Settings) == 32 and C.sizeof(N.Config) == 32 and C.sizeof(N.StepStats) == 32
+    assert C.sizeof(N.Settings) == 32 and C.sizeof(N.Config) == 32 and C.sizeof(N.StepStats) == 40
 
 
 def test_synth_generators_are_deterministic_and_in_range():

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import plife
+from plife._native import FLAG_NO_GRAPH as N_FLAG_NO_GRAPH
 from helpers import make_state, max_over_rms, oracle_step, rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -652,3 +653,114 @@ def test_one_huge_cell_fp64_and_fp32(native_lib):
     g = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, rmax=rmax, wrap=True, dt=DT)
     got = g.download()
     assert np.array_equal(got.id, oid) and rel_l2(got.velocity, ovel) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
+def test_rebuild_applies_host_plan_on_device(native_lib, precision):
+    """plife_rebuild against a numpy restatement: keep / drop / reorder / retype / create / re-place in one pass."""
+    f32 = precision == plife.F32
+    n, m = 20_000, 5
+    pos, vel, types, matrix = make_state(n, m, seed=8, vel_scale=0.2, f32=f32)
+    p = plife.NativePhysics(precision=precision)
+    p.set_matrix(matrix)
+    p.upload(pos, vel, types)
+    rng = np.random.default_rng(3)
+    n_new = 23_000
+    src = np.concatenate([rng.permutation(n)[:15_000], np.full(n_new - 15_000, -1)])
+    rng.shuffle(src)
+    new_types = rng.integers(0, m, n_new).astype(np.int32)
+    place = np.full(n_new, -1)
+    placed_rows = np.nonzero((src < 0) | (rng.random(n_new) < 0.1))[0]  # every new particle, and a tenth of the carried ones
+    place[placed_rows] = rng.permutation(len(placed_rows))
+    placed = rng.random((len(placed_rows), 2))
+    assert np.array_equal(p.types(), types)
+    p.rebuild(src, new_types, place, placed)
+    got = p.download()
+    assert p.count == n_new
+    exp_pos, exp_vel = np.zeros((n_new, 2)), np.zeros((n_new, 2))
+    old = src >= 0
+    exp_pos[old], exp_vel[old] = pos[src[old]], vel[src[old]]
+    pl = place >= 0
+    exp_pos[pl] = placed[place[pl]].astype(np.float32).astype(np.float64) if f32 else placed[place[pl]]
+    exp_vel[pl] = 0
+    exp_id = np.where(old, np.where(old, src, 0), n + place).astype(np.uint32)
+    assert np.array_equal(got.type, new_types) and np.array_equal(got.id, exp_id)
+    assert np.array_equal(got.position, exp_pos) and np.array_equal(got.velocity, exp_vel)
+    p.step(DT, 2)  # the rebuilt state steps
+    assert p.count == n_new and np.array_equal(np.sort(p.download().id), np.sort(exp_id))
+    # invalid plans are refused
+    with pytest.raises(plife.PlifeError):
+        p.rebuild([n_new + 5], [0])
+    with pytest.raises(plife.PlifeError):
+        p.rebuild([-1], [0])  # a new particle without a position
+
+
+def test_type_count_operations_stay_on_device(native_lib):
+    """ExtendedPhysics.setTypeCount / setTypeCountEqual, Physics.setParticleCount and ensureTypes through plife.Physics:
+    histogram as requested, surviving particles keep id / position / velocity, re-placed ones have zero velocity
+    (A/ExtendedPhysics.java:40-118, B/Physics.java:190-223, :266-272, :297-303)."""
+    ph = plife.Physics(particle_count=30_000, seed=5)
+    ph.settings.rmax = 0.02
+    ph.update()
+    ph.update()
+    before = ph.particles
+    ph.set_type_count_equal()
+    assert np.array_equal(ph.get_type_count(), np.full(6, 5000))
+    after = ph.particles
+    assert sorted(after.id.tolist()) == sorted(before.id.tolist())  # same total: nobody is created or dropped
+    b = {int(i): k for k, i in enumerate(before.id)}
+    k0 = np.array([b[int(i)] for i in after.id])
+    same_type = after.type == before.type[k0]
+    assert np.array_equal(after.position, before.position[k0]) and np.array_equal(after.velocity, before.velocity[k0])
+    assert (~same_type).sum() == np.abs(np.bincount(before.type, minlength=6) - 5000).sum() // 2
+    want = np.array([100, 200, 300, 400, 500, 20_000])
+    ph.set_type_count(want)
+    assert np.array_equal(ph.get_type_count(), want) and ph.particle_count == want.sum()
+    g = ph.particles
+    a = {int(i): k for k, i in enumerate(after.id)}
+    kept = np.array([int(i) in a for i in g.id])
+    k1 = np.array([a[int(i)] for i in g.id[kept]])
+    moved = (g.position[kept] != after.position[k1]).any(axis=1)
+    assert np.array_equal(g.velocity[kept][~moved], after.velocity[k1][~moved])
+    assert not g.velocity[kept][moved].any()  # setPosition zeroes the velocity of every re-placed particle
+    ph.set_particle_count(5_000)
+    s = ph.particles
+    assert ph.particle_count == 5_000 and set(s.id.tolist()) <= set(g.id.tolist())
+    ph.set_particle_count(6_000)
+    assert ph.particle_count == 6_000
+    ph.set_matrix_size(3)
+    ph.update()
+    assert ph.particles.type.max() < 3 and ph.particle_count == 6_000
+
+
+@pytest.mark.parametrize("precision", [plife.F32, plife.F64], ids=["f32", "f64"])
+def test_small_grid_graph_replay_matches_plain_launches(native_lib, precision):
+    """Launch-bound regime (BASELINE config 1): the one-CTA cell-list build and the CUDA-graph replay of the step give
+    bit for bit what the plain launch sequence gives (PLIFE_FLAG_NO_GRAPH), through settings changes and edits."""
+    f32 = precision == plife.F32
+    pos, vel, types, matrix = make_state(10_000, 6, seed=11, vel_scale=0.05, f32=f32)
+    a = plife.NativePhysics(precision=precision)
+    b = plife.NativePhysics(precision=precision, flags=N_FLAG_NO_GRAPH)
+    for p in (a, b):
+        p.set_settings(0.04, 0.85, 1.0, True)
+        p.set_matrix(matrix)
+        p.upload(pos, vel, types)
+    for p in (a, b):
+        p.step(DT, 12)
+        p.set_settings(0.04, 0.9, 1.0, True)   # friction changes: the captured step must not be replayed
+        p.step(DT, 7)
+        p.step(0.01, 3)                         # dt changes
+        p.cursor_move(0.5, 0.5, 0.2, 0.01, 0.0)
+        p.step(0.01, 6)
+    ga, gb = a.download(), b.download()
+    assert np.array_equal(ga.id, gb.id) and np.array_equal(ga.position, gb.position) and np.array_equal(ga.velocity, gb.velocity)
+    sa, sb = a.step_stats(), b.step_stats()
+    assert sa["graph_steps"] >= 12 and sb["graph_steps"] == 0 and sa["steps"] == sb["steps"] == 28
+    # and the small path still agrees with the oracle
+    o = oracle_step(pos, vel, types, matrix, steps=1, rmax=0.04, wrap=True, dt=DT)
+    c = plife.NativePhysics(precision=precision)
+    c.set_settings(0.04, 0.85, 1.0, True)
+    c.set_matrix(matrix)
+    c.upload(pos, vel, types)
+    c.step(DT, 1)
+    assert np.array_equal(c.download().id, o.get_particles()[3]) and np.array_equal(c.containers(), o.containers())
