@@ -33,10 +33,14 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
     // v2 staged kernel whenever the per-lane matrix table fits; v1 (global-memory walk) otherwise
     // (below ~4 particles per cell the per-CTA staging and table fill cost more than they save: v1 wins)
     if (p.m <= kTabMaxM && rho >= 4.0 && !(h->flags & PLIFE_FLAG_FORCE_V1)) {
-        // capacity of one staged row range: 128 targets + the bins hanging over both ends + margin
-        const double over = 2.0 * rho * (1.0 + 1.0 / (1 << p.g.ks)); // K bins on either side, plus the partly covered end bins
-        int cap = (int)(kForceThreads + over + 8.0 * sqrt(rho + 1.0) + 32.0);
-        cap = (cap + 31) / 32 * 32;
+        // capacity of one staged row range: the CTA's 128 targets + K bins on either side (2 rho (1 + 1/K) particles on
+        // average) + 4.5 sigma of that count (uniform state; anything denser streams in chunks, traverse_chunked).
+        // PLIFE_STAGE_CAP overrides (experiments).
+        const double mean = kForceThreads + 2.0 * rho * (1.0 + 1.0 / (1 << p.g.ks));
+        int cap = (int)(mean + 4.5 * sqrt(mean) + 8.0);
+        static const int cap_env = getenv("PLIFE_STAGE_CAP") ? atoi(getenv("PLIFE_STAGE_CAP")) : 0;
+        if (cap_env > 0) cap = cap_env;
+        cap = (cap + 15) / 16 * 16;
         if (cap > 1536) cap = 1536;
         return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h), stream);
     }
