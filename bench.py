@@ -348,23 +348,54 @@ def slab_parity_check(torch, dist, plife, stream, rank, world, local_rank, excha
     return bool(int(t[0].item())), moved
 
 
-def histogram_pair_evals(torch, dist, containers, nx, nly, first, rank, world, wrap):
+def histogram_pair_evals(torch, dist, containers, nx, nly, first, rank, world, wrap, pos_xy, rmax, row_lo):
     """Candidate pairs (i, j != i in the 3x3 cells of i) of this rank's OWNED rows as the cell histograms imply them:
     sum_c occ(c) * sum_{3x3} occ - n_owned.  The rows next to the slab come from their OWNERS' histograms (all-gather),
-    not from this rank's ghost rows, so the number also checks that the halo exchange delivered the right rows."""
+    not from this rank's ghost rows, so the number also checks that the halo exchange delivered the right rows.
+    Particles sitting exactly on x == 1.0 or y == 1.0 (Range.wrap can return it) scan the cells around the
+    UN-clamped coordinate (B/Physics.java:404-405), e.g. columns nx-1, 0, 1 instead of nx-2, nx-1, 0: corrected one by one."""
     import numpy as np
+    ny = nx
     ends = containers.astype(np.int64).reshape(nly, nx)[1:nly - 1]  # owned rows (local rows 1 .. nly-2)
     occ = np.diff(np.concatenate([[first], ends.reshape(-1)])).reshape(nly - 2, nx)
-    edge = torch.tensor(np.stack([occ[0], occ[-1]]), device="cuda", dtype=torch.int64)
+    edge = torch.tensor(np.stack([occ[0], occ[1], occ[-1]]), device="cuda", dtype=torch.int64)  # first, second, last owned row
     edges = [torch.zeros_like(edge) for _ in range(world)]
     dist.all_gather(edges, edge)
     zero = np.zeros(nx, np.int64)
-    below = edges[(rank - 1) % world][1].cpu().numpy() if (wrap or rank > 0) else zero
-    above = edges[(rank + 1) % world][0].cpu().numpy() if (wrap or rank < world - 1) else zero
+    has_dn, has_up = (wrap or rank > 0), (wrap or rank < world - 1)
+    below = edges[(rank - 1) % world][2].cpu().numpy() if has_dn else zero
+    above = edges[(rank + 1) % world][0].cpu().numpy() if has_up else zero
+    above2 = edges[(rank + 1) % world][1].cpu().numpy() if has_up else zero
     full = np.concatenate([below[None], occ, above[None]])
     row3 = full + np.roll(full, 1, axis=1) + np.roll(full, -1, axis=1)
     nine = row3[:-2] + row3[1:-1] + row3[2:]
-    return int((occ * nine).sum() - occ.sum()), bool((occ >= 0).all())
+    total = int((occ * nine).sum() - occ.sum())
+    # corrections for targets with an un-clamped coordinate == n (x or y exactly 1.0)
+    x, y = pos_xy[:, 0].astype(np.float64), pos_xy[:, 1].astype(np.float64)
+    cx0, cy0 = (x / rmax).astype(np.int64), (y / rmax).astype(np.int64)
+    special = np.nonzero((cx0 >= nx) | (cy0 >= ny))[0]
+    rows_of = {row_lo - 1 + k: full[k] for k in range(full.shape[0])}
+    rows_of[row_lo + occ.shape[0] + 1] = above2
+
+    def W(c, n):
+        return c + n if c < 0 else (c - n if c >= n else c)
+    exact = True
+    for i in special:
+        cols = [W(W(int(cx0[i]) + d, nx), nx) for d in (-1, 0, 1)]
+        # (y: a slab scans the rows ny-2, ny-1, 0 around a particle on y == 1.0 - global row 1 lives two slabs away and holds
+        # nothing within rmax of it - so its candidate count is the clamped row's; plife_internal.h: scan_row)
+        cyi = min(int(cy0[i]), ny - 1)
+        rws = [W(W(cyi + d, ny), ny) for d in (-1, 0, 1)]
+        got = 0
+        for r in rws:
+            key = r if r in rows_of else (r + ny if (r + ny) in rows_of else r - ny)
+            if key not in rows_of:
+                exact = False
+                continue
+            got += int(sum(rows_of[key][c] for c in cols))
+        ccx, ccy = min(int(cx0[i]), nx - 1), min(int(cy0[i]), ny - 1)
+        total += got - int(nine[ccy - row_lo, ccx])
+    return total, bool((occ >= 0).all()) and exact, len(special)
 
 
 def run_ours(args):
@@ -493,12 +524,29 @@ def run_ours(args):
 
     # ---- correctness words of the timed run itself (multi-GPU) ----
     if world > 1:
+        # the positions now, then one more step with dt = 0: it builds the cell list of exactly these positions, and its
+        # cell offsets and pair count are what is checked below.  (Not "a step that moves nothing": a particle sitting on
+        # y == 1.0 is wrapped to 0.0 by updatePosition even with dt = 0, B/Range.java:46-57, and changes slab.)
+        pos32 = np.empty((p.count, 2), np.float32)
+        p.download_f32(pos32, None, None)
+        with torch.cuda.stream(stream):
+            slab.step(0.0, ex, 1)
+        stats = p.step_stats()
+        n_local = p.count
         lo, hi, nxg = slab.rows()
         cont = p.containers_local(nxg * (hi - lo + 2))
         tot = torch.tensor([n_local, stats["pair_evals"]], device="cuda", dtype=torch.int64)
         dist.all_reduce(tot)
         conserved = int(tot[0].item()) == n
-        expect, sane = histogram_pair_evals(torch, dist, cont, nxg, hi - lo + 2, halo_cap, rank, world, cfg["wrap"])
+        expect, sane, n_special = histogram_pair_evals(torch, dist, cont, nxg, hi - lo + 2, halo_cap, rank, world, cfg["wrap"], pos32, cfg["rmax"], lo)
+        del pos32
+        if args.verbose or expect != stats["pair_evals"]:
+            c2 = cont.astype(np.int64).reshape(hi - lo + 2, nxg)
+            g_above = np.diff(np.concatenate([[c2[-2, -1]], c2[-1]]))  # the ghost rows as this rank holds them
+            g_below = np.diff(c2[0])
+            log(f"pair evaluations {stats['pair_evals']}, implied by the owners' cell histograms {expect} (rows [{lo},{hi}), n={n_local}, "
+                f"{n_special} particles exactly on 1.0, sane={sane}); ghost rows held: above {int(g_above.sum())} particles "
+                f"(min {int(g_above.min())}), below {int(g_below.sum())}+first cell, end of owned block {int(c2[-2, -1])} = first + n = {halo_cap + n_local}")
         flag = torch.tensor([1 if (sane and expect == stats["pair_evals"]) else 0], device="cuda", dtype=torch.int64)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         hist_ok = bool(int(flag.item()))

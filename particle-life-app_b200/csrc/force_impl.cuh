@@ -233,7 +233,7 @@ __device__ __forceinline__ void traverse(const IO &io, const int32_t *__restrict
     using R = typename IO::R;
     // :404-405 floor(x / containerSize) without the ==nx clamp: cached by the binning pass (cell_coords)
     const int cx0 = (cxy & 0xffff) >> g.ks;
-    const int cy0 = cxy >> 16;
+    const int cy0 = scan_row(cxy >> 16, g);
     const bool interior = g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
     if constexpr (is_deferred<V>::value) {
         traverse_listed(io, cell_end, g, interior, xi, yi, cx0, cy0, v);
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 i
         mbar_wait(bar, 0);    // the three ranges have landed
     }
 
-    const int cx0 = (cxy & 0xffff) >> g.ks, cy0 = cxy >> 16;
+    const int cx0 = (cxy & 0xffff) >> g.ks, cy0 = scan_row(cxy >> 16, g);
     const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
     const int fb = (cxy & 0xffff) + (cy0 + g.ly_shift) * g.nxk(); // own bin (interior lanes: no clamp needed)
     MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, self.type, 1.0f, 0u, 0u};

@@ -597,6 +597,7 @@ cudaError_t slab_force_done(plife_handle *h, const Grid &g)
     }
     h->slab_timing_on = false;
     h->prebinned = true; // the epilogue binned the stayers; arrivals are binned by phase FINISH
+    h->prebinned_counts = true;
     h->prebinned_grid = g;
     h->count_dirty = true;
     h->last_grid = g;

@@ -89,6 +89,13 @@ __host__ __device__ inline int local_row(int cy, const Grid &g)
     else if (ly >= g.ny) ly -= g.ny;
     return ly;
 }
+// Slab mode: a particle sitting exactly on y == 1.0 (Range.wrap can return it), or in the strip above
+// ny*rmax, has the un-clamped row ny; the reference scans the rows ny-1, 0, 1 around it (B/Physics.java:404-417), but global
+// row 1 lives two slabs away from the last slab.  Rows ny-2, ny-1, 0 hold every particle within rmax of it (row 1 starts a
+// full rmax above y == 0 == 1), so the last slab scans those instead: the same forces bit for bit (out-of-range candidates
+// add exact zeros), only the candidate COUNT of such a particle differs from the reference's.
+__host__ __device__ inline int scan_row(int cy0, const Grid &g) { return (g.nly != g.ny && cy0 >= g.ny) ? g.ny - 1 : cy0; }
+
 // [start, end) of the local CELLS c_lo .. c_hi (inclusive, same row) in the sorted array: bin END offsets, cell_end[-1] valid
 __device__ __forceinline__ void cell_span(const int32_t *__restrict__ cell_end, int c_lo, int c_hi, int ks, int &s, int &e)
 {

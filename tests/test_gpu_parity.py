@@ -245,6 +245,11 @@ def test_virtual_slabs_match_single_gpu(native_lib, world, wrap, exchange):
     from plife.slab import VirtualCluster
     n, m, rmax, steps = 60_000, 5, 0.02, 12
     pos, vel, types, matrix = make_state(n, m, seed=31 + world, vel_scale=0.3, f32=True)
+    # particles exactly on the upper borders (Range.wrap can put them there): their un-clamped row is ny,
+    # which on the last slab would point at a row two slabs away (plife_internal.h: scan_row)
+    pos[:30, 1] = 1.0
+    pos[30:60, 0] = 1.0
+    pos[60:70] = 1.0
     # same fine-bin count on both sides: the fp32 summation order follows the internal cell list
     single = plife.NativePhysics(precision=plife.F32, bins=4)
     single.set_settings(rmax, 0.85, 1.0, wrap)
