@@ -29,10 +29,8 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
 {
     const float *mt = (const float *)h->d_matrix_t;
     const float *mrow = mt + (size_t)p.m * p.m; // row-major copy follows the transposed one
-    const double rho = (double)h->n / ((double)p.g.nx * (p.g.row_hi - p.g.row_lo)); // particles per owned cell
-    // v2 staged kernel whenever the per-lane matrix table fits; v1 (global-memory walk) otherwise
-    // (below ~4 particles per cell the per-CTA staging and table fill cost more than they save: v1 wins)
-    if (p.m <= kTabMaxM && rho >= 4.0 && !(h->flags & PLIFE_FLAG_FORCE_V1)) {
+    const double rho = p.g.rho; // particles per cell (make_grid's estimate: the same on every rank of a slab run)
+    if (p.g.staged) {
         // capacity of one staged row range: the CTA's 128 targets + K bins on either side (2 rho (1 + 1/K) particles on
         // average) + 4.5 sigma of that count (uniform state; anything denser streams in chunks, traverse_chunked).
         // PLIFE_STAGE_CAP overrides (experiments).
@@ -44,6 +42,7 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
         if (cap > 1536) cap = 1536;
         return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h), stream);
     }
+    if (p.g.ks != 0) return cudaErrorInvalidValue; // the v1 kernel writes results at the compute slot (make_grid never pairs it with fine bins)
     return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mt, h->acc_kind, next_bin(h), stream);
 }
 

@@ -27,6 +27,7 @@ struct Cand {
 // ---- state access policies -------------------------------------------------
 struct IOF32 {
     using R = float;
+    static constexpr int kMinBlocks = 16; // v1 kernel: 32 registers, full occupancy (it is latency-bound at the low densities it serves)
     const float4 *__restrict__ pt;        // sorted records in COMPUTE order (candidates and own position), type << kTypeShift
     const float2 *__restrict__ vel;       // velocities in PRE-sort order: the gather does not move them
     float4 *__restrict__ pt_out;
@@ -65,6 +66,7 @@ struct IOF32 {
 
 struct IOF64 {
     using R = double;
+    static constexpr int kMinBlocks = 1;
     StateF64 in, out;
     __device__ __forceinline__ Cand<double> cand(int j) const
     {
@@ -536,7 +538,7 @@ __device__ __forceinline__ void load_matrix_smem(R *sM, const R *__restrict__ gM
 }
 
 template <typename IO, int KIND, bool SMEM, bool FAST>
-__global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32_t *__restrict__ cell_end,
+__global__ void __launch_bounds__(kForceThreads, IO::kMinBlocks) force_kernel(IO io, const int32_t *__restrict__ cell_end,
                                                              const int32_t *__restrict__ cell_sorted,
                                                              ForceParams<typename IO::R> P,
                                                              const typename IO::R *__restrict__ gMt, NextBin nb)
@@ -581,7 +583,9 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(IO io, const int32
         nx_ = range_clamp(nx_);
         ny_ = range_clamp(ny_);
     }
-    const int o = io.out_slot(i, cxy, cell_end, P.g);
+    // this kernel only ever runs on the plain cell list (ks == 0: fp64, m > 32, fewer than 4 particles per cell - the launcher
+    // refuses anything else), where the compute order is the reference's order
+    const int o = i;
     io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
     nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, P.g);
 }

@@ -197,16 +197,22 @@ int ensure_cells(plife_handle *h, int64_t ncell)
 // on; the staged force kernel must be the one in use (m <= 32, >= 4 particles per cell).  PLIFE_BINS=K overrides.
 // Slab mode: every rank must pick the same K (the halo messages carry per-bin offsets), so the density estimate
 // comes from the halo capacity every rank was configured with, not from the rank's own particle count.
-int choose_ks(const plife_handle *h, const Grid &g)
+void choose_kernel(const plife_handle *h, Grid *g)
 {
-    if (h->precision != PLIFE_F32 || (h->flags & PLIFE_FLAG_FORCE_V1) || h->m > 32) return 0;
+    g->ks = 0;
+    g->staged = 0;
     double rho;
-    if (h->slab.on) rho = (double)h->slab.halo_cap / (1.5 * g.nx);
-    else rho = (double)h->n / ((double)g.nx * g.ny);
-    int ks = rho >= 12.0 ? 3 : (rho >= 6.0 ? 2 : (rho >= 4.0 ? 1 : 0));
+    if (h->slab.on) rho = (double)h->slab.halo_cap / (1.5 * g->nx);
+    else rho = (double)h->n / ((double)g->nx * g->ny);
+    g->rho = (float)rho;
+    // staged kernel whenever the per-lane matrix table fits (m <= 32); below ~4 particles per cell the per-CTA staging and
+    // table fill cost more than they save and the v1 kernel (global-memory walk, plain cell list) wins
+    if (h->precision != PLIFE_F32 || (h->flags & PLIFE_FLAG_FORCE_V1) || h->m > 32 || rho < 4.0) return;
+    g->staged = 1;
+    int ks = rho >= 12.0 ? 3 : (rho >= 6.0 ? 2 : 1);
     if (h->bins_override >= 0) ks = h->bins_override;
-    while (ks > 0 && (((int64_t)(g.nx + 1) << ks) > 65535 || (((int64_t)g.nx * g.nly) << ks) > kMaxCells)) ks--;
-    return ks;
+    while (ks > 0 && (((int64_t)(g->nx + 1) << ks) > 65535 || (((int64_t)g->nx * g->nly) << ks) > kMaxCells)) ks--;
+    g->ks = ks;
 }
 
 // B/Physics.java:82-85 with containerSize = rmax (:312)
@@ -225,6 +231,8 @@ int make_grid(plife_handle *h, Grid *g)
     g->nly = nx;
     g->rows_up = g->rows_dn = 0;
     g->ks = 0;
+    g->staged = 0;
+    g->rho = 0.f;
     if (nx > 16384) return fail(h, PLIFE_ERR_INVALID, "rmax=%g gives nx=%d (max 16384)", rmax, nx);
     if (h->slab.on) {
         const int G = h->slab.world, r = h->slab.rank, ny = g->ny;
@@ -238,7 +246,7 @@ int make_grid(plife_handle *h, Grid *g)
         g->rows_up = lo(up + 1) - lo(up);
         g->rows_dn = lo(dn + 1) - lo(dn);
     }
-    g->ks = choose_ks(h, *g);
+    choose_kernel(h, g);
     return PLIFE_OK;
 }
 

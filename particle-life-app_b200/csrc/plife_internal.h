@@ -56,6 +56,8 @@ struct Grid {
     int ly_shift, nly;
     int rows_up, rows_dn; // rows owned by the ring neighbours (migration reach check)
     int ks;               // log2 of the fine bins per cell along x
+    int staged;           // fp32: the staged force kernel serves this grid (host decision, make_grid); else the v1 kernel, ks == 0
+    float rho;            // particles per cell the decisions above were made for (slab mode: the same estimate on every rank)
     __host__ __device__ int nxk() const { return nx << ks; } // fine bins per row
 };
 
