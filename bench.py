@@ -742,10 +742,10 @@ def run_ours(args):
 
 
 def launches_per_step(world, exchange):
-    # per step: 3 scan + scatter + gather + force (binning is fused into the force pass); slabs add the halo pack (written into
-    # the neighbours' memory, then a flag), the halo wait + unpack, a second force launch (interior rows / edge rows) and ONE
-    # kernel for phase FINISH (push migrants + wait + new counts + append arrivals)
-    return 6 if world == 1 else 10
+    # per step: scan (one launch, decoupled look-back) + scatter + gather + force (binning is fused into the force pass); slabs
+    # add the halo pack (written into the neighbours' memory, then a flag), the halo wait + unpack, a second force launch
+    # (interior rows / edge rows) and ONE kernel for phase FINISH (push migrants + wait + new counts + append arrivals)
+    return 4 if world == 1 else 8
 
 
 def main():

@@ -172,6 +172,122 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
     }
 }
 
+// ---- the same scan in ONE launch: chained tiles with decoupled look-back ----
+// Tiles are handed out by a ticket, so a tile's predecessors are always running or done (no deadlock however the CTAs
+// are scheduled).  A tile publishes its own sum at once (AGG) and, after looking back over its predecessors' words - 32 at a
+// time, until it meets one that already carries an inclusive prefix - its inclusive prefix (PREFIX).  Status words are
+// tagged with the launch's epoch, which the last tile to finish advances (together with resetting the ticket), so nothing
+// has to be cleared between launches and a captured CUDA graph can replay the kernel.
+struct ScanState {
+    unsigned int ticket, done, epoch, pad;
+};
+constexpr unsigned long long kScanAgg = 1ull << 32, kScanPrefix = 2ull << 32;
+
+__global__ void __launch_bounds__(kScanThreads) scan_onepass(int32_t *__restrict__ count, int64_t ncell, int ntiles, int carry0,
+                                                             int32_t *__restrict__ cell_end, ScanState *st,
+                                                             volatile unsigned long long *status)
+{
+    __shared__ int sm[33];
+    __shared__ unsigned int s_tile, s_epoch;
+    __shared__ int s_prefix;
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(&st->ticket, 1u);
+        s_epoch = *reinterpret_cast<volatile unsigned int *>(&st->epoch);
+    }
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const unsigned long long tag = (unsigned long long)(s_epoch & 0x3fffffffu) << 34;
+    const int64_t first = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+    const bool full = first + kScanItems <= ncell;
+    if (full) {
+        int4 *p = reinterpret_cast<int4 *>(count + first);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; k++) {
+            int4 q = p[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            p[k] = make_int4(0, 0, 0, 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            v[k] = 0;
+            if (first + k < ncell) {
+                v[k] = count[first + k];
+                count[first + k] = 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) s += v[k];
+    int total;
+    int ex = block_exclusive_scan(s, total, sm);
+    if (threadIdx.x < 32) { // warp 0 publishes and looks back
+        const int lane = threadIdx.x;
+        if (lane == 0) {
+            __threadfence();
+            status[tile] = tag | (tile == 0 ? kScanPrefix : kScanAgg) | (unsigned int)total;
+        }
+        int prefix = 0;
+        for (int base = tile - 1; base >= 0; base -= 32) {
+            const int t = base - lane;
+            unsigned long long w = 0;
+            bool have_prefix = false;
+            for (;;) { // wait until every word of this window is from this launch
+                w = t >= 0 ? status[t] : (tag | kScanPrefix);
+                const bool ready = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) != 0;
+                if (__all_sync(0xffffffffu, ready)) break;
+            }
+            const unsigned pmask = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == 2ull);
+            const int stop = pmask ? __ffs(pmask) - 1 : 31; // nearest predecessor that carries a prefix
+            int val = lane <= stop ? (int)(unsigned int)w : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            prefix += val;
+            have_prefix = pmask != 0;
+            if (have_prefix) break;
+        }
+        if (lane == 0) {
+            if (tile > 0) {
+                __threadfence();
+                status[tile] = tag | kScanPrefix | (unsigned int)(prefix + total);
+            }
+            s_prefix = prefix;
+        }
+    }
+    __syncthreads();
+    ex += s_prefix + carry0;
+    if (tile == 0 && threadIdx.x == 0) cell_end[-1] = carry0; // start of local bin 0
+    if (full) {
+        int4 *o = reinterpret_cast<int4 *>(cell_end + first);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; k++) {
+            int4 q;
+            q.x = ex; ex += v[4 * k];
+            q.y = ex; ex += v[4 * k + 1];
+            q.z = ex; ex += v[4 * k + 2];
+            q.w = ex; ex += v[4 * k + 3];
+            o[k] = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if (first + k < ncell) cell_end[first + k] = ex;
+            ex += v[k];
+        }
+    }
+    if (threadIdx.x == 0) { // the last tile to finish re-arms the state for the next launch
+        __threadfence();
+        if (atomicAdd(&st->done, 1u) == (unsigned int)ntiles - 1u) {
+            st->ticket = 0;
+            st->done = 0;
+            __threadfence();
+            st->epoch = s_epoch + 1u;
+        }
+    }
+}
+
 // ---- small grids: histogram, scan and cursor scatter in ONE CTA ----
 // Up to kSmallBins bins and kSmallN particles (BASELINE config 1: 10 000 particles, 25 x 25 cells) the step is bound by
 // launch latency, not by work: the five launches of K_BIN's consumers (3 scan + scatter) become one.  The histogram lives
@@ -582,6 +698,12 @@ cudaError_t launch_scan(plife_handle *h, const Grid &g)
 {
     int64_t ncell = (int64_t)g.nxk() * g.nly;
     int ntiles = (int)((ncell + kScanTile - 1) / kScanTile);
+    if (!(h->flags & PLIFE_FLAG_SCAN3)) { // one launch (decoupled look-back); d_tile_sums = ScanState + one status word per tile
+        ScanState *st = reinterpret_cast<ScanState *>(h->d_tile_sums);
+        volatile unsigned long long *status = reinterpret_cast<unsigned long long *>(st + 1);
+        scan_onepass<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ntiles, first_index(h), h->d_cell_end, st, status);
+        return cudaGetLastError();
+    }
     int32_t *ts = reinterpret_cast<int32_t *>(h->d_tile_sums);
     scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ts);
     scan_sums<<<1, 1024, 0, h->stream>>>(ts, ntiles, first_index(h), h->d_cell_end);

@@ -184,7 +184,9 @@ int ensure_cells(plife_handle *h, int64_t ncell)
     CU(h, dev_alloc(&raw, (size_t)padded + 4));
     CU(h, cudaMemsetAsync(raw, 0, 16, h->stream));
     h->d_cell_end = raw + 4;
-    CU(h, cudaMalloc(&h->d_tile_sums, sizeof(unsigned long long) * (size_t)(padded / kScanTile)));
+    // scan scratch: ScanState (16 bytes) + one 64-bit status word per tile (the 3-launch variant uses it as int32 tile sums)
+    CU(h, cudaMalloc(&h->d_tile_sums, 16 + sizeof(unsigned long long) * (size_t)(padded / kScanTile)));
+    CU(h, cudaMemsetAsync(h->d_tile_sums, 0, 16 + sizeof(unsigned long long) * (size_t)(padded / kScanTile), h->stream));
     CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * (size_t)padded, h->stream));
     h->cell_cap = padded;
     h->count_dirty = false;
@@ -337,7 +339,7 @@ int resolve_timings(plife_handle *h)
             h->k_ms[k] += ms;
         }
         h->k_launches[PLIFE_K_BIN] += 1;
-        h->k_launches[PLIFE_K_SCAN] += 3;
+        h->k_launches[PLIFE_K_SCAN] += (h->flags & PLIFE_FLAG_SCAN3) ? 3 : 1;
         h->k_launches[PLIFE_K_SCATTER] += 1;
         h->k_launches[PLIFE_K_GATHER] += 1;
         h->k_launches[PLIFE_K_FORCE] += 1;

@@ -311,8 +311,9 @@ def test_slab_errors(native_lib):
         vc.slabs[0].native.step(DT, 1)
 
 
-@pytest.mark.parametrize("flags,bins", [(plife.FLAG_FORCE_V1, 0), (plife.FLAG_NO_FUSED_BIN, 0), (0, 1), (0, 2), (0, 4), (0, 8), (plife.FLAG_NO_FUSED_BIN, 8)],
-                         ids=["v1", "nofusedbin", "bins1", "bins2", "bins4", "bins8", "nofusedbin_bins8"])
+@pytest.mark.parametrize("flags,bins", [(plife.FLAG_FORCE_V1, 0), (plife.FLAG_NO_FUSED_BIN, 0), (0, 1), (0, 2), (0, 4), (0, 8), (plife.FLAG_NO_FUSED_BIN, 8),
+                                        (plife.FLAG_SCAN3, 8)],
+                         ids=["v1", "nofusedbin", "bins1", "bins2", "bins4", "bins8", "nofusedbin_bins8", "scan3"])
 @pytest.mark.parametrize("case", [dict(n=10_000, m=6, rmax=0.04, wrap=True), dict(n=5_000, m=3, rmax=0.065, wrap=True),
                                   dict(n=5_000, m=3, rmax=0.065, wrap=False), dict(n=40_000, m=16, rmax=0.02, wrap=True)],
                          ids=["c1", "fat_wrap", "fat_clamp", "m16"])
