@@ -10,6 +10,8 @@
 // the previous array order).  The atomic cursor scatter is not, so K_GATHER
 // ranks every slot's source index among the source indices of its cell and
 // writes to start+rank; the result is exactly the reference's permutation.
+#include <stdlib.h>
+
 #include "plife_internal.h"
 
 namespace plife {
@@ -172,68 +174,64 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *__restrict__
     }
 }
 
-// ---- the same scan in ONE launch: chained tiles with decoupled look-back ----
-// Tiles are handed out by a ticket, so a tile's predecessors are always running or done (no deadlock however the CTAs
-// are scheduled).  A tile publishes its own sum at once (AGG) and, after looking back over its predecessors' words - 32 at a
-// time, until it meets one that already carries an inclusive prefix - its inclusive prefix (PREFIX).  Status words are
-// tagged with the launch's epoch, which the last tile to finish advances (together with resetting the ticket), so nothing
-// has to be cleared between launches and a captured CUDA graph can replay the kernel.
+// ---- the same scan in ONE launch: persistent CTAs, reduce - look back - scan ----
+// A few hundred CTAs (all resident) each own a contiguous chunk of tiles.  Pass 1 sums the chunk and publishes the sum
+// (AGG); the CTA then looks back over its predecessors' status words - 32 at a time, until it meets one that already
+// carries an inclusive prefix - and publishes its own inclusive prefix (PREFIX); pass 2 re-reads the chunk (L2-hot: a
+// chunk is ~100 KB), scans it with the carry, writes the offsets and zeroes the histogram.  Chunks are handed out by a
+// ticket, so a chunk's predecessors are always running or done.  Status words are tagged with the launch's epoch, which
+// the last CTA to finish advances (together with re-arming the ticket): nothing has to be cleared between launches and a
+// captured CUDA graph can replay the kernel.  (A tile-per-CTA chained scan was measured first: with ~2000 tiles in flight
+// at once the look-back walks of the first wave made it slower than the three-launch scan.)
 struct ScanState {
     unsigned int ticket, done, epoch, pad;
 };
 constexpr unsigned long long kScanAgg = 1ull << 32, kScanPrefix = 2ull << 32;
+constexpr int kScanCtasPerSm = 4;
 
-__global__ void __launch_bounds__(kScanThreads) scan_onepass(int32_t *__restrict__ count, int64_t ncell, int ntiles, int carry0,
-                                                             int32_t *__restrict__ cell_end, ScanState *st,
+__global__ void __launch_bounds__(kScanThreads) scan_onepass(int32_t *__restrict__ count, int64_t ncell, int ntiles, int tiles_per_cta,
+                                                             int carry0, int32_t *__restrict__ cell_end, ScanState *st,
                                                              volatile unsigned long long *status)
 {
     __shared__ int sm[33];
-    __shared__ unsigned int s_tile, s_epoch;
+    __shared__ unsigned int s_chunk, s_epoch;
     __shared__ int s_prefix;
     if (threadIdx.x == 0) {
-        s_tile = atomicAdd(&st->ticket, 1u);
+        s_chunk = atomicAdd(&st->ticket, 1u);
         s_epoch = *reinterpret_cast<volatile unsigned int *>(&st->epoch);
     }
     __syncthreads();
-    const int tile = (int)s_tile;
+    const int chunk = (int)s_chunk;
     const unsigned long long tag = (unsigned long long)(s_epoch & 0x3fffffffu) << 34;
-    const int64_t first = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
-    int v[kScanItems];
+    const int t0 = chunk * tiles_per_cta, t1 = min(t0 + tiles_per_cta, ntiles);
+    // pass 1: the chunk's sum
     int s = 0;
-    const bool full = first + kScanItems <= ncell;
-    if (full) {
-        int4 *p = reinterpret_cast<int4 *>(count + first);
+    for (int tile = t0; tile < t1; ++tile) {
+        const int64_t first = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+        if (first + kScanItems <= ncell) {
+            const int4 *p = reinterpret_cast<const int4 *>(count + first);
 #pragma unroll
-        for (int k = 0; k < kScanItems / 4; k++) {
-            int4 q = p[k];
-            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-            p[k] = make_int4(0, 0, 0, 0);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; k++) {
-            v[k] = 0;
-            if (first + k < ncell) {
-                v[k] = count[first + k];
-                count[first + k] = 0;
+            for (int k = 0; k < kScanItems / 4; k++) {
+                const int4 q = p[k];
+                s += q.x + q.y + q.z + q.w;
             }
+        } else {
+            for (int k = 0; k < kScanItems; k++)
+                if (first + k < ncell) s += count[first + k];
         }
     }
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) s += v[k];
     int total;
-    int ex = block_exclusive_scan(s, total, sm);
+    block_exclusive_scan(s, total, sm);
     if (threadIdx.x < 32) { // warp 0 publishes and looks back
         const int lane = threadIdx.x;
         if (lane == 0) {
             __threadfence();
-            status[tile] = tag | (tile == 0 ? kScanPrefix : kScanAgg) | (unsigned int)total;
+            status[chunk] = tag | (chunk == 0 ? kScanPrefix : kScanAgg) | (unsigned int)total;
         }
         int prefix = 0;
-        for (int base = tile - 1; base >= 0; base -= 32) {
+        for (int base = chunk - 1; base >= 0; base -= 32) {
             const int t = base - lane;
             unsigned long long w = 0;
-            bool have_prefix = false;
             for (;;) { // wait until every word of this window is from this launch
                 w = t >= 0 ? status[t] : (tag | kScanPrefix);
                 const bool ready = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) != 0;
@@ -245,41 +243,70 @@ __global__ void __launch_bounds__(kScanThreads) scan_onepass(int32_t *__restrict
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
             prefix += val;
-            have_prefix = pmask != 0;
-            if (have_prefix) break;
+            if (pmask) break;
         }
         if (lane == 0) {
-            if (tile > 0) {
+            if (chunk > 0) {
                 __threadfence();
-                status[tile] = tag | kScanPrefix | (unsigned int)(prefix + total);
+                status[chunk] = tag | kScanPrefix | (unsigned int)(prefix + total);
             }
             s_prefix = prefix;
         }
     }
     __syncthreads();
-    ex += s_prefix + carry0;
-    if (tile == 0 && threadIdx.x == 0) cell_end[-1] = carry0; // start of local bin 0
-    if (full) {
-        int4 *o = reinterpret_cast<int4 *>(cell_end + first);
+    int carry = s_prefix + carry0;
+    if (chunk == 0 && threadIdx.x == 0) cell_end[-1] = carry0; // start of local bin 0
+    // pass 2: scan the chunk tile by tile with the running carry, zero the histogram
+    for (int tile = t0; tile < t1; ++tile) {
+        const int64_t first = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+        int v[kScanItems];
+        int ts = 0;
+        const bool full = first + kScanItems <= ncell;
+        if (full) {
+            int4 *p = reinterpret_cast<int4 *>(count + first);
 #pragma unroll
-        for (int k = 0; k < kScanItems / 4; k++) {
-            int4 q;
-            q.x = ex; ex += v[4 * k];
-            q.y = ex; ex += v[4 * k + 1];
-            q.z = ex; ex += v[4 * k + 2];
-            q.w = ex; ex += v[4 * k + 3];
-            o[k] = q;
+            for (int k = 0; k < kScanItems / 4; k++) {
+                int4 q = p[k];
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+                p[k] = make_int4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; k++) {
+                v[k] = 0;
+                if (first + k < ncell) {
+                    v[k] = count[first + k];
+                    count[first + k] = 0;
+                }
+            }
         }
-    } else {
 #pragma unroll
-        for (int k = 0; k < kScanItems; k++) {
-            if (first + k < ncell) cell_end[first + k] = ex;
-            ex += v[k];
+        for (int k = 0; k < kScanItems; k++) ts += v[k];
+        int tile_total;
+        int ex = block_exclusive_scan(ts, tile_total, sm) + carry;
+        carry += tile_total;
+        if (full) {
+            int4 *o = reinterpret_cast<int4 *>(cell_end + first);
+#pragma unroll
+            for (int k = 0; k < kScanItems / 4; k++) {
+                int4 q;
+                q.x = ex; ex += v[4 * k];
+                q.y = ex; ex += v[4 * k + 1];
+                q.z = ex; ex += v[4 * k + 2];
+                q.w = ex; ex += v[4 * k + 3];
+                o[k] = q;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; k++) {
+                if (first + k < ncell) cell_end[first + k] = ex;
+                ex += v[k];
+            }
         }
     }
-    if (threadIdx.x == 0) { // the last tile to finish re-arms the state for the next launch
+    if (threadIdx.x == 0) { // the last CTA to finish re-arms the state for the next launch
         __threadfence();
-        if (atomicAdd(&st->done, 1u) == (unsigned int)ntiles - 1u) {
+        if (atomicAdd(&st->done, 1u) == gridDim.x - 1u) {
             st->ticket = 0;
             st->done = 0;
             __threadfence();
@@ -701,7 +728,14 @@ cudaError_t launch_scan(plife_handle *h, const Grid &g)
     if (!(h->flags & PLIFE_FLAG_SCAN3)) { // one launch (decoupled look-back); d_tile_sums = ScanState + one status word per tile
         ScanState *st = reinterpret_cast<ScanState *>(h->d_tile_sums);
         volatile unsigned long long *status = reinterpret_cast<unsigned long long *>(st + 1);
-        scan_onepass<<<ntiles, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ntiles, first_index(h), h->d_cell_end, st, status);
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+        static const int per_sm_env = getenv("PLIFE_SCAN_CTAS") ? atoi(getenv("PLIFE_SCAN_CTAS")) : 0;
+        int nctas = nsm * (per_sm_env > 0 && per_sm_env <= 8 ? per_sm_env : kScanCtasPerSm); // all resident: the CTAs wait for each other
+        if (nctas > ntiles) nctas = ntiles;
+        const int tpc = (ntiles + nctas - 1) / nctas;
+        nctas = (ntiles + tpc - 1) / tpc;
+        scan_onepass<<<nctas, kScanThreads, 0, h->stream>>>(h->d_count, ncell, ntiles, tpc, first_index(h), h->d_cell_end, st, status);
         return cudaGetLastError();
     }
     int32_t *ts = reinterpret_cast<int32_t *>(h->d_tile_sums);
