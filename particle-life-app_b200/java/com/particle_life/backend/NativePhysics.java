@@ -57,7 +57,7 @@ public class NativePhysics extends Physics {
     private static final MemoryLayout SETTINGS = MemoryLayout.structLayout(F64.withName("rmax"), F64.withName("friction"),
             F64.withName("force"), I32.withName("wrap"), I32.withName("reserved"));
 
-    private final Arena arena = Arena.ofShared(); // lives as long as the handle: settings block, matrix, snapshot buffers
+    private final Arena arena = Arena.ofShared(); // lives as long as the handle: settings block, matrix
     private final MemorySegment settingsBlock = arena.allocate(SETTINGS);
     private MemorySegment matrixBlock = MemorySegment.NULL; // re-allocated when the matrix size changes
     private int matrixBlockSize = -1;
@@ -68,6 +68,7 @@ public class NativePhysics extends Physics {
     public static final class Snapshot {
         public MemorySegment positions, velocities, types; // n*2 floats, n*2 floats, n bytes; off-heap, GL-uploadable
         public int particleCount;
+        Arena arena; // owns the three buffers: closed and replaced when the particle count changes (brush / delete every frame)
     }
 
     private final Snapshot[] snapshots = {new Snapshot(), new Snapshot()};
@@ -91,6 +92,12 @@ public class NativePhysics extends Physics {
     @Override
     public void update() {
         try {
+            // Order matters when the matrix SHRANK (setMatrixSize + ensureTypes ran on the Java side): the resident particles
+            // still hold types >= m, so plife_set_matrix would refuse (PLIFE_ERR_STATE).  Upload the retyped particles first -
+            // they validate against the old, larger matrix - then the matrix.  When it grew: matrix first, so that the new
+            // types validate.
+            boolean shrank = settings.matrix.size() < matrixBlockSize;
+            if (dirty && shrank) push();
             pushSettings();
             if (dirty) push();
             check((int) STEP.invoke(handle, settings.dt, 1));
@@ -160,10 +167,12 @@ public class NativePhysics extends Physics {
     public void requestSnapshot() throws Throwable {
         int n = (int) (long) COUNT.invoke(handle);
         Snapshot s = snapshots[snapshotIndex];
-        if (s.particleCount != n || s.positions == null) { // size changed: new buffers (the old ones die with the arena)
-            s.positions = arena.allocate(ValueLayout.JAVA_FLOAT, 2L * n);
-            s.velocities = arena.allocate(ValueLayout.JAVA_FLOAT, 2L * n);
-            s.types = arena.allocate(ValueLayout.JAVA_BYTE, n);
+        if (s.particleCount != n || s.positions == null) { // size changed: free this set's buffers, allocate new ones
+            if (s.arena != null) s.arena.close(); // (its previous snapshot was handed out two requests ago: the renderer is done with it)
+            s.arena = Arena.ofShared();
+            s.positions = s.arena.allocate(ValueLayout.JAVA_FLOAT, 2L * n);
+            s.velocities = s.arena.allocate(ValueLayout.JAVA_FLOAT, 2L * n);
+            s.types = s.arena.allocate(ValueLayout.JAVA_BYTE, n);
             s.particleCount = n;
         }
         check((int) SNAPSHOT_ASYNC_U8.invoke(handle, s.positions, s.velocities, s.types));
@@ -206,7 +215,8 @@ public class NativePhysics extends Physics {
         try {
             if (handle != null) DESTROY.invoke(handle);
             handle = null;
-            arena.close(); // settings block, matrix block, snapshot buffers
+            for (Snapshot s : snapshots) if (s.arena != null) s.arena.close();
+            arena.close(); // settings block, matrix block
         } catch (Throwable ignored) {
         }
         super.kill();

@@ -275,12 +275,24 @@ class Simulation:
         if self.not_reacting_for() <= threshold_ms:
             return False
         if not self.loop.stop(stop_millis):
+            # The abandoned loop thread may still be inside the native step on this handle.  The handle is single-owner
+            # (include/plife.h): only request_stop may come from another thread, and destroying it under a running call
+            # would be a use-after-free.  So: ask it to stop now, free it once the abandoned thread has left.
+            old_thread, old_physics = self.loop._thread, self.physics
             self.loop.kill()
             try:
-                self.physics.force_update_stop()
-                self.physics.kill()
+                old_physics.force_update_stop()
             except Exception:  # noqa: BLE001 - a wedged backend must not keep the reset from happening
                 pass
+
+            def reap():
+                if old_thread is not None:
+                    old_thread.join()
+                try:
+                    old_physics.kill()
+                except Exception:  # noqa: BLE001
+                    pass
+            threading.Thread(target=reap, name="plife-reaper", daemon=True).start()
         self.physics = make_physics()
         self.loop = Loop()
         self.steps = 0

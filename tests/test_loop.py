@@ -185,11 +185,18 @@ def test_simulation_dt_policy_snapshots_and_watchdog():
     sim.snapshot.snapshot_time -= 10_000                      # as if the last snapshot were ten seconds old
     fresh = []
     assert sim.reset_if_not_reacting(lambda: fresh.append(_FakePhysics()) or fresh[-1], threshold_ms=3000, stop_millis=50) is True
-    assert stuck.killed and sim.physics is fresh[0] and sim.not_reacting_for() < 3000
+    # the stuck physics is NOT freed while its abandoned thread may still be inside the native step (single-owner handle):
+    # it is asked to stop at once and killed only after that thread has left
+    assert not stuck.killed and sim.physics is fresh[0] and sim.not_reacting_for() < 3000
     for _ in range(200):
         if fresh[0].updates > 3:
             break
         time.sleep(0.005)
     assert fresh[0].updates > 3                                # the new loop runs the new physics
     gate.set()                                                  # let the abandoned thread finish
+    for _ in range(400):
+        if stuck.killed:
+            break
+        time.sleep(0.005)
+    assert stuck.killed                                         # ... and now the old handle is released
     assert sim.close(2000)
