@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kThreads) bin_f32(const float4 *__restrict__ p
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     float4 p = __ldg(&pt[i]);
-    int cxy = cell_coords((double)p.x, (double)p.y, g);
+    int cxy = cell_coords_fast((double)p.x, (double)p.y, g);
     int c = container_of(cxy, g);
     cell[i] = c < 0 ? -1 : cxy; // slab mode: uploads hold owned particles only; anything else is dropped
     if (c >= 0) atomicAdd(&count[c], 1);
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kThreads) bin_f64(const double2 *__restrict__ 
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     double2 p = __ldg(&pos[i]);
-    int cxy = cell_coords(p.x, p.y, g);
+    int cxy = cell_coords_fast(p.x, p.y, g);
     cell[i] = cxy;
     atomicAdd(&count[container_of(cxy, g)], 1);
 }

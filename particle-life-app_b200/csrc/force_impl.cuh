@@ -474,7 +474,7 @@ struct NextBin {
     __device__ __forceinline__ void add(int i, R x, R y, R vx, R vy, int type, uint32_t id, const Grid &g) const
     {
         if (!cell) return;
-        const int cxy = cell_coords((double)x, (double)y, g);
+        const int cxy = cell_coords_fast((double)x, (double)y, g);
         const int c = container_of(cxy, g);
         if (c >= 0) {
             cell[i] = cxy;

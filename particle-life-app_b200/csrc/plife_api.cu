@@ -227,6 +227,7 @@ int make_grid(plife_handle *h, Grid *g)
     g->nx = nx;
     g->ny = nx;
     g->cs = rmax;
+    g->inv_cs = 1.0 / rmax;
     g->row_lo = 0;
     g->row_hi = nx;
     g->ly_shift = 0;
