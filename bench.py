@@ -293,7 +293,8 @@ def single_gpu_secondary(torch, plife, stream, device, name, precision, steps, l
         gbs = bytes_step * c["n"] / (ms * 1e-3) / 1e9
         out["roofline_step"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                                 "algorithmic_bytes_per_particle_step": bytes_step,
-                                "traffic": traffic.get(name + "_step_bytes_per_particle")}
+                                "traffic": (traffic[name + "_step_bytes_per_particle"] * c["n"] / 1e9) if (precision == plife.F32 and accel is None and name + "_step_bytes_per_particle" in traffic) else None,
+                                "traffic_note": "GB per step: dram__bytes_read + dram__bytes_write summed over the step's kernels (ncu --set full, profiles/r2_traffic.json)"}
         return q, out
     except Exception:
         q.close()
@@ -727,7 +728,9 @@ def run_ours(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES_FORCE,
                      "binding": "fp32 issue (candidate pair evaluations per particle at 16 particles/cell); HBM fraction is low by construction, see fp32 and secondary.C3lo for the HBM-bound regime"},
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak * world, "unit": "GB/s", "frac": step_gbs / (hbm_peak * world),
-                          "algorithmic_bytes_per_particle_step": ALGO_BYTES_STEP},
+                          "algorithmic_bytes_per_particle_step": ALGO_BYTES_STEP,
+                          "traffic": traffic.get("C3_step_bytes_per_particle", 0) * n / 1e9 or None,
+                          "traffic_note": "GB per step over all GPUs: dram bytes of the step's kernels (ncu, profiles/r2_traffic.json)"},
         "fp32": {"achieved": fp32_force_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": fp32_force_tf / fp32_peak_tf if fp32_force_tf else None,
                  "whole_step_achieved": fp32_step_tf, "whole_step_frac": fp32_step_tf / (fp32_peak_tf * world),
                  "flop_per_pair_eval": FLOP_PER_PAIR, "peak_source": fp32_peak_src, "nominal_peak": fp32_nominal_tf,
