@@ -568,6 +568,15 @@ def run_ours(args):
         p.set_profiling(False)
     force_ms = kt["force"][0] / max(1, kt["force"][1])
     per_kernel = {k: v[0] / args.steps for k, v in kt.items()}
+    per_rank = None
+    if world > 1:
+        # the ranks step in lockstep (every step waits for both neighbours' migrants), so the slowest GPU sets the pace:
+        # report every rank's own kernel time next to the step time
+        mine = torch.tensor([per_kernel["force"], sum(per_kernel.values())], device="cuda", dtype=torch.float64)
+        allk = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        per_rank = {"force_ms": [round(float(x[0]), 4) for x in allk], "kernels_ms": [round(float(x[1]), 4) for x in allk],
+                    "note": "per rank: force bucket (both force launches, halo wait and unpack in between) and the sum of all buckets; ms_per_step minus the largest sum is what the end-of-step migration exchange and the rank-to-rank skew cost"}
 
     # ---- end to end through the C ABI with host buffers ----
     ncap = n if world == 1 else n_local + n_local // 8 + 65536
@@ -736,6 +745,7 @@ def run_ours(args):
                  "flop_per_pair_eval": FLOP_PER_PAIR, "peak_source": fp32_peak_src, "nominal_peak": fp32_nominal_tf,
                  "pair_evals_counted": "the reference's candidate pairs (3x3 cells, B/Physics.java:423-439); the kernel itself evaluates fewer (finer internal binning)"},
         "kernel_ms_per_step": per_kernel,
+        "kernel_ms_per_step_by_rank": per_rank,
         "parity_check": parity,
         "secondary": secondary,
         "cpu_baseline": cpu,

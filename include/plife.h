@@ -241,6 +241,9 @@ int plife_rebuild(plife_handle *h, int64_t n_new, const int32_t *src, const int3
  *   halo_send[0] -> down neighbour's halo_recv[1],  halo_send[1] -> up neighbour's halo_recv[0]
  *   mig_send[0]  -> down neighbour's mig_recv[1],   mig_send[1]  -> up neighbour's mig_recv[0]
  * (down = rank-1, up = rank+1, periodic when wrap is on; no exchange across a closed boundary).
+ * Displacement bound (the reference has none): the migration exchange of a step runs while the interior rows are
+ * still being computed, so a particle may enter a neighbour slab only from the slab's first or last row - i.e. it must move
+ * less than one grid row (rmax) per step towards the neighbour - and never further than the neighbour: PLIFE_ERR_STATE otherwise.
  * External exchange (bufs != NULL): buffers are device memory owned by the caller, in 16-byte records:
  * plife_slab_halo_records(nx, halo_cap) / plife_slab_migrate_records(mig_cap) records each.
  * fp32 handles only.  plife_upload accepts only particles of the rank's own rows (PLIFE_ERR_INVALID otherwise);

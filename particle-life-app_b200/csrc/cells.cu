@@ -752,7 +752,7 @@ cudaError_t launch_scatter(plife_handle *h, const Grid &g)
     const bool dev = h->slab.on && h->slab.counts;
     const int n = dev ? (int)h->slab.n_bound : (int)h->n_phys; // physical pre-sort length (dead slots included)
     if (n == 0) return cudaSuccess;
-    const DevInt np{(int)h->n_phys, dev ? &h->slab.counts->n_phys : nullptr};
+    const DevInt np{(int)h->n_phys, dev ? &h->slab.cnt()->n_phys : nullptr};
     const double rho = (double)h->n / ((double)g.nxk() * (g.row_hi - g.row_lo)); // particles per bin
     if (rho >= 4.0) scatter_perm<true><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, np, g, first_index(h), h->d_cell_end, h->d_perm);
     else scatter_perm<false><<<blocks_for(n, kThreads * kScatterUnroll), kThreads, 0, h->stream>>>(h->d_cell, np, g, first_index(h), h->d_cell_end, h->d_perm);
@@ -768,7 +768,7 @@ cudaError_t launch_gather(plife_handle *h, const Grid &g)
     bool stable = !(h->flags & PLIFE_FLAG_UNSTABLE_SORT);
     int nb = h->precision == PLIFE_F32 ? blocks_for(n, kThreads * kGatherUnroll) : blocks_for(n, kThreads);
     if (h->precision == PLIFE_F32) {
-        const DevInt nn{(int)h->n, dev ? &h->slab.counts->n : nullptr};
+        const DevInt nn{(int)h->n, dev ? &h->slab.cnt()->n : nullptr};
         const StableKey key = stable_key_of(h); // slabs: arrivals are ordered by their previous global position
         int *tr = h->slab.on ? h->slab.d_tr : nullptr;
         if (stable)
@@ -793,7 +793,7 @@ StableKey stable_key_of(const plife_handle *h)
     if (h->slab.on) {
         const SlabState &S = h->slab;
         const bool wrap = h->settings.wrap != 0 && S.world > 1;
-        key.cnt = S.counts;
+        key.cnt = S.cnt();
         if (wrap && S.rank == 0 && S.rank != S.world - 1) key.order = 1;  // residents, above, below(seam)
         else if (wrap && S.rank == S.world - 1) key.order = 2;            // above(seam), below, residents
     }

@@ -15,17 +15,18 @@ static IOF32 make_io(plife_handle *h)
                  (h->flags & PLIFE_FLAG_UNSTABLE_SORT) ? 0 : 1, stable_key_of(h)};
 }
 
-static NextBin next_bin(plife_handle *h)
+static NextBin next_bin(plife_handle *h, bool no_leavers = false)
 {
-    if (h->flags & PLIFE_FLAG_NO_FUSED_BIN) return NextBin{nullptr, nullptr, {nullptr, nullptr}, 0};
-    NextBin nb{h->d_cell, h->small_step ? nullptr : h->d_count, {h->slab.on ? h->slab.mig_send[0] : nullptr, h->slab.on ? h->slab.mig_send[1] : nullptr}, (int)h->slab.mig_cap};
+    if (h->flags & PLIFE_FLAG_NO_FUSED_BIN) return NextBin{nullptr, nullptr, {nullptr, nullptr}, 0, nullptr};
+    NextBin nb{h->d_cell, h->small_step ? nullptr : h->d_count, {h->slab.on ? h->slab.mig_send[0] : nullptr, h->slab.on ? h->slab.mig_send[1] : nullptr},
+               (int)h->slab.mig_cap, no_leavers ? h->slab.d_err : nullptr};
     return nb;
 }
 
 // The kernels read the old velocities from s32[cur].vel and write the new ones into s32[cur ^ 1].vel; swapping the two
 // pointers (launch_force_f32_done) makes s32[cur] = {new positions, new velocities} again for every other entry point.
 // `nblocks` CTAs of 128 targets; p.tr / p.n_dev select device-resident target ranges (slab mode).
-cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks, cudaStream_t stream)
+cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks, cudaStream_t stream, bool no_leavers)
 {
     const float *mt = (const float *)h->d_matrix_t;
     const float *mrow = mt + (size_t)p.m * p.m; // row-major copy follows the transposed one
@@ -40,10 +41,10 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
         if (cap_env > 0) cap = cap_env;
         cap = (cap + 15) / 16 * 16;
         if (cap > 1536) cap = 1536;
-        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h), stream);
+        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h, no_leavers), stream);
     }
     if (p.g.ks != 0) return cudaErrorInvalidValue; // the v1 kernel writes results at the compute slot (make_grid never pairs it with fine bins)
-    return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mt, h->acc_kind, next_bin(h), stream);
+    return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mt, h->acc_kind, next_bin(h, no_leavers), stream);
 }
 
 void launch_force_f32_done(plife_handle *h)

@@ -13,8 +13,8 @@ static IOF64 make_io(plife_handle *h)
 
 cudaError_t launch_force_f64(plife_handle *h, const ForceParams<double> &p)
 {
-    NextBin nb{nullptr, nullptr, {nullptr, nullptr}, 0};
-    if (!(h->flags & PLIFE_FLAG_NO_FUSED_BIN)) nb = NextBin{h->d_cell, h->small_step ? nullptr : h->d_count, {nullptr, nullptr}, 0};
+    NextBin nb{nullptr, nullptr, {nullptr, nullptr}, 0, nullptr};
+    if (!(h->flags & PLIFE_FLAG_NO_FUSED_BIN)) nb = NextBin{h->d_cell, h->small_step ? nullptr : h->d_count, {nullptr, nullptr}, 0, nullptr};
     return dispatch_force<IOF64, false>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, (p.n + kForceThreads - 1) / kForceThreads,
                                         (const double *)h->d_matrix_t, h->acc_kind, nb, h->stream);
 }

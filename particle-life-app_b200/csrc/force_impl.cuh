@@ -470,6 +470,7 @@ struct NextBin {
     int32_t *count; // per-bin histogram (zeroed by K_SCAN of this step)
     float4 *mig[2]; // migration messages [down, up] (slab mode) or nullptr
     int mig_cap;
+    int *late_err;  // slab mode, interior launch: a particle that leaves the slab raises this error bit instead (see slab.cu)
     template <typename R>
     __device__ __forceinline__ void add(int i, R x, R y, R vx, R vy, int type, uint32_t id, const Grid &g) const
     {
@@ -482,6 +483,10 @@ struct NextBin {
             return;
         }
         cell[i] = -1; // leaves this slab
+        if (late_err) {
+            atomicOr(late_err, 4); // kErrFar: the migration exchange of this step is already under way
+            return;
+        }
         if (!mig[0]) return;
         int cy = cxy >> 16;
         if (cy == g.ny) cy = g.ny - 1;

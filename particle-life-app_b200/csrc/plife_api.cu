@@ -291,7 +291,7 @@ ForceParams<R> make_params(const plife_handle *h, const Grid &g, double dt)
     ForceParams<R> p{};
     p.n = (int)h->n;
     p.m = h->m;
-    p.n_dev = h->slab.on && h->slab.counts ? &h->slab.counts->n : nullptr;
+    p.n_dev = h->slab.on && h->slab.counts ? &h->slab.cnt()->n : nullptr;
     p.tr = nullptr;
     p.bin_lo = 0;
     p.bin_hi = g.nxk() * g.nly - 1;
@@ -575,7 +575,8 @@ int slab_sort(plife_handle *h, const Grid &g)
 cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_tr, int nblocks, int bin_lo, int bin_hi, cudaStream_t stream,
                        bool first_part, bool last_part)
 {
-    (void)last_part;
+    // the interior launch (first_part) runs next to the migration exchange: its particles must stay in the slab
+    const bool no_leavers = first_part && !last_part;
     cudaError_t e = cudaSuccess;
     if (first_part && h->slab_timing_on) { // profiling: event 4 = start of the force pass (main stream)
         StepTimer tm(h);
@@ -588,7 +589,7 @@ cudaError_t slab_force(plife_handle *h, const Grid &g, double dt, const int *d_t
     p.tr = d_tr;
     p.bin_lo = bin_lo;
     p.bin_hi = bin_hi;
-    if (e == cudaSuccess) e = launch_force_f32_part(h, p, nblocks, stream);
+    if (e == cudaSuccess) e = launch_force_f32_part(h, p, nblocks, stream, no_leavers);
     return e;
 }
 // both launches are queued (and the main stream waits for the edge launch): the new state is the current one

@@ -30,7 +30,7 @@ struct SlabCounts {
     int n;        // live particles
     int n_phys;   // physical length of the pre-sort array (dead slots included)
     int n_old, k_below, k_above;
-    int err;      // sticky error bits (kSlabErr*)
+    int err;      // error bits seen so far (copy of the sticky device word, for the host's ring)
     int sent_dn, sent_up;
     unsigned long long seq; // last finished step
 };
@@ -263,7 +263,11 @@ struct SlabState {
     float4 *peer_base[2]{};         // the neighbours' xbuf mapped into this process / device
     bool peer_ipc[2]{};
     // device-resident counts: a step needs no host synchronisation
-    SlabCounts *counts = nullptr;        // device
+    SlabCounts *counts = nullptr;        // device: TWO structs - a step reads counts[seq & 1], its finish kernel (which runs next to the
+                                         // interior force launch) writes counts[(seq + 1) & 1]
+    int *d_err = nullptr;                // device: sticky error bits (kErr*, slab.cu)
+    SlabCounts *cnt() const { return counts ? counts + (seq & 1) : nullptr; }
+    SlabCounts *nxt() const { return counts ? counts + ((seq + 1) & 1) : nullptr; }
     int *d_tr = nullptr;                 // device: target ranges of the force launches (the gather kernel writes them), 12 ints
     volatile unsigned long long *d_go = nullptr; // device: the finish CTA releases the append CTAs of the same launch
     volatile SlabCounts *h_ring = nullptr; // mapped pinned: the counts after each of the last 8 steps (written by slab_finish)
@@ -398,7 +402,7 @@ cudaError_t launch_snapshot_f32(plife_handle *h, float2 *pos, float2 *vel, int32
 
 // force_f32.cu / force_f64.cu
 cudaError_t launch_force_f32(plife_handle *h, const ForceParams<float> &p);
-cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks, cudaStream_t stream); // slab mode: one of the two launches
+cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, int nblocks, cudaStream_t stream, bool no_leavers = false); // slab mode: one of the two launches
 void launch_force_f32_done(plife_handle *h);                                                  // ... then swap the velocity buffers
 cudaError_t launch_force_f64(plife_handle *h, const ForceParams<double> &p);
 cudaError_t launch_neighbors_f32(plife_handle *h, const ForceParams<float> &p, int32_t *cnt, unsigned long long *hash);

@@ -55,7 +55,7 @@ constexpr int kThreads = 256;
 enum {
     kErrHalo = 1,      // halo row did not fit / grid or bin mismatch between ranks
     kErrTimeout = 2,   // a neighbour's message did not arrive within the wait limit
-    kErrFar = 4,       // a particle crossed more than one slab in one step
+    kErrFar = 4,       // a particle crossed more than one slab in one step, or left the slab from an interior row (>= 1 row in one step)
     kErrClosed = 8,    // a particle left through a closed boundary
     kErrMigCap = 16,   // migration message overflow
     kErrCapacity = 32, // arrivals exceed the particle capacity
@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(kThreads) pack_halo(const float4 *__restrict__
 // which 0: ghost row below (local row 0), right-aligned before the owned block at `first`
 // which 1: ghost row above (local row nly-1), placed after the owned block
 __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_sorted, int32_t *__restrict__ cell_end, Grid g,
-                                                        int first, SlabCounts *__restrict__ cnt, const float4 *msg0, const float4 *msg1,
-                                                        const volatile unsigned long long *flag0, const volatile unsigned long long *flag1,
-                                                        unsigned long long seq, unsigned long long spin_ns)
+                                                        int first, const SlabCounts *__restrict__ cnt, int *__restrict__ err, const float4 *msg0,
+                                                        const float4 *msg1, const volatile unsigned long long *flag0,
+                                                        const volatile unsigned long long *flag1, unsigned long long seq, unsigned long long spin_ns)
 {
     const int which = blockIdx.y;
     const float4 *msg = which ? msg1 : msg0;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_
         if (threadIdx.x == 0) s_timeout = wait_flag(flag, seq, spin_ns) ? 0 : 1;
         __syncthreads();
         if (s_timeout) {
-            if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&cnt->err, kErrTimeout);
+            if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(err, kErrTimeout);
             return;
         }
     }
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) unpack_halo(float4 *__restrict__ pt_
     const int t = blockIdx.x * kThreads + threadIdx.x;
     const int nxk = g.nxk();
     if (hd.x < 0 || hd.y != nxk) { // overflow at the sender, or the ranks disagree about the grid / the bins per cell
-        if (t == 0) atomicOr(&cnt->err, kErrHalo);
+        if (t == 0) atomicOr(err, kErrHalo);
         return;
     }
     const int n = cnt->n;
@@ -189,8 +189,8 @@ constexpr int kMigCtas = 8;
 __global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restrict__ ms0, const float4 *__restrict__ ms1, float4 *peer0, float4 *peer1,
                                                          volatile unsigned long long *pflag0, volatile unsigned long long *pflag1,
                                                          unsigned int *tickets, const volatile unsigned long long *f0,
-                                                         const volatile unsigned long long *f1, unsigned long long seq, SlabCounts *cnt,
-                                                         const float4 *mi0, const float4 *mi1, int has_dn, int has_up, int mig_cap, int cap, int bound,
+                                                         const volatile unsigned long long *f1, unsigned long long seq, const SlabCounts *cnt,
+                                                         SlabCounts *nxt, int *errw, const float4 *mi0, const float4 *mi1, int has_dn, int has_up, int mig_cap, int cap, int bound,
                                                          volatile SlabCounts *ring, volatile unsigned long long *go, unsigned long long spin_ns, Grid g,
                                                          float4 *__restrict__ pt, float2 *__restrict__ vel, int32_t *__restrict__ cell,
                                                          int32_t *__restrict__ count)
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restric
     // ---- finish ----
     if (blockIdx.x == 0 && dir == 0) {
         if (threadIdx.x == 0) {
-            int err = cnt->err;
+            int err = 0;
             if (f0 && !wait_flag(f0, seq, spin_ns)) err |= kErrTimeout;
             if (f1 && !wait_flag(f1, seq, spin_ns)) err |= kErrTimeout;
             const volatile int *s0 = reinterpret_cast<const volatile int *>(ms0), *s1 = reinterpret_cast<const volatile int *>(ms1);
@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restric
                 k_below = k_above = 0;
             }
             if (L > bound || cnt->n_phys > bound) err |= kErrBound;
+            if (err) atomicOr(errw, err);
+            err = *reinterpret_cast<volatile int *>(errw); // everything found so far, by any kernel (sticky)
             SlabCounts c;
             c.n_old = L;
             c.k_below = k_below;
@@ -243,7 +245,9 @@ __global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restric
             c.sent_dn = sent_dn;
             c.sent_up = sent_up;
             c.seq = seq;
-            *cnt = c;
+            *nxt = c; // the next step reads the other struct: this kernel may run next to this step's interior force launch
+            __threadfence();
+            *go = seq; // release the other CTAs of this kernel before the (slow) host-visible copy
             volatile SlabCounts *r = ring + (seq & 7);
             r->seq = 0;
             __threadfence_system();
@@ -251,8 +255,7 @@ __global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restric
             r->err = c.err; r->sent_dn = c.sent_dn; r->sent_up = c.sent_up;
             __threadfence_system();
             r->seq = seq;
-            __threadfence();
-            *go = seq; // release the other CTAs of this kernel
+            __threadfence_system();
         }
     } else if (threadIdx.x == 0) {
         const unsigned long long t0 = wall_ns();
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restric
     __syncthreads();
     // ---- append ----
     const float4 *msg = dir ? mi1 : mi0;
-    const volatile SlabCounts *vc = cnt;
+    const volatile SlabCounts *vc = nxt;
     const int k = dir ? vc->k_above : vc->k_below;
     if (!msg || k == 0) return;
     const int base = vc->n_old + (dir ? vc->k_below : 0);
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kThreads) slab_migrate(const float4 *__restric
         const int c = container_of(cxy, g);
         cell[dst] = c < 0 ? -1 : cxy;
         if (c >= 0) atomicAdd(count + c, 1);
-        else atomicOr(&cnt->err, kErrOwner); // sender and receiver disagree about ownership
+        else atomicOr(errw, kErrOwner); // sender and receiver disagree about ownership
     }
 }
 
@@ -298,7 +301,7 @@ int report(plife_handle *h, int err)
     if (!err) return PLIFE_OK;
     h->slab.err_seen = err;
     if (err & kErrTimeout) return fail(h, PLIFE_ERR_STATE, "slab: timed out waiting for a neighbour's message");
-    if (err & kErrFar) return fail(h, PLIFE_ERR_STATE, "slab: a particle crossed more than one slab in one step");
+    if (err & kErrFar) return fail(h, PLIFE_ERR_STATE, "slab: a particle moved too far in one step (left its slab from an interior row, or crossed more than one slab)");
     if (err & kErrClosed) return fail(h, PLIFE_ERR_STATE, "slab: particle left through a closed boundary");
     if (err & kErrMigCap) return fail(h, PLIFE_ERR_STATE, "slab: migration message overflow (raise mig_cap)");
     if (err & kErrCapacity) return fail(h, PLIFE_ERR_OOM, "slab: particle capacity exceeded by arrivals");
@@ -339,6 +342,7 @@ void slab_release(plife_handle *h)
     }
     if (S.h_ring) cudaFreeHost((void *)S.h_ring);
     cudaFree(S.counts);
+    cudaFree(S.d_err);
     cudaFree(S.d_tr);
     cudaFree((void *)S.d_go);
     for (int k = 0; k < 4; k++)
@@ -411,7 +415,8 @@ int slab_set_counts(plife_handle *h)
     c.n_phys = (int)h->n_phys;
     c.n_old = (int)h->n_phys;
     c.seq = S.seq - 1;
-    cudaError_t e = cudaMemcpyAsync(S.counts, &c, sizeof c, cudaMemcpyHostToDevice, h->stream);
+    cudaError_t e = cudaMemcpyAsync(S.cnt(), &c, sizeof c, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(S.d_err, 0, sizeof(int), h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return slab_fail(h, PLIFE_ERR_CUDA, cudaGetErrorString(e));
     S.seq_known = S.seq - 1;
@@ -484,8 +489,10 @@ int plife_slab_configure(plife_handle *h, int32_t rank, int32_t world, int64_t h
             return fail(h, PLIFE_ERR_OOM, "slab_configure: allocating exchange buffers failed");
         }
     }
-    cudaError_t e = cudaMalloc((void **)&S.counts, sizeof(SlabCounts));
-    if (e == cudaSuccess) e = cudaMemset(S.counts, 0, sizeof(SlabCounts));
+    cudaError_t e = cudaMalloc((void **)&S.counts, 2 * sizeof(SlabCounts));
+    if (e == cudaSuccess) e = cudaMemset(S.counts, 0, 2 * sizeof(SlabCounts));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&S.d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(S.d_err, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void **)&S.d_go, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset((void *)S.d_go, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc((void **)&S.d_tr, 12 * sizeof(int));
@@ -641,22 +648,40 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         S.phase = PLIFE_SLAB_FORCE;
         return PLIFE_OK;
     }
+    // phase FINISH as one launch: push the migrants, wait for the neighbours', new counts, append the arrivals.
+    // `vel_new` = the velocity buffer this step's force launches write (the arrivals' velocities join it).
+    auto launch_migrate = [&](cudaStream_t st, float2 *vel_new) -> cudaError_t {
+        const bool peer = S.peer_mode;
+        dim3 mg(kMigCtas, 2);
+        slab_migrate<<<mg, kThreads, 0, st>>>(
+            S.mig_send[0], S.mig_send[1], peer && has_dn ? mig_slot(dn, S, parity, 1) : nullptr, peer && has_up ? mig_slot(up, S, parity, 0) : nullptr,
+            peer && has_dn ? flag_of(dn, F_MIG_UP) : nullptr, peer && has_up ? flag_of(up, F_MIG_DN) : nullptr, peer ? tickets + 2 : nullptr,
+            peer && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, peer && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr, S.seq, S.cnt(), S.nxt(), S.d_err,
+            has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr, has_dn ? 1 : 0, has_up ? 1 : 0, (int)S.mig_cap, (int)h->cap, (int)S.n_bound,
+            S.h_ring, S.d_go, S.spin_ns, g, h->s32[h->cur].pt, vel_new, h->d_cell, h->d_count);
+        return cudaGetLastError();
+    };
     if (phase == PLIFE_SLAB_FORCE) {
         const int sorted = h->cur ^ 1;
         const bool peer = S.peer_mode;
         const int nxk = g.nxk();
-        // interior rows: they read owned rows only, so the halo may still be in flight
+        // interior rows: they read owned rows only, so the halo may still be in flight.  Their particles must stay in the slab
+        // (a particle may enter a neighbour slab only from the first / last owned row, i.e. move less than a row per step
+        // towards it): the migration exchange runs next to this launch, a late leaver raises kErrFar.
         const int nb_all = (int)((S.n_bound + 127) / 128) + 1;
         const int nb_edge = (int)((2 * S.halo_cap + 127) / 128) + 2;
         CUS(h, slab_force(h, g, dt, S.d_tr, nb_all, nxk, (g.nly - 1) * nxk - 1, h->stream, true, false));
         dim3 grid(32, 2);
-        unpack_halo<<<grid, kThreads, 0, side>>>(h->s32[sorted].pt, h->d_cell_end, g, first, S.counts,
+        unpack_halo<<<grid, kThreads, 0, side>>>(h->s32[sorted].pt, h->d_cell_end, g, first, S.cnt(), S.d_err,
                                                  has_dn ? halo_in[0] : nullptr, has_up ? halo_in[1] : nullptr,
                                                  peer && has_dn ? flag_of(S.xbuf, F_HALO_DN) : nullptr,
                                                  peer && has_up ? flag_of(S.xbuf, F_HALO_UP) : nullptr, S.seq, S.spin_ns);
         CUS(h, cudaGetLastError());
         CUS(h, slab_force(h, g, dt, S.d_tr + 4, nb_edge, 0, nxk * g.nly - 1, side, false, true));
         if (S.peer_mode) {
+            // the whole migration exchange also runs on the side stream, next to the interior launch: nothing of it is left on
+            // the critical path (the arrivals' velocities go into the buffer the force launches are writing)
+            CUS(h, launch_migrate(side, h->s32[h->cur ^ 1].vel));
             CUS(h, cudaEventRecord(S.ev_edge, side));
             CUS(h, cudaStreamWaitEvent(h->stream, S.ev_edge, 0));
         }
@@ -664,19 +689,10 @@ int plife_slab_phase(plife_handle *h, int32_t phase, double dt)
         S.phase = PLIFE_SLAB_FINISH;
         return PLIFE_OK;
     }
-    // PLIFE_SLAB_FINISH: push the migrants, wait for the neighbours', new counts, append the arrivals - one launch
-    {
-        const bool peer = S.peer_mode;
-        dim3 mg(kMigCtas, 2);
-        slab_migrate<<<mg, kThreads, 0, h->stream>>>(
-            S.mig_send[0], S.mig_send[1], peer && has_dn ? mig_slot(dn, S, parity, 1) : nullptr, peer && has_up ? mig_slot(up, S, parity, 0) : nullptr,
-            peer && has_dn ? flag_of(dn, F_MIG_UP) : nullptr, peer && has_up ? flag_of(up, F_MIG_DN) : nullptr, peer ? tickets + 2 : nullptr,
-            peer && has_dn ? flag_of(S.xbuf, F_MIG_DN) : nullptr, peer && has_up ? flag_of(S.xbuf, F_MIG_UP) : nullptr, S.seq, S.counts,
-            has_dn ? mig_in[0] : nullptr, has_up ? mig_in[1] : nullptr, has_dn ? 1 : 0, has_up ? 1 : 0, (int)S.mig_cap, (int)h->cap, (int)S.n_bound,
-            S.h_ring, S.d_go, S.spin_ns, g, h->s32[h->cur].pt, h->s32[h->cur].vel, h->d_cell, h->d_count);
-        CUS(h, cudaGetLastError());
-        CUS(h, cudaEventRecord(S.step_done[S.seq & 3], h->stream));
-    }
+    // PLIFE_SLAB_FINISH.  Peer exchange: everything is queued already.  External exchange: the host has moved the migration
+    // messages between the phases; consume them now.
+    if (!S.peer_mode) CUS(h, launch_migrate(h->stream, h->s32[h->cur].vel));
+    CUS(h, cudaEventRecord(S.step_done[S.seq & 3], h->stream));
     S.phase = PLIFE_SLAB_SORT;
     S.seq++;
     h->steps++;
