@@ -349,7 +349,7 @@ def slab_parity_check(torch, dist, plife, stream, rank, world, local_rank, excha
     return bool(int(t[0].item())), moved
 
 
-def histogram_pair_evals(torch, dist, containers, nx, nly, first, rank, world, wrap, pos_xy, rmax, row_lo):
+def histogram_pair_evals(torch, dist, containers, nx, nly, first, rank, world, wrap, pos_xy, rmax, row_lo, device="cuda"):
     """Candidate pairs (i, j != i in the 3x3 cells of i) of this rank's OWNED rows as the cell histograms imply them:
     sum_c occ(c) * sum_{3x3} occ - n_owned.  The rows next to the slab come from their OWNERS' histograms (all-gather),
     not from this rank's ghost rows, so the number also checks that the halo exchange delivered the right rows.
@@ -359,7 +359,7 @@ def histogram_pair_evals(torch, dist, containers, nx, nly, first, rank, world, w
     ny = nx
     ends = containers.astype(np.int64).reshape(nly, nx)[1:nly - 1]  # owned rows (local rows 1 .. nly-2)
     occ = np.diff(np.concatenate([[first], ends.reshape(-1)])).reshape(nly - 2, nx)
-    edge = torch.tensor(np.stack([occ[0], occ[1], occ[-1]]), device="cuda", dtype=torch.int64)  # first, second, last owned row
+    edge = torch.tensor(np.stack([occ[0], occ[1], occ[-1]]), device=device, dtype=torch.int64)  # first, second, last owned row
     edges = [torch.zeros_like(edge) for _ in range(world)]
     dist.all_gather(edges, edge)
     zero = np.zeros(nx, np.int64)
