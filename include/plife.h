@@ -50,6 +50,7 @@ extern "C" {
                                       settings have been stable for two steps; any change of dt, settings or particles re-captures) */
 /* 16 was PLIFE_FLAG_PAIRS (round 1's experimental two-targets-per-lane kernel, removed); the bit is ignored */
 #define PLIFE_FLAG_SCAN3 32         /* exclusive scan over the bins as three launches (tile sums, scan of sums, apply) instead of one */
+#define PLIFE_FLAG_NO_CELLS 64      /* fp32, at most 65536 particles: use the staged force kernel instead of the warp-per-cell one */
 #define PLIFE_FLAG_NO_FUSED_BIN 8  /* do not fuse the next step's binning into the force pass */
 #define PLIFE_FLAG_FORCE_V1 4      /* fp32: use the global-memory force kernel instead of the shared-memory staged one */
 

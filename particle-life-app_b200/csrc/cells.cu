@@ -322,11 +322,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_onepass(int32_t *__restrict
 constexpr int kSmallThreads = 1024;
 
 __global__ void __launch_bounds__(kSmallThreads) small_sort(const int32_t *__restrict__ cell, int n_phys, Grid g, int nbins,
-                                                            int32_t *__restrict__ cell_end, int32_t *__restrict__ perm)
+                                                            int32_t *__restrict__ cell_end, int32_t *__restrict__ perm,
+                                                            volatile int *__restrict__ max_occ)
 {
     extern __shared__ int s_cnt[]; // [nbins]
     __shared__ int sm[33];
+    __shared__ int s_max;
     const int tid = threadIdx.x;
+    if (tid == 0) s_max = 0;
     for (int b = tid; b < nbins; b += kSmallThreads) s_cnt[b] = 0;
     __syncthreads();
     for (int i = tid; i < n_phys; i += kSmallThreads) {
@@ -337,8 +340,15 @@ __global__ void __launch_bounds__(kSmallThreads) small_sort(const int32_t *__res
     // exclusive scan: thread t owns the bins [t*B, (t+1)*B)
     const int B = (nbins + kSmallThreads - 1) / kSmallThreads;
     const int b0 = tid * B, b1 = min(b0 + B, nbins);
-    int local = 0;
-    for (int b = b0; b < b1; ++b) local += s_cnt[b];
+    int local = 0, mx = 0;
+    for (int b = b0; b < b1; ++b) {
+        local += s_cnt[b];
+        mx = max(mx, s_cnt[b]);
+    }
+    // fullest bin of this step -> host (mapped pinned memory, read without synchronising: it picks the force kernel of
+    // the following steps - one warp per cell only pays while no cell is much fuller than the average)
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((tid & 31) == 0) atomicMax(&s_max, mx);
     int total;
     int ex = block_exclusive_scan(local, total, sm);
     for (int b = b0; b < b1; ++b) {
@@ -346,7 +356,10 @@ __global__ void __launch_bounds__(kSmallThreads) small_sort(const int32_t *__res
         s_cnt[b] = ex; // cursor = start of the bin
         ex += c;
     }
-    if (tid == 0) cell_end[-1] = 0;
+    if (tid == 0) {
+        cell_end[-1] = 0;
+        if (max_occ) *max_occ = s_max; // (block_exclusive_scan synchronised since the atomicMax above)
+    }
     __syncthreads();
     for (int i = tid; i < n_phys; i += kSmallThreads) { // B/Physics.java:343-348 (order inside a bin is fixed by K_GATHER)
         const int c = container_of(__ldg(&cell[i]), g);
@@ -717,7 +730,7 @@ cudaError_t launch_bin(plife_handle *h, const Grid &g)
 cudaError_t launch_small_sort(plife_handle *h, const Grid &g)
 {
     const int nbins = g.nxk() * g.nly;
-    small_sort<<<1, kSmallThreads, sizeof(int) * nbins, h->stream>>>(h->d_cell, (int)h->n_phys, g, nbins, h->d_cell_end, h->d_perm);
+    small_sort<<<1, kSmallThreads, sizeof(int) * nbins, h->stream>>>(h->d_cell, (int)h->n_phys, g, nbins, h->d_cell_end, h->d_perm, h->h_maxocc);
     return cudaGetLastError();
 }
 

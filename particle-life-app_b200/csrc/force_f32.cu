@@ -31,6 +31,8 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
     const float *mt = (const float *)h->d_matrix_t;
     const float *mrow = mt + (size_t)p.m * p.m; // row-major copy follows the transposed one
     const double rho = p.g.rho; // particles per cell (make_grid's estimate: the same on every rank of a slab run)
+    if (p.g.staged == 2) // small particle counts: one warp per cell
+        return dispatch_force_cells(make_io(h), h->d_cell_end, h->d_cell_sorted, p, mt, h->acc_kind, next_bin(h, no_leavers), stream);
     if (p.g.staged) {
         // capacity of one staged row range: the CTA's 128 targets + K bins on either side (2 rho (1 + 1/K) particles on
         // average) + 4.5 sigma of that count (uniform state; anything denser streams in chunks, traverse_chunked).

@@ -698,6 +698,35 @@ __device__ __forceinline__ void traverse_global32(const IOF32 &io, const int32_t
     }
 }
 
+// the same walk handing the visitor PLAIN types (matrix in global / shared memory instead of the per-lane table)
+template <typename V>
+__device__ __forceinline__ void traverse_global32_plain(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g, int wrap,
+                                                        int i, float xi, float yi, int cx0, int cy0, V &v)
+{
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+        const int ox = k % 3 - 1, oy = k / 3 - 1;
+        int cx = wrap_container(cx0 + ox, g.nx);
+        int cy = wrap_container(cy0 + oy, g.ny);
+        if (wrap) {
+            cx = wrap_container(cx, g.nx);
+            cy = wrap_container(cy, g.ny);
+        } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
+            continue;
+        }
+        const int ci = cx + local_row(cy, g) * g.nx;
+        int s, e;
+        cell_span(cell_end, ci, ci, g.ks, s, e);
+        for (int j = s; j < e; ++j) {
+            if (j == i) continue;
+            const Cand<float> q = io.cand(j);
+            const float dx = wrap ? wrap_connection(xi, q.x) : q.x - xi;
+            const float dy = wrap ? wrap_connection(yi, q.y) : q.y - yi;
+            v.pair(j, q, dx, dy);
+        }
+    }
+}
+
 // interior lane, staged ranges: 3 rows x bins [fb - K, fb + K]
 template <typename V>
 __device__ __forceinline__ void traverse_staged(const int32_t *__restrict__ cell_end, const Grid &g, float xi, float yi, int fb,
@@ -926,6 +955,210 @@ inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_en
     default: return cudaErrorInvalidValue;
     }
 #undef PLIFE_LAUNCH_STAGED
+    return cudaGetLastError();
+}
+
+// ---- small particle counts: one warp per cell, candidates spread over the lanes (fp32) -------------------------------
+// With ten thousand particles (BASELINE config 1: the app's own default) the staged kernel has one warp per scheduler
+// running a 4 500-instruction dependent stream, and one lane in six sits on the periodic seam and walks global memory one
+// L2 round trip per candidate: 43 us for 0.3 us worth of arithmetic.  Here a warp owns a CELL: it copies the particles
+// of the cell's 9 neighbour cells - in the reference's order and with its cell wrapping (B/Physics.java:407-421), so seam
+// cells and the duplicate visits of tiny grids need no special case - into its slice of shared memory, then LPT lanes share
+// one target: each takes every LPT-th candidate with the exact per-pair min-image (wrap_connection), and a shuffle adds the
+// partial sums.  A target whose un-clamped coordinates are not its cell's (x or y exactly 1.0, the fat strip) takes the
+// literal walk.  Only used on the plain cell list (ks == 0), so the compute order is the reference's order.
+constexpr int kCellsLpt = 4; // lanes per target
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kForceThreads) force_kernel_cells(IOF32 io, const int32_t *__restrict__ cell_end,
+                                                                   const int32_t *__restrict__ cell_sorted, ForceParams<float> P,
+                                                                   const float *__restrict__ gMt, int capw, int wpc, NextBin nb)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kWarps = kForceThreads / 32;
+    float4 *buf = reinterpret_cast<float4 *>(smem_raw) + (size_t)(threadIdx.x >> 5) * capw; // this warp's candidates
+    float *sM = reinterpret_cast<float *>(smem_raw + (size_t)kWarps * capw * 16);
+    const Grid g = P.g;
+    load_matrix_smem(sM, gMt, P.m, FAST ? P.fast_a_scale : 1.0f);
+
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int cell = w / wpc, part = w % wpc;
+    if (cell >= g.nx * g.ny) return;
+    const int ccx = cell % g.nx, ccy = cell / g.nx;
+    int cs, ce;
+    cell_span(cell_end, cell, cell, 0, cs, ce);
+    const int nt = ce - cs;
+    constexpr int TPP = 32 / kCellsLpt; // targets per pass
+    if (part * TPP >= nt) return;
+    // the 9 neighbour cells, lane k < 9 holds cell k of the reference's order (:88-98, :407-421)
+    int s_k = 0, len_k = 0;
+    if (lane < 9) {
+        const int ox = lane % 3 - 1, oy = lane / 3 - 1;
+        int cx = wrap_container(ccx + ox, g.nx), cy = wrap_container(ccy + oy, g.ny);
+        bool use = true;
+        if (P.wrap) {
+            cx = wrap_container(cx, g.nx);
+            cy = wrap_container(cy, g.ny);
+        } else if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny) {
+            use = false;
+        }
+        if (use) {
+            int e_k;
+            cell_span(cell_end, cx + cy * g.nx, cx + cy * g.nx, 0, s_k, e_k);
+            len_k = e_k - s_k;
+        }
+    }
+    int off_k = len_k; // exclusive prefix of the lengths over lanes 0..8
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, off_k, o);
+        if (lane >= o) off_k += t;
+    }
+    const int T = __shfl_sync(0xffffffffu, off_k, 8); // all candidates of the cell's targets
+    off_k -= len_k;
+    const bool single = T <= capw - 2 * kCellsLpt * 4;
+
+    const int target = lane % TPP, sub = lane / TPP;
+    bool loaded = false;
+#pragma unroll 1
+    for (int t0 = part * TPP; t0 < nt; t0 += wpc * TPP) {
+        const int t = t0 + target;
+        const bool active = t < nt;
+        const int i = cs + (active ? t : 0); // sorted index == reference slot (ks == 0, single GPU)
+        const float4 me = __ldg(io.pt + i);
+        const int own = __float_as_int(me.z) >> kTypeShift;
+        const int cxy = __ldg(cell_sorted + i);
+        const bool plain = (cxy & 0xffff) == ccx && (cxy >> 16) == ccy; // else: un-clamped coordinates differ from the cell's
+        MatrixView<float, kMatShared> M{nullptr, sM, P.m, own, 1.0f, 0u, 0u};
+        M.init();
+        float vx, vy;
+        io.self_vel(i, vx, vy);
+        FastParticleLife32<kMatShared> vf{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        LiteralForce<float, KIND, kMatShared> vl{0.f, 0.f, P.r2, P.invr, P.k2, P.accp, M}; // this lane's share of the increments
+#pragma unroll 1
+        for (int c0 = 0; c0 < T; c0 += capw - 2 * kCellsLpt * 4) {
+            const int clen = min(capw - 2 * kCellsLpt * 4, T - c0);
+            if (!(single && loaded)) {
+                __syncwarp();
+                for (int base = 0; base < clen + kCellsLpt * 4; base += 32) { // uniform trip count: the shuffles need every lane
+                    const int idx = base + lane, f = c0 + idx;
+                    int src = -1;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { // which of the 9 cells holds flat index f
+                        const int ok = __shfl_sync(0xffffffffu, off_k, k), sk = __shfl_sync(0xffffffffu, s_k, k),
+                                  lk = __shfl_sync(0xffffffffu, len_k, k);
+                        if (idx < clen && f >= ok && f < ok + lk) src = sk + f - ok;
+                    }
+                    float4 q = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f); // padding: far away
+                    if (src >= 0) {
+                        q = __ldg(io.pt + src);
+                        q.z = __int_as_float(__float_as_int(q.z) >> kTypeShift);
+                    }
+                    if (idx < clen + kCellsLpt * 4) buf[idx] = q;
+                }
+                loaded = true;
+                __syncwarp();
+            }
+            if (active && plain) {
+                for (int j = sub; j < clen; j += kCellsLpt * 4) { // 4 candidates of this lane per trip (padded)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 q = buf[j + u * kCellsLpt];
+                        const float dx = P.wrap ? wrap_connection(me.x, q.x) : q.x - me.x; // :464-467
+                        const float dy = P.wrap ? wrap_connection(me.y, q.y) : q.y - me.y;
+                        const Cand<float> cq{q.x, q.y, __float_as_int(q.z), 0u};
+                        if constexpr (FAST) vf.pair(-1, cq, dx, dy);
+                        else vl.pair(-1, cq, dx, dy);
+                    }
+                }
+            }
+        }
+        float ax, ay;
+        if constexpr (FAST) {
+            ax = vf.ax;
+            ay = vf.ay;
+        } else {
+            ax = vl.vx;
+            ay = vl.vy;
+        }
+#pragma unroll
+        for (int o = TPP; o < 32; o <<= 1) {
+            ax += __shfl_xor_sync(0xffffffffu, ax, o);
+            ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        }
+        if (!active || sub != 0) continue;
+        float nvx, nvy;
+        if (!plain) { // rare: the literal 9-cell walk around the un-clamped coordinates
+            const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
+            MatrixView<float, kMatGlobal> Mg{gMt, nullptr, P.m, own, FAST ? P.fast_a_scale : 1.0f, 0u, 0u};
+            if constexpr (FAST) {
+                FastParticleLife32<kMatGlobal> v2{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, Mg};
+                traverse_global32_plain(io, cell_end, g, P.wrap, i, me.x, me.y, cx0, cy0, v2);
+                ax = v2.ax;
+                ay = v2.ay;
+            } else {
+                LiteralForce<float, KIND, kMatGlobal> v2{0.f, 0.f, P.r2, P.invr, P.k2, P.accp, Mg};
+                traverse_global32_plain(io, cell_end, g, P.wrap, i, me.x, me.y, cx0, cy0, v2);
+                ax = v2.vx;
+                ay = v2.vy;
+            }
+        }
+        if constexpr (FAST) {
+            nvx = fmaf(P.fast_k, ax, vx * P.mu);
+            nvy = fmaf(P.fast_k, ay, vy * P.mu);
+        } else {
+            nvx = vx * P.mu + ax;
+            nvy = vy * P.mu + ay;
+        }
+        float nx_ = fmaf(nvx, P.dt, me.x);
+        float ny_ = fmaf(nvy, P.dt, me.y);
+        if (P.wrap) {
+            nx_ = range_wrap(nx_);
+            ny_ = range_wrap(ny_);
+        } else {
+            nx_ = range_clamp(nx_);
+            ny_ = range_clamp(ny_);
+        }
+        io.store(i, nx_, ny_, nvx, nvy, own, __float_as_uint(me.w));
+        nb.add(i, nx_, ny_, nvx, nvy, own, __float_as_uint(me.w), g);
+    }
+}
+
+inline cudaError_t dispatch_force_cells(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted, const ForceParams<float> &P,
+                                        const float *gMt, int kind, NextBin nbin, cudaStream_t stream)
+{
+    const int ncell = P.g.nx * P.g.ny;
+    // warps per cell: enough to fill the machine several times over; a warp whose first pass lies beyond the cell's
+    // particles leaves at once, so fuller cells simply keep more of their warps
+    int wpc = (4800 + ncell - 1) / ncell;
+    if (wpc > 16) wpc = 16;
+    if (wpc < 1) wpc = 1;
+    int capw = (int)(9.0f * P.g.rho * 1.5f) + 64;
+    capw = (capw + 31) / 32 * 32;
+    if (capw > 1024) capw = 1024;
+    const int nwarps = ncell * wpc;
+    const int nblocks = (nwarps + kForceThreads / 32 - 1) / (kForceThreads / 32);
+    const size_t sbytes = (size_t)(kForceThreads / 32) * capw * 16 + (size_t)P.m * P.m * 4;
+#define PLIFE_LAUNCH_CELLS(KIND, FAST)                                                                           \
+    do {                                                                                                         \
+        auto kfn = force_kernel_cells<KIND, FAST>;                                                               \
+        if (sbytes > 48 * 1024) {                                                                                \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);  \
+            if (e != cudaSuccess) return e;                                                                      \
+        }                                                                                                        \
+        kfn<<<nblocks, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, P, gMt, capw, wpc, nbin);     \
+    } while (0)
+    switch (kind) {
+    case PLIFE_ACC_PARTICLE_LIFE: PLIFE_LAUNCH_CELLS(PLIFE_ACC_PARTICLE_LIFE, true); break;
+    case PLIFE_ACC_PARTICLE_LIFE_R: PLIFE_LAUNCH_CELLS(PLIFE_ACC_PARTICLE_LIFE_R, false); break;
+    case PLIFE_ACC_PARTICLE_LIFE_R2: PLIFE_LAUNCH_CELLS(PLIFE_ACC_PARTICLE_LIFE_R2, false); break;
+    case PLIFE_ACC_ROTATOR_90: PLIFE_LAUNCH_CELLS(PLIFE_ACC_ROTATOR_90, false); break;
+    case PLIFE_ACC_ROTATOR_ATTR: PLIFE_LAUNCH_CELLS(PLIFE_ACC_ROTATOR_ATTR, false); break;
+    case PLIFE_ACC_PLANETS: PLIFE_LAUNCH_CELLS(PLIFE_ACC_PLANETS, false); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef PLIFE_LAUNCH_CELLS
     return cudaGetLastError();
 }
 

@@ -210,6 +210,21 @@ void choose_kernel(const plife_handle *h, Grid *g)
     // staged kernel whenever the per-lane matrix table fits (m <= 32); below ~4 particles per cell the per-CTA staging and
     // table fill cost more than they save and the v1 kernel (global-memory walk, plain cell list) wins
     if (h->precision != PLIFE_F32 || (h->flags & PLIFE_FLAG_FORCE_V1) || h->m > 32 || rho < 4.0) return;
+    // small particle counts (latency-bound: the machine is mostly empty): one warp per cell on the plain cell list
+    // - while no cell is much fuller than the average (small_sort reports the fullest cell of every step; the value is read
+    // without synchronising, a step or two late): in a clustered state a warp per cell is badly balanced and the staged
+    // kernel, which streams dense ranges through shared memory in chunks, is the faster one again (crossover measured at
+    // about 6 x the mean on an evolving 10 000-particle state; hysteresis so that the choice does not flip every step).
+    if (!h->slab.on && h->n <= kSmallN && (int64_t)g->nx * g->ny <= kSmallBins && h->m <= 64 && rho <= 64.0 && !(h->flags & PLIFE_FLAG_NO_CELLS)) {
+        // (the staged path counts per fine bin: K bins per cell, so scale to an upper bound of the cell's count)
+        const int occ = h->h_maxocc ? (*h->h_maxocc << (h->last_grid.staged == 1 ? h->last_grid.ks : 0)) : 0;
+        const double mean = rho > 4.0 ? rho : 4.0;
+        const bool was_cells = h->last_grid.staged == 2;
+        if (occ <= (was_cells ? 10.0 : 7.0) * mean) {
+            g->staged = 2;
+            return;
+        }
+    }
     g->staged = 1;
     int ks = rho >= 12.0 ? 3 : (rho >= 6.0 ? 2 : 1);
     if (h->bins_override >= 0) ks = h->bins_override;
@@ -456,6 +471,7 @@ plife_handle::GraphKey graph_key(const plife_handle *h, double dt, const Grid &g
     k.m = h->m;
     k.flags = h->flags;
     k.ks = g.ks;
+    k.staged = g.staged;
     k.n = h->n;
     k.matrix_version = h->matrix_version;
     if (h->precision == PLIFE_F32) {
@@ -670,6 +686,11 @@ int plife_create(const plife_config *cfg, plife_handle **out)
     }
     cudaMemset(h->d_scalar, 0, (8 + 256) * sizeof(unsigned long long));
     h->d_hist = h->d_scalar + 8;
+    if (cudaHostAlloc((void **)&h->h_maxocc, sizeof(int), cudaHostAllocMapped) == cudaSuccess) *h->h_maxocc = 0;
+    else {
+        cudaGetLastError();
+        h->h_maxocc = nullptr;
+    }
     h->capacity_hint = cfg->capacity;
     {   // fine bins per cell along x: plife_config.bins, or the environment (for experiments), else from the density
         int k = cfg->bins;
@@ -714,6 +735,7 @@ int plife_destroy(plife_handle *h)
         cudaStreamDestroy(h->copy_stream);
     }
     cudaFree(h->d_scalar);
+    if (h->h_maxocc) cudaFreeHost((void *)h->h_maxocc);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;

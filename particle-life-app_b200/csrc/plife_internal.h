@@ -343,11 +343,12 @@ struct plife_handle {
     plife::Grid last_grid{0, 0, 0.0};
     bool prebinned = false;   // d_cell / d_count already hold the binning of the current state (fused into the last force pass)
     bool small_step = false;       // the current / last step ran in small mode
+    volatile int *h_maxocc = nullptr; // mapped pinned: particles in the fullest bin, written by small_sort every step (read lagging)
     bool prebinned_counts = false; // ... including the histogram d_count (not in small mode: small_sort recounts in shared memory)
     // launch-bound regime: the step replays a captured CUDA graph (one per velocity-buffer parity)
     struct GraphKey {
         double dt, rmax, friction, force, accp[4];
-        int wrap, acc_kind, m, flags, ks;
+        int wrap, acc_kind, m, flags, ks, staged;
         long long n, matrix_version;
         const void *pt0, *pt1, *vel0, *vel1, *cell_end;
         int cur;

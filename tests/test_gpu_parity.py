@@ -250,8 +250,8 @@ def test_virtual_slabs_match_single_gpu(native_lib, world, wrap, exchange):
     pos[:30, 1] = 1.0
     pos[30:60, 0] = 1.0
     pos[60:70] = 1.0
-    # same fine-bin count on both sides: the fp32 summation order follows the internal cell list
-    single = plife.NativePhysics(precision=plife.F32, bins=4)
+    # same kernel and fine-bin count on both sides: the fp32 summation order follows the internal cell list
+    single = plife.NativePhysics(precision=plife.F32, bins=4, flags=plife.FLAG_NO_CELLS)
     single.set_settings(rmax, 0.85, 1.0, wrap)
     single.set_matrix(matrix)
     single.upload(pos, vel, types)
@@ -312,8 +312,10 @@ def test_slab_errors(native_lib):
 
 
 @pytest.mark.parametrize("flags,bins", [(plife.FLAG_FORCE_V1, 0), (plife.FLAG_NO_FUSED_BIN, 0), (0, 1), (0, 2), (0, 4), (0, 8), (plife.FLAG_NO_FUSED_BIN, 8),
-                                        (plife.FLAG_SCAN3, 8)],
-                         ids=["v1", "nofusedbin", "bins1", "bins2", "bins4", "bins8", "nofusedbin_bins8", "scan3"])
+                                        (plife.FLAG_SCAN3, 8), (plife.FLAG_NO_CELLS, 0), (plife.FLAG_NO_CELLS, 1), (plife.FLAG_NO_CELLS, 8),
+                                        (plife.FLAG_NO_CELLS | plife.FLAG_SCAN3, 8)],
+                         ids=["v1", "nofusedbin", "bins1", "bins2", "bins4", "bins8", "nofusedbin_bins8", "scan3", "staged", "staged_bins1", "staged_bins8",
+                              "staged_scan3"])
 @pytest.mark.parametrize("case", [dict(n=10_000, m=6, rmax=0.04, wrap=True), dict(n=5_000, m=3, rmax=0.065, wrap=True),
                                   dict(n=5_000, m=3, rmax=0.065, wrap=False), dict(n=40_000, m=16, rmax=0.02, wrap=True)],
                          ids=["c1", "fat_wrap", "fat_clamp", "m16"])
@@ -585,7 +587,8 @@ def test_clustered_state(native_lib, precision, bins):
         o = oracle_step(pos, vel, types, matrix, rmax=rmax, wrap=wrap, dt=DT)
         opos, ovel, otyp, oid = o.get_particles()
         assert np.bincount(np.diff(np.concatenate([[0], o.containers()]))).size > 200  # some cell holds > 200 particles
-        g = gpu_step(native_lib, precision, pos, vel, types, matrix, bins=bins, rmax=rmax, wrap=wrap, dt=DT)
+        # bins = 0: the default path (warp-per-cell kernel at this size); bins given: the staged kernel (chunked staging of the dense CTAs)
+        g = gpu_step(native_lib, precision, pos, vel, types, matrix, bins=bins, flags=plife.FLAG_NO_CELLS if bins else 0, rmax=rmax, wrap=wrap, dt=DT)
         got = g.download()
         assert np.array_equal(got.id, oid) and np.array_equal(g.containers(), o.containers())
         assert g.step_stats()["pair_evals"] == o.pair_stats()[0]
@@ -605,7 +608,8 @@ def _blob_state(n, m, seed):
 
 
 @pytest.mark.parametrize("accel", [(3, ()), (5, ()), (0, (0.45,))], ids=["rotator90", "planets", "beta045"])
-def test_clustered_state_chunked_staging_other_accelerators(native_lib, accel):
+@pytest.mark.parametrize("flags", [0, plife.FLAG_NO_CELLS], ids=["cells", "staged"])
+def test_clustered_state_chunked_staging_other_accelerators(native_lib, accel, flags):
     """Dense CTAs stream their candidate ranges through shared memory in chunks (traverse_chunked); the literal
     visitors (distance test per candidate) take the same route as the branch-free default one."""
     pos, vel, types, matrix = _blob_state(30_000, 4, 21)
@@ -614,7 +618,7 @@ def test_clustered_state_chunked_staging_other_accelerators(native_lib, accel):
         kw = dict(rmax=0.02, wrap=wrap, dt=DT)
         o = oracle_step(pos, vel, types, matrix, accel_kind=accel[0], accel_params=params, **kw)
         _, ovel, _, oid = o.get_particles()
-        g = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, accel=accel, **kw)
+        g = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, accel=accel, flags=flags, **kw)
         got = g.download()
         assert np.array_equal(got.id, oid) and g.step_stats()["pair_evals"] == o.pair_stats()[0]
         assert rel_l2(got.velocity, ovel) <= 1e-5
@@ -626,7 +630,7 @@ def test_clustered_state_many_steps_fp32_tracks_fp64(native_lib):
     while no particle sits within rounding distance of a cell boundary, so compare sets and drift instead."""
     pos, vel, types, matrix = _blob_state(50_001, 6, 22)
     kw = dict(rmax=0.01, wrap=True, dt=DT)
-    a = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, steps=40, **kw)
+    a = gpu_step(native_lib, plife.F32, pos, vel, types, matrix, steps=40, flags=plife.FLAG_NO_CELLS, **kw)  # staged kernel, chunked
     b = gpu_step(native_lib, plife.F64, pos, vel, types, matrix, steps=40, **kw)
     pa, pb = a.download(), b.download()
     ia, ib = np.argsort(pa.id), np.argsort(pb.id)
