@@ -66,7 +66,7 @@ struct IOF32 {
 
 struct IOF64 {
     using R = double;
-    static constexpr int kMinBlocks = 1;
+    static constexpr int kMinBlocks = 8; // 64 registers: 8 CTAs per SM (70 registers would cost one)
     StateF64 in, out;
     __device__ __forceinline__ Cand<double> cand(int j) const
     {
