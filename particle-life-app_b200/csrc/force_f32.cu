@@ -43,7 +43,9 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
         if (cap_env > 0) cap = cap_env;
         cap = (cap + 15) / 16 * 16;
         if (cap > 1536) cap = 1536;
-        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h, no_leavers), stream);
+        static const int var_env = getenv("PLIFE_STAGED_VARIANT") ? atoi(getenv("PLIFE_STAGED_VARIANT")) : 0; // experiments: 1, 2 or 4
+        const int variant = var_env ? var_env : ((h->flags & PLIFE_FLAG_ONE_TARGET) ? 1 : 4);
+        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h, no_leavers), stream, variant);
     }
     if (p.g.ks != 0) return cudaErrorInvalidValue; // the v1 kernel writes results at the compute slot (make_grid never pairs it with fine bins)
     return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mt, h->acc_kind, next_bin(h, no_leavers), stream);

@@ -395,6 +395,17 @@ struct LiteralForce {
     {
         if (test(dx, dy)) hit(q, dx, dy);
     }
+    __device__ __forceinline__ void pair_rel(const float4 &q, float2 nself)
+    {
+        pair(-1, Cand<R>{q.x, q.y, __float_as_int(q.z), 0u}, q.x + nself.x, q.y + nself.y);
+    }
+    __device__ __forceinline__ void quad(const float4 &X, const float4 &Y, const float4 &Kq, float2 nself)
+    {
+        pair_rel(make_float4(X.x, Y.x, Kq.x, 0.f), nself);
+        pair_rel(make_float4(X.y, Y.y, Kq.y, 0.f), nself);
+        pair_rel(make_float4(X.z, Y.z, Kq.z, 0.f), nself);
+        pair_rel(make_float4(X.w, Y.w, Kq.w, 0.f), nself);
+    }
     __device__ __forceinline__ void finish(R &ovx, R &ovy) const
     {
         ovx = vx;
@@ -402,33 +413,103 @@ struct LiteralForce {
     }
 };
 
-// fp32 fast visitor for kind 0 (A/Main.java:275-280), branch-free.  With b = beta*rmax, d0 = (1+beta)*rmax/2,
-// h = (1-beta)*rmax/2 (absolute distance units) the reference's f(d/rmax) is
-//     f = (1/b) * [ min(d - b, 0) + a' * max(h - |d - d0|, 0) ],  a' = a * 2*beta/(1-beta)
-// exactly: the first term is the repulsion (d < b), the second the triangular lobe on [b, rmax], and both vanish
-// beyond rmax, so the `d2 <= rmax^2` test (B/Physics.java:432) is implied (f is continuous and 0 at the cutoff).
-// The accumulated quantity is f*b/d (the acceleration is pos*(f/d), A/Main.java:279), computed straight from
-// u = 1/d = rsqrt(d2):
-//     f*b/d = min(1 - b*u, 0) + a' * max(h*u - |1 - d0*u|, 0)
-// which needs neither d nor a final multiplication by 1/d.  The factor 1/b is folded into the final scale
-// (fast_k), a' into the shared-memory matrix.
+// ---- packed FP32 (sm_100a FADD2 / FFMA2: two fp32 lanes per instruction, each an ordinary IEEE fp32 add / fma) ----
+// The force pass is bound by the SM's issue rate (one warp instruction per cycle and scheduler), not by the FP32
+// pipe: a packed instruction does the work of two in ONE issue slot.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+
+// fp32 fast visitor for kind 0 (A/Main.java:275-280), branch-free.  With b = beta*rmax (absolute distance units) the
+// reference's f(d/rmax) is
+//     f = (1/b) * [ min(d - b, 0) + a' * max(min(d - b, rmax - d), 0) ],  a' = a * 2*beta/(1-beta)
+// exactly: the first term is the repulsion (d < b), the second the triangular lobe on [b, rmax] (rising side d - b up to
+// its peak at (b + rmax)/2, falling side rmax - d), and both vanish beyond rmax, so the `d2 <= rmax^2` test
+// (B/Physics.java:432) is implied (f is continuous and 0 at the cutoff).  The accumulated quantity is f*b/d (the
+// acceleration is pos*(f/d), A/Main.java:279), computed straight from u = 1/d = rsqrt(d2):
+//     r = 1 - b*u,  p = 1 - rmax*u,  f*b/d = min(r, 0) + a' * max(min(-p, r), 0)
+// which needs neither d nor a final multiplication by 1/d.  The factor 1/b is folded into the final scale (fast_k), a'
+// into the shared-memory matrix.  {r, p} is ONE packed fma, {ax, ay} += g * {dx, dy} another, and the staged loops form
+// {dx, dy} with one packed add (the record's x and y sit in an aligned register pair after the LDS.128):
+// 13.75 issued instructions per pair evaluation instead of 16.75.
 template <int MODE>
 struct FastParticleLife32 {
-    float ax, ay;
-    float b, d0, h;
+    float2 acc; // {ax, ay}
+    float2 c1;  // {-b, -rmax}
     MatrixView<float, MODE> M;
-    __device__ __forceinline__ void pair(int, const Cand<float> &q, float dx, float dy)
+    __device__ __forceinline__ FastParticleLife32(const ForceParams<float> &P, const MatrixView<float, MODE> &m)
+        : acc(make_float2(0.f, 0.f)), c1(make_float2(-P.fast_b, -P.rmax)), M(m)
     {
-        const float d2 = fmaf(dx, dx, fmaf(dy, dy, kTiny));
-        const float u = rsqrt_fast(d2);
-        const float a = M.get(q.type);
-        const float rep = fminf(fmaf(-b, u, 1.0f), 0.0f);
-        const float w = fmaf(-d0, u, 1.0f);
-        const float att = fmaxf(fmaf(h, u, -fabsf(w)), 0.0f);
-        const float g = fmaf(a, att, rep); // self / coincident: dx = dy = 0 kills the term
-        ax = fmaf(g, dx, ax);
-        ay = fmaf(g, dy, ay);
+        // keep the pair in registers: without this ptxas re-reads both halves from the constant bank in every loop trip
+        asm volatile("" : "+f"(c1.x), "+f"(c1.y));
     }
+    __device__ __forceinline__ FastParticleLife32(float2 acc_, float2 c1_, uint32_t row) : acc(acc_), c1(c1_)
+    {
+        M.g = nullptr;
+        M.s = nullptr;
+        M.m = 0;
+        M.own = 0;
+        M.scale = 1.0f;
+        M.row = row;
+        M.mb = 0u;
+    }
+    __device__ __forceinline__ float ax() const { return acc.x; }
+    __device__ __forceinline__ float ay() const { return acc.y; }
+    __device__ __forceinline__ void core(int key, float2 d)
+    {
+        const float d2 = fmaf(d.x, d.x, fmaf(d.y, d.y, kTiny));
+        const float u = rsqrt_fast(d2);
+        const float a = M.get(key);
+        const float2 rp = ffma2(c1, make_float2(u, u), make_float2(1.0f, 1.0f)); // (the addend is an immediate)
+        const float rep = fminf(rp.x, 0.0f);
+        const float att = fmaxf(fminf(-rp.y, rp.x), 0.0f);
+        const float g = fmaf(a, att, rep); // self / coincident: dx = dy = 0 kills the term
+        acc = ffma2(make_float2(g, g), d, acc);
+    }
+    __device__ __forceinline__ void pair(int, const Cand<float> &q, float dx, float dy) { core(q.type, make_float2(dx, dy)); }
+    // four candidates {x0..x3}, {y0..y3}, {key0..key3} (force_kernel_staged4): the same operations per pair as core(), in
+    // candidate order, two candidates per packed instruction where the operands sit in register pairs
+    __device__ __forceinline__ void quad(const float4 &X, const float4 &Y, const float4 &Kq, float2 nself)
+    {
+        const float2 nx2 = make_float2(nself.x, nself.x), ny2 = make_float2(nself.y, nself.y);
+        const float2 tiny2 = make_float2(kTiny, kTiny), one2 = make_float2(1.0f, 1.0f);
+        const float2 dxa = fadd2(make_float2(X.x, X.y), nx2), dxb = fadd2(make_float2(X.z, X.w), nx2);
+        const float2 dya = fadd2(make_float2(Y.x, Y.y), ny2), dyb = fadd2(make_float2(Y.z, Y.w), ny2);
+        const float2 sa = ffma2(dxa, dxa, ffma2(dya, dya, tiny2)), sb = ffma2(dxb, dxb, ffma2(dyb, dyb, tiny2));
+        const float2 ua = make_float2(rsqrt_fast(sa.x), rsqrt_fast(sa.y)), ub = make_float2(rsqrt_fast(sb.x), rsqrt_fast(sb.y));
+        const float2 aa = make_float2(M.get(__float_as_int(Kq.x)), M.get(__float_as_int(Kq.y)));
+        const float2 ab = make_float2(M.get(__float_as_int(Kq.z)), M.get(__float_as_int(Kq.w)));
+        const float2 cb = make_float2(c1.x, c1.x), cr = make_float2(c1.y, c1.y);
+        const float2 ra = ffma2(cb, ua, one2), rb = ffma2(cb, ub, one2); // r = 1 - b*u
+        const float2 pa = ffma2(cr, ua, one2), pb = ffma2(cr, ub, one2); // p = 1 - rmax*u
+        const float2 ga = ffma2(aa, make_float2(fmaxf(fminf(-pa.x, ra.x), 0.0f), fmaxf(fminf(-pa.y, ra.y), 0.0f)),
+                                make_float2(fminf(ra.x, 0.0f), fminf(ra.y, 0.0f)));
+        const float2 gb = ffma2(ab, make_float2(fmaxf(fminf(-pb.x, rb.x), 0.0f), fmaxf(fminf(-pb.y, rb.y), 0.0f)),
+                                make_float2(fminf(rb.x, 0.0f), fminf(rb.y, 0.0f)));
+        acc.x = fmaf(ga.x, dxa.x, acc.x);
+        acc.y = fmaf(ga.x, dya.x, acc.y);
+        acc.x = fmaf(ga.y, dxa.y, acc.x);
+        acc.y = fmaf(ga.y, dya.y, acc.y);
+        acc.x = fmaf(gb.x, dxb.x, acc.x);
+        acc.y = fmaf(gb.x, dyb.x, acc.y);
+        acc.x = fmaf(gb.y, dxb.y, acc.x);
+        acc.y = fmaf(gb.y, dyb.y, acc.y);
+    }
+    // staged record {x, y, key, -} against nself = {-xi, -yi}: q.x + (-xi) is exactly q.x - xi
+    __device__ __forceinline__ void pair_rel(const float4 &q, float2 nself) { core(__float_as_int(q.z), fadd2(make_float2(q.x, q.y), nself)); }
 };
 
 struct NeighborDiag {
@@ -569,10 +650,10 @@ __global__ void __launch_bounds__(kForceThreads, IO::kMinBlocks) force_kernel(IO
 
     R nvx, nvy;
     if constexpr (FAST) {
-        FastParticleLife32<MODE> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        FastParticleLife32<MODE> v(P, M);
         traverse(io, cell_end, P.g, P.wrap, si, self.x, self.y, cxy, v);
-        nvx = fmaf(P.fast_k, v.ax, vx * P.mu); // friction first (:401-402), then the summed acceleration
-        nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
+        nvx = fmaf(P.fast_k, v.ax(), vx * P.mu); // friction first (:401-402), then the summed acceleration
+        nvy = fmaf(P.fast_k, v.ay(), vy * P.mu);
     } else {
         LiteralForce<R, KIND, MODE> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
         traverse(io, cell_end, P.g, P.wrap, si, self.x, self.y, cxy, v);
@@ -620,6 +701,9 @@ __global__ void __launch_bounds__(kForceThreads, IO::kMinBlocks) force_kernel(IO
 // case where the range itself ends.  Lanes on the domain seam walk global memory with the literal
 // 9-cell loop; CTAs whose ranges exceed the staging capacity (dense clusters) stream them through
 // it in chunks (traverse_chunked).
+#ifndef PLIFE_STAGED_MIN_BLOCKS
+#define PLIFE_STAGED_MIN_BLOCKS 12
+#endif
 constexpr int kTabMaxM = 32;
 constexpr int kStagePad = 3; // sentinels after each staged range
 static_assert(kForceThreads * 4 == (1 << kTypeShift), "lane-table row stride");
@@ -627,7 +711,9 @@ static_assert(kForceThreads * 4 == (1 << kTypeShift), "lane-table row stride");
 __device__ __forceinline__ float4 lds128(uint32_t a)
 {
     float4 v;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    // volatile + memory clobber: the staging area is rewritten between barriers (chunked walks), and an asm the compiler
+    // believes to be a pure function of its address may be moved across them
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
 
@@ -733,6 +819,7 @@ __device__ __forceinline__ void traverse_staged(const int32_t *__restrict__ cell
                                                 uint32_t stage_addr, int cap, const int *s_start, V &v)
 {
     const int K = 1 << g.ks, nxk = g.nxk();
+    const float2 nself = make_float2(-xi, -yi);
     // all six range bounds first: one round trip instead of three
     int s[3], e[3];
 #pragma unroll
@@ -749,8 +836,7 @@ __device__ __forceinline__ void traverse_staged(const int32_t *__restrict__ cell
         for (; a < a1; a += 64u) { // 4 candidates per trip, padded (see above)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float4 q = lds128(a + 16u * u);
-                v.pair(-1, Cand<float>{q.x, q.y, __float_as_int(q.z), 0u}, q.x - xi, q.y - yi);
+                v.pair_rel(lds128(a + 16u * u), nself);
             }
         }
     }
@@ -769,6 +855,7 @@ __device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t 
 {
     const int K = 1 << g.ks, nxk = g.nxk();
     const int tid = threadIdx.x;
+    const float2 nself = make_float2(-xi, -yi);
 #pragma unroll 1
     for (int r = 0; r < 3; ++r) {
         int s = 0, e = 0;
@@ -793,8 +880,7 @@ __device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t 
                 for (; a < aend; a += 64u) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float4 q = lds128(a + 16u * u);
-                        v.pair(-1, Cand<float>{q.x, q.y, __float_as_int(q.z), 0u}, q.x - xi, q.y - yi);
+                        v.pair_rel(lds128(a + 16u * u), nself);
                     }
                 }
             }
@@ -804,7 +890,7 @@ __device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t 
 
 // gM: row-major matrix [own][other] (for the vectorised row copy)
 template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 io, const int32_t *__restrict__ cell_end,
+__global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED_MIN_BLOCKS) force_kernel_staged(IOF32 io, const int32_t *__restrict__ cell_end,
                                                                     const int32_t *__restrict__ cell_sorted,
                                                                     ForceParams<float> P, const float *__restrict__ gM,
                                                                     int cap, NextBin nb)
@@ -906,10 +992,10 @@ __global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 i
         if (valid && !interior) traverse_global32(io, cell_end, g, P.wrap, si, self.x, self.y, cx0, cy0, v);
     };
     if constexpr (FAST) {
-        FastParticleLife32<kMatLaneTab> v{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        FastParticleLife32<kMatLaneTab> v(P, M);
         walk(v);
-        nvx = fmaf(P.fast_k, v.ax, vx * P.mu);
-        nvy = fmaf(P.fast_k, v.ay, vy * P.mu);
+        nvx = fmaf(P.fast_k, v.ax(), vx * P.mu);
+        nvy = fmaf(P.fast_k, v.ay(), vy * P.mu);
     } else {
         LiteralForce<float, KIND, kMatLaneTab> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
         walk(v);
@@ -930,12 +1016,533 @@ __global__ void __launch_bounds__(kForceThreads, 12) force_kernel_staged(IOF32 i
     nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, g);
 }
 
+// ---- v3: two targets per lane -----------------------------------------------------------------------------------------
+// ncu on the kernel above at 16 particles per cell (profiles/r2_force_c3.ncu_details.txt): "Mem Busy 94 %" - the SM's ONE
+// shared-memory pipe (one 128-byte wavefront per cycle for all four schedulers), not the issue slots (80 %), is what
+// binds it.  With fine bins the 32 lanes of a warp read up to 16 different 16-byte records per LDS.128 (4.5 wavefronts on
+// average, 8 distinct bank groups), plus one wavefront for the matrix lookup: 5.5 wavefronts per candidate and target.
+// Here a lane owns TWO consecutive targets (a CTA is 64 threads, still 128 targets and the same staging): one LDS.128
+// of the candidate and one LDS.64 of the two matrix entries (table [type][2 * thread + {0, 1}]: conflict-free, two
+// wavefronts) serve two pair evaluations - 3.3 wavefronts each.  The two targets are neighbours in the sorted order, so
+// they sit in the same or in adjacent bins: the lane walks the union of their ranges, bins [binA - K, binB + K], and
+// the few candidates outside a target's own window are beyond rmax in x for it (exact zeros, like the padding).
+// Targets that cannot share a walk (different rows, more than a cell apart, one of them on the seam) take one pass each
+// with the other slot parked far away.  Per pair: the same operations in the same order as the kernel above, so both
+// kernels give bit-identical results.
+#ifndef PLIFE_STAGED2_MIN_BLOCKS
+#define PLIFE_STAGED2_MIN_BLOCKS 11
+#endif
+constexpr int kForceThreads2 = kForceThreads / 2;
+constexpr float kParked = -2.0e9f; // -position of a parked target slot: every candidate (sentinels included) is far away
+
+__device__ __forceinline__ float2 lds64(uint32_t a)
+{
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+
+struct FastParticleLife32x2 {
+    float2 acc0, acc1; // {ax, ay} of the two targets
+    float2 c1;         // {-b, -rmax}
+    uint32_t row2;     // shared-window byte address of tab[0][2 * thread]
+    __device__ __forceinline__ FastParticleLife32x2(const ForceParams<float> &P, uint32_t row)
+        : acc0(make_float2(0.f, 0.f)), acc1(make_float2(0.f, 0.f)), c1(make_float2(-P.fast_b, -P.rmax)), row2(row)
+    {
+    }
+    static __device__ __forceinline__ float weight(float2 rp, float a)
+    {
+        const float rep = fminf(rp.x, 0.0f);
+        const float att = fmaxf(fminf(-rp.y, rp.x), 0.0f);
+        return fmaf(a, att, rep);
+    }
+    __device__ __forceinline__ void pair2(const float4 &q, float2 n0, float2 n1)
+    {
+        const float2 qp = make_float2(q.x, q.y);
+        const float2 d0 = fadd2(qp, n0), d1 = fadd2(qp, n1);
+        const float s0 = fmaf(d0.x, d0.x, fmaf(d0.y, d0.y, kTiny)), s1 = fmaf(d1.x, d1.x, fmaf(d1.y, d1.y, kTiny));
+        const float u0 = rsqrt_fast(s0), u1 = rsqrt_fast(s1);
+        const float2 a = lds64(row2 + (uint32_t)__float_as_int(q.z));
+        const float2 one = make_float2(1.0f, 1.0f);
+        const float g0 = weight(ffma2(c1, make_float2(u0, u0), one), a.x);
+        const float g1 = weight(ffma2(c1, make_float2(u1, u1), one), a.y);
+        acc0 = ffma2(make_float2(g0, g0), d0, acc0);
+        acc1 = ffma2(make_float2(g1, g1), d1, acc1);
+    }
+};
+
+// candidates [a, a1) of the staging area (byte addresses), 4 per trip (padded, see above)
+__device__ __forceinline__ void walk_span2(uint32_t a, uint32_t a1, float2 n0, float2 n1, FastParticleLife32x2 &v)
+{
+#pragma unroll 1
+    for (; a < a1; a += 64u) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v.pair2(lds128(a + 16u * u), n0, n1);
+    }
+}
+
+__global__ void __launch_bounds__(kForceThreads2, PLIFE_STAGED2_MIN_BLOCKS)
+    force_kernel_staged2(IOF32 io, const int32_t *__restrict__ cell_end, const int32_t *__restrict__ cell_sorted, ForceParams<float> P,
+                         const float *__restrict__ gM, int cap, NextBin nb)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                                  // [3][cap + kStagePad]
+    float *tab = reinterpret_cast<float *>(smem_raw + (size_t)3 * (cap + kStagePad) * 16);  // [m][kForceThreads]: column = 2 * thread + slot
+    __shared__ int s_start[3], s_len[3];
+    __shared__ __align__(8) unsigned long long s_bar;
+
+    int i0, lim;
+    if (!cta_targets(P, i0, lim)) return;
+    const int tid = threadIdx.x;
+    const int iA = i0 + 2 * tid; // this lane's targets: iA and iA + 1
+    const bool validA = iA < lim, validB = iA + 1 < lim;
+    const Grid g = P.g;
+    const int K = 1 << g.ks, nxk = g.nxk();
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+
+    if (tid == 0) { // the three row ranges of this CTA's targets: found and copied exactly like in force_kernel_staged
+        mbar_init(bar, 1);
+        const int b0 = container_of(__ldg(cell_sorted + i0), g);
+        const int b1 = container_of(__ldg(cell_sorted + min(i0 + kForceThreads, lim) - 1), g);
+        int st[3], ln[3];
+        bool ok = true;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int lo = max(b0 + (r - 1) * nxk - K, P.bin_lo);
+            const int hi = min(b1 + (r - 1) * nxk + K, P.bin_hi);
+            st[r] = 0;
+            ln[r] = 0;
+            if (lo <= hi) {
+                st[r] = __ldg(cell_end + lo - 1);
+                ln[r] = __ldg(cell_end + hi) - st[r];
+            }
+            s_start[r] = st[r];
+            s_len[r] = ln[r];
+            ok = ok && ln[r] <= cap;
+        }
+        if (ok) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(ln[0] + ln[1] + ln[2]) * 16u);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float4 *dst = stage + r * (cap + kStagePad);
+                if (ln[r] > 0) bulk_g2s(stage_addr + (uint32_t)(r * (cap + kStagePad)) * 16u, io.pt + st[r], (uint32_t)ln[r] * 16u, bar);
+#pragma unroll
+                for (int k = 0; k < kStagePad; ++k) dst[ln[r] + k] = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
+            }
+        }
+    }
+    // own particles (records carry type << kTypeShift), bin words, velocities
+    float4 meA = make_float4(0.f, 0.f, 0.f, 0.f), meB = meA;
+    int cxyA = 0, cxyB = 0;
+    float vxA = 0.f, vyA = 0.f, vxB = 0.f, vyB = 0.f;
+    if (validA) {
+        meA = __ldg(io.pt + P.first + iA);
+        cxyA = __ldg(cell_sorted + iA);
+        io.self_vel(iA, vxA, vyA);
+    }
+    if (validB) {
+        meB = __ldg(io.pt + P.first + iA + 1);
+        cxyB = __ldg(cell_sorted + iA + 1);
+        io.self_vel(iA + 1, vxB, vyB);
+    }
+    const int typeA = __float_as_int(meA.z) >> kTypeShift, typeB = __float_as_int(meB.z) >> kTypeShift;
+    { // matrix rows of the two targets -> tab[other][2 * tid + {0, 1}]
+        const float mscale = P.fast_a_scale;
+        const float *rowA = gM + typeA * P.m, *rowB = gM + typeB * P.m;
+        float2 *col = reinterpret_cast<float2 *>(tab) + tid;
+        if ((P.m & 3) == 0) {
+            for (int t = 0; t < P.m; t += 4) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(rowA + t));
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rowB + t));
+                col[(t + 0) * kForceThreads2] = make_float2(a4.x * mscale, b4.x * mscale);
+                col[(t + 1) * kForceThreads2] = make_float2(a4.y * mscale, b4.y * mscale);
+                col[(t + 2) * kForceThreads2] = make_float2(a4.z * mscale, b4.z * mscale);
+                col[(t + 3) * kForceThreads2] = make_float2(a4.w * mscale, b4.w * mscale);
+            }
+        } else {
+            for (int t = 0; t < P.m; ++t) col[t * kForceThreads2] = make_float2(__ldg(rowA + t) * mscale, __ldg(rowB + t) * mscale);
+        }
+    }
+    __syncthreads();
+    const bool staged_ok = s_len[0] <= cap && s_len[1] <= cap && s_len[2] <= cap;
+    if (staged_ok) {
+        if (!validA) return; // (in chunked mode every thread is needed at the barriers)
+        mbar_wait(bar, 0);
+    }
+
+    const int cx0A = (cxyA & 0xffff) >> g.ks, cy0A = scan_row(cxyA >> 16, g);
+    const int cx0B = (cxyB & 0xffff) >> g.ks, cy0B = scan_row(cxyB >> 16, g);
+    const bool intA = validA && g.nx >= 4 && cx0A >= 1 && cx0A <= g.nx - 2 && cy0A >= 1 && cy0A <= g.ny - 2;
+    const bool intB = validB && g.nx >= 4 && cx0B >= 1 && cx0B <= g.nx - 2 && cy0B >= 1 && cy0B <= g.ny - 2;
+    const int fbA = (cxyA & 0xffff) + (cy0A + g.ly_shift) * nxk, fbB = (cxyB & 0xffff) + (cy0B + g.ly_shift) * nxk;
+    // one shared walk if the two windows overlap almost completely (same row, at most a cell apart); else one pass each
+    const bool paired = intA && intB && cy0A == cy0B && fbB >= fbA && fbB - fbA <= K;
+    const uint32_t row2 = (uint32_t)__cvta_generic_to_shared(tab) + 8u * (uint32_t)tid;
+    FastParticleLife32x2 v(P, row2);
+    const float2 park = make_float2(kParked, kParked);
+    const float2 nA = make_float2(-meA.x, -meA.y), nB = make_float2(-meB.x, -meB.y);
+    const int chunk_cap = 3 * (cap + kStagePad) - kStagePad;
+    // pass 0: A (together with B if paired); pass 1: B alone (unpaired only, rare)
+    const bool live0 = intA, live1 = intB && !paired;
+    const int hi0 = paired ? fbB : fbA;
+    const float2 nB0 = paired ? nB : park;
+    int s0[3], e0[3], s1[3], e1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        s0[r] = live0 ? __ldg(cell_end + fbA + (r - 1) * nxk - K - 1) : 0;
+        e0[r] = live0 ? __ldg(cell_end + hi0 + (r - 1) * nxk + K) : 0;
+        s1[r] = live1 ? __ldg(cell_end + fbB + (r - 1) * nxk - K - 1) : 0;
+        e1[r] = live1 ? __ldg(cell_end + fbB + (r - 1) * nxk + K) : 0;
+    }
+    if (staged_ok) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s0[r] - s_start[r]) * 16u;
+            walk_span2(a, a + (uint32_t)(e0[r] - s0[r]) * 16u, nA, nB0, v);
+        }
+        if (live1) {
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+                const int sr = r == 0 ? s1[0] : (r == 1 ? s1[1] : s1[2]), er = r == 0 ? e1[0] : (r == 1 ? e1[1] : e1[2]);
+                const uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + sr - s_start[r]) * 16u;
+                walk_span2(a, a + (uint32_t)(er - sr) * 16u, park, nB, v);
+            }
+        }
+    } else { // dense cluster: the row ranges stream through the staging area in chunks (CTA-uniform loops, two barriers each)
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+            const int row_lo = s_start[r], row_hi = row_lo + s_len[r];
+            const int sr0 = r == 0 ? s0[0] : (r == 1 ? s0[1] : s0[2]), er0 = r == 0 ? e0[0] : (r == 1 ? e0[1] : e0[2]);
+            const int sr1 = r == 0 ? s1[0] : (r == 1 ? s1[1] : s1[2]), er1 = r == 0 ? e1[0] : (r == 1 ? e1[1] : e1[2]);
+#pragma unroll 1
+            for (int c0 = row_lo; c0 < row_hi; c0 += chunk_cap) {
+                const int clen = min(chunk_cap, row_hi - c0);
+                __syncthreads(); // the previous chunk has been consumed
+                const float4 *src = io.pt + c0;
+                for (int k = tid; k < clen + kStagePad; k += kForceThreads2)
+                    stage[k] = k < clen ? __ldg(src + k) : make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
+                __syncthreads();
+                int a0 = max(sr0, c0), a1 = min(er0, c0 + clen);
+                if (a0 < a1) walk_span2(stage_addr + (uint32_t)(a0 - c0) * 16u, stage_addr + (uint32_t)(a1 - c0) * 16u, nA, nB0, v);
+                a0 = max(sr1, c0), a1 = min(er1, c0 + clen);
+                if (a0 < a1) walk_span2(stage_addr + (uint32_t)(a0 - c0) * 16u, stage_addr + (uint32_t)(a1 - c0) * 16u, park, nB, v);
+            }
+        }
+    }
+    // seam targets: the literal 9-cell walk over global memory, one target at a time
+    float axA = v.acc0.x, ayA = v.acc0.y, axB = v.acc1.x, ayB = v.acc1.y;
+    if ((validA && !intA) || (validB && !intB)) {
+        MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, 0, 1.0f, 0u, 0u};
+        if (validA && !intA) {
+            M.row = row2;
+            FastParticleLife32<kMatLaneTab> v1(P, M);
+            traverse_global32(io, cell_end, g, P.wrap, P.first + iA, meA.x, meA.y, cx0A, cy0A, v1);
+            axA = v1.ax();
+            ayA = v1.ay();
+        }
+        if (validB && !intB) {
+            M.row = row2 + 4u;
+            FastParticleLife32<kMatLaneTab> v1(P, M);
+            traverse_global32(io, cell_end, g, P.wrap, P.first + iA + 1, meB.x, meB.y, cx0B, cy0B, v1);
+            axB = v1.ax();
+            ayB = v1.ay();
+        }
+    }
+    auto finish = [&](int i, const float4 &me, int type, int cxy, float vx, float vy, float ax, float ay) {
+        const float nvx = fmaf(P.fast_k, ax, vx * P.mu); // friction first (:401-402), then the summed acceleration
+        const float nvy = fmaf(P.fast_k, ay, vy * P.mu);
+        float nx_ = fmaf(nvx, P.dt, me.x);
+        float ny_ = fmaf(nvy, P.dt, me.y);
+        if (P.wrap) {
+            nx_ = range_wrap(nx_);
+            ny_ = range_wrap(ny_);
+        } else {
+            nx_ = range_clamp(nx_);
+            ny_ = range_clamp(ny_);
+        }
+        const int o = io.out_slot(i, cxy, cell_end, g);
+        io.store(o, nx_, ny_, nvx, nvy, type, __float_as_uint(me.w));
+        nb.add(o, nx_, ny_, nvx, nvy, type, __float_as_uint(me.w), g);
+    };
+    if (validA) finish(iA, meA, typeA, cxyA, vxA, vyA, axA, ayA);
+    if (validB) finish(iA + 1, meB, typeB, cxyB, vxB, vyB, axB, ayB);
+}
+
+// ---- v4: candidates staged four wide ------------------------------------------------------------------------------------
+// What binds force_kernel_staged at 16 particles per cell is the SM's shared-memory data pipe (ncu: l1tex data-pipe
+// wavefronts 95 % of peak, issue slots 71 %; profiles/r2_force_kernel.md): with fine bins the lanes of a warp read up to
+// 16 different 16-byte records per LDS.128, spread over a window of 32+ records - 4.5 wavefronts per candidate, plus one
+// for the matrix lookup.  Here the staging area holds the candidates in groups of four, {x0..x3 | y0..y3 | key0..key3}
+// (48 bytes), aligned to the global sorted index: a lane fetches a group with three LDS.128, and the 32 lanes of a warp
+// together touch some nine CONSECUTIVE groups per load (their range starts lie within ~32 records of each other), whose
+// 16-byte parts fall into different bank groups (the group stride of 3 x 16 bytes is coprime to 8): about two wavefronts
+// per load, 1.5 per candidate instead of 4.5.  The arithmetic per pair is the same, operation for operation, as in the
+// kernel above (bit-identical results); dx, dy, d2, {r, p} and the weight are formed for two candidates per packed
+// instruction.  The price: the ranges can no longer be bulk-copied (the records are transposed on the way in: LDG.128 ->
+// 3 x STS.32, conflict-free), and a lane's walk starts at the group boundary below its range (1.5 extra candidates per
+// row on average; they sit in bins left of the lane's window, beyond rmax in x: exact zeros like the padding at the end).
+#ifndef PLIFE_STAGED4_MIN_BLOCKS
+#define PLIFE_STAGED4_MIN_BLOCKS 10 // 48 registers: four candidates in flight per lane
+#endif
+constexpr int kGroupBytes = 48;
+constexpr int kStageLead = 4; // room for the groups' alignment below a range start
+constexpr int kStageTail = 4; // spare
+constexpr float kFar = 1.0e9f; // x of a masked / sentinel candidate
+
+// smem byte offset of candidate slot k of a row (slots are group-aligned: 4 per 48-byte group)
+__device__ __forceinline__ uint32_t slot_x(uint32_t k) { return (k >> 2) * (uint32_t)kGroupBytes + (k & 3u) * 4u; }
+
+// slots [0, n_slots) of the staging area at `base` <- sorted records [j0, j0 + n_slots), transposed into groups
+// (LDG.128 -> 3 x STS.32, conflict-free); slots outside [lo, hi) become sentinels (far away, matrix key 0)
+__device__ __forceinline__ void stage_in4(unsigned char *base, const float4 *__restrict__ pt, int j0, int n_slots, int lo, int hi)
+{
+    for (int k = threadIdx.x; k < n_slots; k += kForceThreads) {
+        const int j = j0 + k;
+        float4 q = make_float4(kFar, kFar, 0.f, 0.f);
+        if (j >= lo && j < hi) q = __ldg(pt + j);
+        float *px = reinterpret_cast<float *>(base + slot_x((uint32_t)k));
+        px[0] = q.x;
+        px[4] = q.y;
+        px[8] = q.z;
+    }
+}
+
+// Candidates [s_rel, e_rel) (slot numbers) of the staging row at byte address rb, in order.  The first and the last
+// group are read in full but the slots outside the range are masked: the records next to a range are NOT always far away
+// in x - where the rest of a grid row is empty they belong to the adjacent grid row, i.e. to another of this lane's ranges.
+template <typename V>
+__device__ __forceinline__ void walk_row4(uint32_t rb, int s_rel, int e_rel, float2 nself, V &v)
+{
+    if (s_rel >= e_rel) return;
+    uint32_t a = rb + (uint32_t)(s_rel >> 2) * kGroupBytes;
+    const uint32_t al = rb + (uint32_t)((e_rel - 1) >> 2) * kGroupBytes; // the last group
+    const int lead = s_rel & 3, cnt = e_rel & 3; // cnt == 0: the last group is full
+    float4 X = lds128(a);
+    if (lead > 0) X.x = kFar;
+    if (lead > 1) X.y = kFar;
+    if (lead > 2) X.z = kFar;
+    if (a != al) {
+        v.quad(X, lds128(a + 16u), lds128(a + 32u), nself);
+#pragma unroll 1
+        for (a += (uint32_t)kGroupBytes; a < al; a += (uint32_t)kGroupBytes) v.quad(lds128(a), lds128(a + 16u), lds128(a + 32u), nself);
+        X = lds128(al);
+    }
+    if (cnt != 0) {
+        X.w = kFar;
+        if (cnt <= 2) X.z = kFar;
+        if (cnt <= 1) X.y = kFar;
+    }
+    v.quad(X, lds128(al + 16u), lds128(al + 32u), nself);
+}
+
+// The masked walk of the fast visitor as a real function call: it serves the few CTAs that straddle a grid row (and the
+// chunked walks of dense clusters), and as a call it costs the common path neither registers nor code.
+template <int MODE>
+__device__ __noinline__ float2 walk_row4_call(uint32_t rb, int s_rel, int e_rel, float2 nself, float2 acc, float2 c1, uint32_t row)
+{
+    FastParticleLife32<MODE> v(acc, c1, row);
+    walk_row4(rb, s_rel, e_rel, nself, v);
+    return v.acc;
+}
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED4_MIN_BLOCKS)
+    force_kernel_staged4(IOF32 io, const int32_t *__restrict__ cell_end, const int32_t *__restrict__ cell_sorted, ForceParams<float> P,
+                         const float *__restrict__ gM, int cap, NextBin nb)
+{
+    // cap: candidate slots per row (multiple of 4), lead and tail included
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tab = reinterpret_cast<float *>(smem_raw + (size_t)3 * cap * 12); // [m][kForceThreads]
+    __shared__ int s_start[3], s_len[3], s_clean;
+
+    int i0, lim;
+    if (!cta_targets(P, i0, lim)) return;
+    const int tid = threadIdx.x;
+    const int i = i0 + tid;
+    const bool valid = i < lim;
+    const Grid g = P.g;
+    const int K = 1 << g.ks, nxk = g.nxk();
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t row_bytes = (uint32_t)cap * 12u;
+
+    if (tid == 0) { // the three row ranges of this CTA's targets
+        const int b0 = container_of(__ldg(cell_sorted + i0), g);
+        const int b1 = container_of(__ldg(cell_sorted + min(i0 + kForceThreads, lim) - 1), g);
+        // clean: the targets share ONE grid row and the K bins of margin on either side stay inside it.  Every record next
+        // to a lane's range then sits left or right of the lane's window in the same grid row, beyond rmax in x (or is a
+        // sentinel past the staged range): the walk needs no masks, its extra candidates add exact zeros.
+        const int x0 = b0 % nxk;
+        s_clean = (x0 >= K && x0 + (b1 - b0) + K < nxk) ? 1 : 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int lo = max(b0 + (r - 1) * nxk - K, P.bin_lo);
+            const int hi = min(b1 + (r - 1) * nxk + K, P.bin_hi);
+            int st = 0, ln = 0;
+            if (lo <= hi) {
+                st = __ldg(cell_end + lo - 1);
+                ln = __ldg(cell_end + hi) - st;
+            }
+            s_start[r] = st;
+            s_len[r] = ln;
+        }
+    }
+    Cand<float> self{0.f, 0.f, 0, 0u};
+    int cxy = 0;
+    const int si = P.first + i;
+    float vx = 0.f, vy = 0.f;
+    if (valid) {
+        self = io.cand(si);
+        cxy = __ldg(cell_sorted + i);
+        io.self_vel(i, vx, vy);
+    }
+    { // this lane's matrix row -> tab[other][tid] (bank = lane: conflict-free lookups)
+        const float mscale = FAST ? P.fast_a_scale : 1.0f;
+        const float *rowp = gM + self.type * P.m;
+        if ((P.m & 3) == 0) {
+            for (int t = 0; t < P.m; t += 4) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rowp + t));
+                tab[(t + 0) * kForceThreads + tid] = r4.x * mscale;
+                tab[(t + 1) * kForceThreads + tid] = r4.y * mscale;
+                tab[(t + 2) * kForceThreads + tid] = r4.z * mscale;
+                tab[(t + 3) * kForceThreads + tid] = r4.w * mscale;
+            }
+        } else {
+            for (int t = 0; t < P.m; ++t) tab[t * kForceThreads + tid] = __ldg(rowp + t) * mscale;
+        }
+    }
+    __syncthreads(); // s_start / s_len / s_clean
+    const int room = cap - kStageLead - kStageTail;
+    const bool staged_ok = s_len[0] <= room && s_len[1] <= room && s_len[2] <= room;
+    if (staged_ok) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int j0 = s_start[r] & ~3; // group boundaries follow the global sorted index
+            stage_in4(smem_raw + (size_t)r * row_bytes, io.pt, j0, ((s_start[r] - j0 + s_len[r] + 3) & ~3) + kStageTail, s_start[r],
+                      s_start[r] + s_len[r]);
+        }
+        __syncthreads();
+        if (!valid) return; // (in chunked mode every thread is needed at the barriers)
+    }
+
+    const int cx0 = (cxy & 0xffff) >> g.ks, cy0 = scan_row(cxy >> 16, g);
+    const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
+    const int fb = (cxy & 0xffff) + (cy0 + g.ly_shift) * nxk; // own bin (interior lanes: no clamp needed)
+    MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, self.type, 1.0f, 0u, 0u};
+    M.init();
+    const float2 nself = make_float2(-self.x, -self.y);
+    float nvx, nvy;
+    // walk(v, masked_row): `masked_row(rb, s_rel, e_rel)` is how this visitor walks one row with masks
+    auto walk = [&](auto &v, auto masked_row) {
+        int s[3] = {0, 0, 0}, e[3] = {0, 0, 0};
+        if (interior) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int base = fb + (r - 1) * nxk;
+                s[r] = __ldg(cell_end + base - K - 1);
+                e[r] = __ldg(cell_end + base + K);
+            }
+        }
+        if (staged_ok && s_clean && FAST) {
+            if (interior) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int j0 = s_start[r] & ~3;
+                    uint32_t a = stage_addr + (uint32_t)r * row_bytes + (uint32_t)((s[r] - j0) >> 2) * kGroupBytes;
+                    const uint32_t a1 = stage_addr + (uint32_t)r * row_bytes + (uint32_t)((e[r] - j0 + 3) >> 2) * kGroupBytes;
+#pragma unroll 1
+                    for (; a < a1; a += (uint32_t)kGroupBytes) v.quad(lds128(a), lds128(a + 16u), lds128(a + 32u), nself);
+                }
+            }
+        } else if (staged_ok) {
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+                const int j0 = s_start[r] & ~3;
+                const int sr = r == 0 ? s[0] : (r == 1 ? s[1] : s[2]), er = r == 0 ? e[0] : (r == 1 ? e[1] : e[2]);
+                masked_row(stage_addr + (uint32_t)r * row_bytes, sr - j0, er - j0);
+            }
+        } else { // dense cluster: the row ranges stream through the whole staging area in chunks (CTA-uniform loops)
+            const int chunk = 3 * cap - kStageTail; // multiple of 4
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+                const int row_lo = s_start[r], row_hi = row_lo + s_len[r];
+                const int sr = r == 0 ? s[0] : (r == 1 ? s[1] : s[2]), er = r == 0 ? e[0] : (r == 1 ? e[1] : e[2]);
+#pragma unroll 1
+                for (int c0 = row_lo & ~3; c0 < row_hi; c0 += chunk) {
+                    const int c1 = min(c0 + chunk, row_hi); // this chunk's records: [max(c0, row_lo), c1)
+                    __syncthreads();                        // the previous chunk has been consumed
+                    stage_in4(smem_raw, io.pt, c0, (c1 - c0 + 3) & ~3, row_lo, c1);
+                    __syncthreads();
+                    masked_row(stage_addr, max(sr, c0) - c0, min(er, c1) - c0);
+                }
+            }
+        }
+        if (valid && !interior) traverse_global32(io, cell_end, g, P.wrap, si, self.x, self.y, cx0, cy0, v);
+    };
+    if constexpr (FAST) {
+        FastParticleLife32<kMatLaneTab> v(P, M);
+        walk(v, [&](uint32_t rb, int s_rel, int e_rel) { v.acc = walk_row4_call<kMatLaneTab>(rb, s_rel, e_rel, nself, v.acc, v.c1, M.row); });
+        nvx = fmaf(P.fast_k, v.ax(), vx * P.mu);
+        nvy = fmaf(P.fast_k, v.ay(), vy * P.mu);
+    } else {
+        LiteralForce<float, KIND, kMatLaneTab> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
+        walk(v, [&](uint32_t rb, int s_rel, int e_rel) { walk_row4(rb, s_rel, e_rel, nself, v); });
+        v.finish(nvx, nvy);
+    }
+    if (!valid) return;
+    float nx_ = fmaf(nvx, P.dt, self.x);
+    float ny_ = fmaf(nvy, P.dt, self.y);
+    if (P.wrap) {
+        nx_ = range_wrap(nx_);
+        ny_ = range_wrap(ny_);
+    } else {
+        nx_ = range_clamp(nx_);
+        ny_ = range_clamp(ny_);
+    }
+    const int o = io.out_slot(i, cxy, cell_end, g);
+    io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
+    nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, g);
+}
+
+// variant: 4 = candidates staged four wide (default), 2 = two targets per lane (kind 0 only), 1 = bulk-copied 16-byte records
 inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted,
                                          const ForceParams<float> &P, int nblocks, const float *gM, int kind, int cap, NextBin nbin,
-                                         cudaStream_t stream)
+                                         cudaStream_t stream, int variant)
 {
     if (nblocks <= 0) return cudaSuccess;
+    if (variant == 4) {
+        const int cap4 = ((cap + 3) & ~3) + kStageLead + kStageTail;
+        const size_t sbytes4 = (size_t)3 * cap4 * 12 + (size_t)P.m * kForceThreads * 4;
+#define PLIFE_LAUNCH_STAGED4(KIND, FAST)                                                                         \
+    do {                                                                                                         \
+        auto kfn = force_kernel_staged4<KIND, FAST>;                                                             \
+        if (sbytes4 > 48 * 1024) {                                                                               \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes4); \
+            if (e != cudaSuccess) return e;                                                                      \
+        }                                                                                                        \
+        kfn<<<nblocks, kForceThreads, sbytes4, stream>>>(io, cell_end, cell_sorted, P, gM, cap4, nbin);          \
+    } while (0)
+        switch (kind) {
+        case PLIFE_ACC_PARTICLE_LIFE: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PARTICLE_LIFE, true); break;
+        case PLIFE_ACC_PARTICLE_LIFE_R: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PARTICLE_LIFE_R, false); break;
+        case PLIFE_ACC_PARTICLE_LIFE_R2: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PARTICLE_LIFE_R2, false); break;
+        case PLIFE_ACC_ROTATOR_90: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_ROTATOR_90, false); break;
+        case PLIFE_ACC_ROTATOR_ATTR: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_ROTATOR_ATTR, false); break;
+        case PLIFE_ACC_PLANETS: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PLANETS, false); break;
+        default: return cudaErrorInvalidValue;
+        }
+#undef PLIFE_LAUNCH_STAGED4
+        return cudaGetLastError();
+    }
     const size_t sbytes = (size_t)3 * (cap + kStagePad) * 16 + (size_t)P.m * kForceThreads * 4;
+    if (variant == 2 && kind == PLIFE_ACC_PARTICLE_LIFE) {
+        if (sbytes > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(force_kernel_staged2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
+            if (e != cudaSuccess) return e;
+        }
+        force_kernel_staged2<<<nblocks, kForceThreads2, sbytes, stream>>>(io, cell_end, cell_sorted, P, gM, cap, nbin);
+        return cudaGetLastError();
+    }
 #define PLIFE_LAUNCH_STAGED(KIND, FAST)                                                                          \
     do {                                                                                                         \
         auto kfn = force_kernel_staged<KIND, FAST>;                                                              \
@@ -1034,7 +1641,7 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_cells(IOF32 io, co
         M.init();
         float vx, vy;
         io.self_vel(i, vx, vy);
-        FastParticleLife32<kMatShared> vf{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, M};
+        FastParticleLife32<kMatShared> vf(P, M);
         LiteralForce<float, KIND, kMatShared> vl{0.f, 0.f, P.r2, P.invr, P.k2, P.accp, M}; // this lane's share of the increments
 #pragma unroll 1
         for (int c0 = 0; c0 < T; c0 += capw - 2 * kCellsLpt * 4) {
@@ -1076,8 +1683,8 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_cells(IOF32 io, co
         }
         float ax, ay;
         if constexpr (FAST) {
-            ax = vf.ax;
-            ay = vf.ay;
+            ax = vf.ax();
+            ay = vf.ay();
         } else {
             ax = vl.vx;
             ay = vl.vy;
@@ -1093,10 +1700,10 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_cells(IOF32 io, co
             const int cx0 = cxy & 0xffff, cy0 = cxy >> 16;
             MatrixView<float, kMatGlobal> Mg{gMt, nullptr, P.m, own, FAST ? P.fast_a_scale : 1.0f, 0u, 0u};
             if constexpr (FAST) {
-                FastParticleLife32<kMatGlobal> v2{0.f, 0.f, P.fast_b, P.fast_d0, P.fast_h, Mg};
+                FastParticleLife32<kMatGlobal> v2(P, Mg);
                 traverse_global32_plain(io, cell_end, g, P.wrap, i, me.x, me.y, cx0, cy0, v2);
-                ax = v2.ax;
-                ay = v2.ay;
+                ax = v2.ax();
+                ay = v2.ay();
             } else {
                 LiteralForce<float, KIND, kMatGlobal> v2{0.f, 0.f, P.r2, P.invr, P.k2, P.accp, Mg};
                 traverse_global32_plain(io, cell_end, g, P.wrap, i, me.x, me.y, cx0, cy0, v2);
