@@ -48,7 +48,7 @@ extern "C" {
 #define PLIFE_FLAG_UNSTABLE_SORT 1 /* skip the in-cell stable ordering (faster; order in a cell arbitrary) */
 #define PLIFE_FLAG_NO_GRAPH 2      /* never replay the step as a CUDA graph (default: captured below 262144 particles, once the
                                       settings have been stable for two steps; any change of dt, settings or particles re-captures) */
-#define PLIFE_FLAG_ONE_TARGET 16   /* fp32 staged force kernel: one target per lane (the round-2 kernel) instead of two; same results bit for bit */
+/* 16 was PLIFE_FLAG_PAIRS (round 1's experimental two-targets-per-lane kernel, removed); the bit is ignored */
 #define PLIFE_FLAG_SCAN3 32         /* exclusive scan over the bins as three launches (tile sums, scan of sums, apply) instead of one */
 #define PLIFE_FLAG_NO_CELLS 64      /* fp32, at most 65536 particles: use the staged force kernel instead of the warp-per-cell one */
 #define PLIFE_FLAG_NO_FUSED_BIN 8  /* do not fuse the next step's binning into the force pass */

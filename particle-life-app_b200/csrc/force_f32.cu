@@ -35,7 +35,7 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
         return dispatch_force_cells(make_io(h), h->d_cell_end, h->d_cell_sorted, p, mt, h->acc_kind, next_bin(h, no_leavers), stream);
     if (p.g.staged) {
         // capacity of one staged row range: the CTA's 128 targets + K bins on either side (2 rho (1 + 1/K) particles on
-        // average) + 4.5 sigma of that count (uniform state; anything denser streams in chunks, traverse_chunked).
+        // average) + 4.5 sigma of that count (uniform state; anything denser streams in chunks).
         // PLIFE_STAGE_CAP overrides (experiments).
         const double mean = kForceThreads + 2.0 * rho * (1.0 + 1.0 / (1 << p.g.ks));
         int cap = (int)(mean + 4.5 * sqrt(mean) + 8.0);
@@ -43,9 +43,7 @@ cudaError_t launch_force_f32_part(plife_handle *h, const ForceParams<float> &p, 
         if (cap_env > 0) cap = cap_env;
         cap = (cap + 15) / 16 * 16;
         if (cap > 1536) cap = 1536;
-        static const int var_env = getenv("PLIFE_STAGED_VARIANT") ? atoi(getenv("PLIFE_STAGED_VARIANT")) : 0; // experiments: 1, 2 or 4
-        const int variant = var_env ? var_env : ((h->flags & PLIFE_FLAG_ONE_TARGET) ? 1 : 4);
-        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h, no_leavers), stream, variant);
+        return dispatch_force_staged(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mrow, h->acc_kind, cap, next_bin(h, no_leavers), stream);
     }
     if (p.g.ks != 0) return cudaErrorInvalidValue; // the v1 kernel writes results at the compute slot (make_grid never pairs it with fine bins)
     return dispatch_force<IOF32, true>(make_io(h), h->d_cell_end, h->d_cell_sorted, p, nblocks, mt, h->acc_kind, next_bin(h, no_leavers), stream);

@@ -508,8 +508,6 @@ struct FastParticleLife32 {
         acc.x = fmaf(gb.y, dxb.y, acc.x);
         acc.y = fmaf(gb.y, dyb.y, acc.y);
     }
-    // staged record {x, y, key, -} against nself = {-xi, -yi}: q.x + (-xi) is exactly q.x - xi
-    __device__ __forceinline__ void pair_rel(const float4 &q, float2 nself) { core(__float_as_int(q.z), fadd2(make_float2(q.x, q.y), nself)); }
 };
 
 struct NeighborDiag {
@@ -630,7 +628,7 @@ __global__ void __launch_bounds__(kForceThreads, IO::kMinBlocks) force_kernel(IO
                                                              const typename IO::R *__restrict__ gMt, NextBin nb)
 {
     using R = typename IO::R;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     R *sM = reinterpret_cast<R *>(smem_raw);
     int i0, lim;
     if (!cta_targets(P, i0, lim)) return;
@@ -681,31 +679,19 @@ __global__ void __launch_bounds__(kForceThreads, IO::kMinBlocks) force_kernel(IO
 // kernel (fused and unfused arithmetic) and which one a launch binds to is decided at module-load time:
 // results then differ by an ulp from process to process (found the hard way, profiles/r1_multigpu.md).
 #ifdef PLIFE_FORCE_F32_TU
-// ---- v2: shared-memory staged candidates (fp32) ------------------------------------------
-// The per-lane `LDG.128` of the kernel above costs 4 L1 data-pipe cycles per warp whatever the
-// address pattern, and the shared matrix lookup bank-conflicts between lanes of different cells
-// (profiles/r1_force_kernel.md); together they saturate L1TEX before the FP32 pipes.  Here each
-// CTA (128 consecutive sorted particles, about 8 cells) first copies the three index ranges that
-// cover the rows above / of / below its targets into shared memory - bin ids are row-major, so
-// [binA + dy*nxk - K, binB + dy*nxk + K] is ONE contiguous index range per dy - with three 1-D bulk copies
-// (cp.async.bulk + mbarrier, issued by one thread: no per-thread copy loop, no address arithmetic), and every lane
-// copies its own matrix row into a [type][thread] table.  The inner loop then issues one `LDS.128` (2.5 cycles with
-// the 2-3 distinct addresses of a warp) and one conflict-free `LDS.32` (bank = lane) per candidate.
+// ---- shared-memory staged candidates (fp32) ----------------------------------------------------------------------------
+// The per-lane `LDG.128` of the kernel above costs 4 L1 data-pipe cycles per warp whatever the address pattern, and the
+// shared matrix lookup bank-conflicts between lanes of different cells (profiles/r1_force_kernel.md); together they
+// saturate L1TEX before the FP32 pipes.  The staged kernel below copies the three index ranges that cover the rows
+// above / of / below a CTA's targets into shared memory - bin ids are row-major, so [binA + dy*nxk - K, binB + dy*nxk + K]
+// is ONE contiguous index range per dy - and every lane copies its own matrix row into a [type][thread] table (bank = lane:
+// conflict-free lookups).
 //
 // Fine bins: a lane walks the bins [own - K, own + K] of each row: every particle within rmax in x lies there
 // (bin = floor(K x / rmax) is monotone in x), and a row needs (2 + 1/K) cell widths of candidates instead of 3.
-//
-// Trip counts are rounded up to a multiple of 4 (no remainder loops): the extra candidates are
-// the first particles of the next bins, whose |dx| exceeds rmax for an interior lane, so
-// they contribute exactly zero; each staged range is followed by 3 far-away sentinels for the
-// case where the range itself ends.  Lanes on the domain seam walk global memory with the literal
-// 9-cell loop; CTAs whose ranges exceed the staging capacity (dense clusters) stream them through
-// it in chunks (traverse_chunked).
-#ifndef PLIFE_STAGED_MIN_BLOCKS
-#define PLIFE_STAGED_MIN_BLOCKS 12
-#endif
+// Lanes on the domain seam walk global memory with the literal 9-cell loop; CTAs whose ranges exceed the staging
+// capacity (dense clusters) stream them through it in chunks.
 constexpr int kTabMaxM = 32;
-constexpr int kStagePad = 3; // sentinels after each staged range
 static_assert(kForceThreads * 4 == (1 << kTypeShift), "lane-table row stride");
 
 __device__ __forceinline__ float4 lds128(uint32_t a)
@@ -715,35 +701,6 @@ __device__ __forceinline__ float4 lds128(uint32_t a)
     // believes to be a pure function of its address may be moved across them
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
-}
-
-// ---- mbarrier + 1-D bulk copy (TMA unit) ----
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); // visible to the async proxy
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// size: multiple of 16 bytes, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
 }
 
 // The literal 9-cell walk over global memory (seam lanes): B/Physics.java:412-437.  Records carry shifted types.
@@ -811,462 +768,6 @@ __device__ __forceinline__ void traverse_global32_plain(const IOF32 &io, const i
             v.pair(j, q, dx, dy);
         }
     }
-}
-
-// interior lane, staged ranges: 3 rows x bins [fb - K, fb + K]
-template <typename V>
-__device__ __forceinline__ void traverse_staged(const int32_t *__restrict__ cell_end, const Grid &g, float xi, float yi, int fb,
-                                                uint32_t stage_addr, int cap, const int *s_start, V &v)
-{
-    const int K = 1 << g.ks, nxk = g.nxk();
-    const float2 nself = make_float2(-xi, -yi);
-    // all six range bounds first: one round trip instead of three
-    int s[3], e[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int base = fb + (r - 1) * nxk;
-        s[r] = __ldg(cell_end + base - K - 1);
-        e[r] = __ldg(cell_end + base + K);
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s[r] - s_start[r]) * 16u;
-        const uint32_t a1 = a + (uint32_t)(e[r] - s[r]) * 16u;
-#pragma unroll 1
-        for (; a < a1; a += 64u) { // 4 candidates per trip, padded (see above)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                v.pair_rel(lds128(a + 16u * u), nself);
-            }
-        }
-    }
-}
-
-// Dense clusters: the three row ranges of a CTA do not fit the staging area (it is sized for the mean
-// density).  Instead of sending the whole CTA down the global-memory walk - where an evolved state
-// spends most of its pair evaluations - the ranges are streamed through the staging area in chunks.
-// Every thread of the CTA takes part in every chunk (two barriers each); a lane evaluates the part of
-// its own [s, e) that lies inside the chunk.  The 3 sentinels sit after EVERY chunk, so a padded trip
-// that runs off a chunk's end reads sentinels, never candidates the next chunk will deliver again.
-template <typename V>
-__device__ __forceinline__ void traverse_chunked(const IOF32 &io, const int32_t *__restrict__ cell_end, const Grid &g,
-                                                 bool interior, float xi, float yi, int fb, float4 *stage,
-                                                 uint32_t stage_addr, int chunk_cap, const int *s_start, const int *s_len, V &v)
-{
-    const int K = 1 << g.ks, nxk = g.nxk();
-    const int tid = threadIdx.x;
-    const float2 nself = make_float2(-xi, -yi);
-#pragma unroll 1
-    for (int r = 0; r < 3; ++r) {
-        int s = 0, e = 0;
-        if (interior) {
-            const int base = fb + (r - 1) * nxk;
-            s = __ldg(cell_end + base - K - 1);
-            e = __ldg(cell_end + base + K);
-        }
-        const int row_lo = s_start[r], row_hi = row_lo + s_len[r];
-#pragma unroll 1
-        for (int c0 = row_lo; c0 < row_hi; c0 += chunk_cap) {
-            const int clen = min(chunk_cap, row_hi - c0);
-            __syncthreads(); // the previous chunk has been consumed
-            const float4 *src = io.pt + c0;
-            for (int k = tid; k < clen + kStagePad; k += kForceThreads)
-                stage[k] = k < clen ? __ldg(src + k) : make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
-            __syncthreads();
-            const int a0 = max(s, c0), a1 = min(e, c0 + clen);
-            if (a0 < a1) {
-                uint32_t a = stage_addr + (uint32_t)(a0 - c0) * 16u;
-                const uint32_t aend = stage_addr + (uint32_t)(a1 - c0) * 16u;
-                for (; a < aend; a += 64u) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        v.pair_rel(lds128(a + 16u * u), nself);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// gM: row-major matrix [own][other] (for the vectorised row copy)
-template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED_MIN_BLOCKS) force_kernel_staged(IOF32 io, const int32_t *__restrict__ cell_end,
-                                                                    const int32_t *__restrict__ cell_sorted,
-                                                                    ForceParams<float> P, const float *__restrict__ gM,
-                                                                    int cap, NextBin nb)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                                      // [3][cap + kStagePad]
-    float *tab = reinterpret_cast<float *>(smem_raw + (size_t)3 * (cap + kStagePad) * 16);      // [m][kForceThreads]
-    __shared__ int s_start[3], s_len[3];
-    __shared__ __align__(8) unsigned long long s_bar;
-
-    int i0, lim;
-    if (!cta_targets(P, i0, lim)) return;
-    const int tid = threadIdx.x;
-    const int i = i0 + tid;
-    const bool valid = i < lim;
-    const Grid g = P.g;
-    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
-
-    // One thread finds the three row ranges of this CTA's targets and starts their copies; the others meanwhile
-    // load their own particle and fill the matrix table.
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        const int K = 1 << g.ks, nxk = g.nxk();
-        const int b0 = container_of(__ldg(cell_sorted + i0), g);
-        const int b1 = container_of(__ldg(cell_sorted + min(i0 + kForceThreads, lim) - 1), g);
-        int st[3], ln[3];
-        bool ok = true;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int lo = max(b0 + (r - 1) * nxk - K, P.bin_lo);
-            const int hi = min(b1 + (r - 1) * nxk + K, P.bin_hi);
-            st[r] = 0;
-            ln[r] = 0;
-            if (lo <= hi) {
-                st[r] = __ldg(cell_end + lo - 1);
-                ln[r] = __ldg(cell_end + hi) - st[r];
-            }
-            s_start[r] = st[r];
-            s_len[r] = ln[r];
-            ok = ok && ln[r] <= cap;
-        }
-        if (ok) {
-            mbar_arrive_expect_tx(bar, (uint32_t)(ln[0] + ln[1] + ln[2]) * 16u);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float4 *dst = stage + r * (cap + kStagePad);
-                if (ln[r] > 0) bulk_g2s(stage_addr + (uint32_t)(r * (cap + kStagePad)) * 16u, io.pt + st[r], (uint32_t)ln[r] * 16u, bar);
-#pragma unroll
-                for (int k = 0; k < kStagePad; ++k) dst[ln[r] + k] = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f); // sentinel: far away, matrix key 0
-            }
-        }
-    }
-    Cand<float> self{0.f, 0.f, 0, 0u};
-    int cxy = 0;
-    const int si = P.first + i; // index of this target in the sorted array (ghost rows precede it in slab mode)
-    float vx = 0.f, vy = 0.f;
-    if (valid) {
-        self = io.cand(si);
-        cxy = __ldg(cell_sorted + i);
-        io.self_vel(i, vx, vy);
-    }
-    // this lane's matrix row -> tab[other][tid] (bank = lane: conflict-free lookups)
-    {
-        const float mscale = FAST ? P.fast_a_scale : 1.0f;
-        const float *rowp = gM + self.type * P.m;
-        if ((P.m & 3) == 0) {
-            for (int t = 0; t < P.m; t += 4) {
-                const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rowp + t));
-                tab[(t + 0) * kForceThreads + tid] = r4.x * mscale;
-                tab[(t + 1) * kForceThreads + tid] = r4.y * mscale;
-                tab[(t + 2) * kForceThreads + tid] = r4.z * mscale;
-                tab[(t + 3) * kForceThreads + tid] = r4.w * mscale;
-            }
-        } else {
-            for (int t = 0; t < P.m; ++t) tab[t * kForceThreads + tid] = __ldg(rowp + t) * mscale;
-        }
-    }
-    __syncthreads(); // s_start / s_len, the barrier's initialisation and the sentinels are visible
-    const bool staged_ok = s_len[0] <= cap && s_len[1] <= cap && s_len[2] <= cap;
-    if (staged_ok) {
-        if (!valid) return;   // (in chunked mode, CTA-uniform, every thread is needed at the barriers)
-        mbar_wait(bar, 0);    // the three ranges have landed
-    }
-
-    const int cx0 = (cxy & 0xffff) >> g.ks, cy0 = scan_row(cxy >> 16, g);
-    const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
-    const int fb = (cxy & 0xffff) + (cy0 + g.ly_shift) * g.nxk(); // own bin (interior lanes: no clamp needed)
-    MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, self.type, 1.0f, 0u, 0u};
-    M.init();
-    const int chunk_cap = 3 * (cap + kStagePad) - kStagePad; // the whole staging area as one buffer
-    float nvx, nvy;
-    auto walk = [&](auto &v) {
-        if (staged_ok) {
-            if (interior) traverse_staged(cell_end, g, self.x, self.y, fb, stage_addr, cap, s_start, v);
-        } else {
-            traverse_chunked(io, cell_end, g, interior, self.x, self.y, fb, stage, stage_addr, chunk_cap, s_start, s_len, v);
-        }
-        if (valid && !interior) traverse_global32(io, cell_end, g, P.wrap, si, self.x, self.y, cx0, cy0, v);
-    };
-    if constexpr (FAST) {
-        FastParticleLife32<kMatLaneTab> v(P, M);
-        walk(v);
-        nvx = fmaf(P.fast_k, v.ax(), vx * P.mu);
-        nvy = fmaf(P.fast_k, v.ay(), vy * P.mu);
-    } else {
-        LiteralForce<float, KIND, kMatLaneTab> v{vx * P.mu, vy * P.mu, P.r2, P.invr, P.k2, P.accp, M};
-        walk(v);
-        v.finish(nvx, nvy);
-    }
-    if (!valid) return;
-    float nx_ = fmaf(nvx, P.dt, self.x);
-    float ny_ = fmaf(nvy, P.dt, self.y);
-    if (P.wrap) {
-        nx_ = range_wrap(nx_);
-        ny_ = range_wrap(ny_);
-    } else {
-        nx_ = range_clamp(nx_);
-        ny_ = range_clamp(ny_);
-    }
-    const int o = io.out_slot(i, cxy, cell_end, g);
-    io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
-    nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, g);
-}
-
-// ---- v3: two targets per lane -----------------------------------------------------------------------------------------
-// ncu on the kernel above at 16 particles per cell (profiles/r2_force_c3.ncu_details.txt): "Mem Busy 94 %" - the SM's ONE
-// shared-memory pipe (one 128-byte wavefront per cycle for all four schedulers), not the issue slots (80 %), is what
-// binds it.  With fine bins the 32 lanes of a warp read up to 16 different 16-byte records per LDS.128 (4.5 wavefronts on
-// average, 8 distinct bank groups), plus one wavefront for the matrix lookup: 5.5 wavefronts per candidate and target.
-// Here a lane owns TWO consecutive targets (a CTA is 64 threads, still 128 targets and the same staging): one LDS.128
-// of the candidate and one LDS.64 of the two matrix entries (table [type][2 * thread + {0, 1}]: conflict-free, two
-// wavefronts) serve two pair evaluations - 3.3 wavefronts each.  The two targets are neighbours in the sorted order, so
-// they sit in the same or in adjacent bins: the lane walks the union of their ranges, bins [binA - K, binB + K], and
-// the few candidates outside a target's own window are beyond rmax in x for it (exact zeros, like the padding).
-// Targets that cannot share a walk (different rows, more than a cell apart, one of them on the seam) take one pass each
-// with the other slot parked far away.  Per pair: the same operations in the same order as the kernel above, so both
-// kernels give bit-identical results.
-#ifndef PLIFE_STAGED2_MIN_BLOCKS
-#define PLIFE_STAGED2_MIN_BLOCKS 11
-#endif
-constexpr int kForceThreads2 = kForceThreads / 2;
-constexpr float kParked = -2.0e9f; // -position of a parked target slot: every candidate (sentinels included) is far away
-
-__device__ __forceinline__ float2 lds64(uint32_t a)
-{
-    float2 v;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-    return v;
-}
-
-struct FastParticleLife32x2 {
-    float2 acc0, acc1; // {ax, ay} of the two targets
-    float2 c1;         // {-b, -rmax}
-    uint32_t row2;     // shared-window byte address of tab[0][2 * thread]
-    __device__ __forceinline__ FastParticleLife32x2(const ForceParams<float> &P, uint32_t row)
-        : acc0(make_float2(0.f, 0.f)), acc1(make_float2(0.f, 0.f)), c1(make_float2(-P.fast_b, -P.rmax)), row2(row)
-    {
-    }
-    static __device__ __forceinline__ float weight(float2 rp, float a)
-    {
-        const float rep = fminf(rp.x, 0.0f);
-        const float att = fmaxf(fminf(-rp.y, rp.x), 0.0f);
-        return fmaf(a, att, rep);
-    }
-    __device__ __forceinline__ void pair2(const float4 &q, float2 n0, float2 n1)
-    {
-        const float2 qp = make_float2(q.x, q.y);
-        const float2 d0 = fadd2(qp, n0), d1 = fadd2(qp, n1);
-        const float s0 = fmaf(d0.x, d0.x, fmaf(d0.y, d0.y, kTiny)), s1 = fmaf(d1.x, d1.x, fmaf(d1.y, d1.y, kTiny));
-        const float u0 = rsqrt_fast(s0), u1 = rsqrt_fast(s1);
-        const float2 a = lds64(row2 + (uint32_t)__float_as_int(q.z));
-        const float2 one = make_float2(1.0f, 1.0f);
-        const float g0 = weight(ffma2(c1, make_float2(u0, u0), one), a.x);
-        const float g1 = weight(ffma2(c1, make_float2(u1, u1), one), a.y);
-        acc0 = ffma2(make_float2(g0, g0), d0, acc0);
-        acc1 = ffma2(make_float2(g1, g1), d1, acc1);
-    }
-};
-
-// candidates [a, a1) of the staging area (byte addresses), 4 per trip (padded, see above)
-__device__ __forceinline__ void walk_span2(uint32_t a, uint32_t a1, float2 n0, float2 n1, FastParticleLife32x2 &v)
-{
-#pragma unroll 1
-    for (; a < a1; a += 64u) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v.pair2(lds128(a + 16u * u), n0, n1);
-    }
-}
-
-__global__ void __launch_bounds__(kForceThreads2, PLIFE_STAGED2_MIN_BLOCKS)
-    force_kernel_staged2(IOF32 io, const int32_t *__restrict__ cell_end, const int32_t *__restrict__ cell_sorted, ForceParams<float> P,
-                         const float *__restrict__ gM, int cap, NextBin nb)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                                  // [3][cap + kStagePad]
-    float *tab = reinterpret_cast<float *>(smem_raw + (size_t)3 * (cap + kStagePad) * 16);  // [m][kForceThreads]: column = 2 * thread + slot
-    __shared__ int s_start[3], s_len[3];
-    __shared__ __align__(8) unsigned long long s_bar;
-
-    int i0, lim;
-    if (!cta_targets(P, i0, lim)) return;
-    const int tid = threadIdx.x;
-    const int iA = i0 + 2 * tid; // this lane's targets: iA and iA + 1
-    const bool validA = iA < lim, validB = iA + 1 < lim;
-    const Grid g = P.g;
-    const int K = 1 << g.ks, nxk = g.nxk();
-    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
-
-    if (tid == 0) { // the three row ranges of this CTA's targets: found and copied exactly like in force_kernel_staged
-        mbar_init(bar, 1);
-        const int b0 = container_of(__ldg(cell_sorted + i0), g);
-        const int b1 = container_of(__ldg(cell_sorted + min(i0 + kForceThreads, lim) - 1), g);
-        int st[3], ln[3];
-        bool ok = true;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int lo = max(b0 + (r - 1) * nxk - K, P.bin_lo);
-            const int hi = min(b1 + (r - 1) * nxk + K, P.bin_hi);
-            st[r] = 0;
-            ln[r] = 0;
-            if (lo <= hi) {
-                st[r] = __ldg(cell_end + lo - 1);
-                ln[r] = __ldg(cell_end + hi) - st[r];
-            }
-            s_start[r] = st[r];
-            s_len[r] = ln[r];
-            ok = ok && ln[r] <= cap;
-        }
-        if (ok) {
-            mbar_arrive_expect_tx(bar, (uint32_t)(ln[0] + ln[1] + ln[2]) * 16u);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float4 *dst = stage + r * (cap + kStagePad);
-                if (ln[r] > 0) bulk_g2s(stage_addr + (uint32_t)(r * (cap + kStagePad)) * 16u, io.pt + st[r], (uint32_t)ln[r] * 16u, bar);
-#pragma unroll
-                for (int k = 0; k < kStagePad; ++k) dst[ln[r] + k] = make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
-            }
-        }
-    }
-    // own particles (records carry type << kTypeShift), bin words, velocities
-    float4 meA = make_float4(0.f, 0.f, 0.f, 0.f), meB = meA;
-    int cxyA = 0, cxyB = 0;
-    float vxA = 0.f, vyA = 0.f, vxB = 0.f, vyB = 0.f;
-    if (validA) {
-        meA = __ldg(io.pt + P.first + iA);
-        cxyA = __ldg(cell_sorted + iA);
-        io.self_vel(iA, vxA, vyA);
-    }
-    if (validB) {
-        meB = __ldg(io.pt + P.first + iA + 1);
-        cxyB = __ldg(cell_sorted + iA + 1);
-        io.self_vel(iA + 1, vxB, vyB);
-    }
-    const int typeA = __float_as_int(meA.z) >> kTypeShift, typeB = __float_as_int(meB.z) >> kTypeShift;
-    { // matrix rows of the two targets -> tab[other][2 * tid + {0, 1}]
-        const float mscale = P.fast_a_scale;
-        const float *rowA = gM + typeA * P.m, *rowB = gM + typeB * P.m;
-        float2 *col = reinterpret_cast<float2 *>(tab) + tid;
-        if ((P.m & 3) == 0) {
-            for (int t = 0; t < P.m; t += 4) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(rowA + t));
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rowB + t));
-                col[(t + 0) * kForceThreads2] = make_float2(a4.x * mscale, b4.x * mscale);
-                col[(t + 1) * kForceThreads2] = make_float2(a4.y * mscale, b4.y * mscale);
-                col[(t + 2) * kForceThreads2] = make_float2(a4.z * mscale, b4.z * mscale);
-                col[(t + 3) * kForceThreads2] = make_float2(a4.w * mscale, b4.w * mscale);
-            }
-        } else {
-            for (int t = 0; t < P.m; ++t) col[t * kForceThreads2] = make_float2(__ldg(rowA + t) * mscale, __ldg(rowB + t) * mscale);
-        }
-    }
-    __syncthreads();
-    const bool staged_ok = s_len[0] <= cap && s_len[1] <= cap && s_len[2] <= cap;
-    if (staged_ok) {
-        if (!validA) return; // (in chunked mode every thread is needed at the barriers)
-        mbar_wait(bar, 0);
-    }
-
-    const int cx0A = (cxyA & 0xffff) >> g.ks, cy0A = scan_row(cxyA >> 16, g);
-    const int cx0B = (cxyB & 0xffff) >> g.ks, cy0B = scan_row(cxyB >> 16, g);
-    const bool intA = validA && g.nx >= 4 && cx0A >= 1 && cx0A <= g.nx - 2 && cy0A >= 1 && cy0A <= g.ny - 2;
-    const bool intB = validB && g.nx >= 4 && cx0B >= 1 && cx0B <= g.nx - 2 && cy0B >= 1 && cy0B <= g.ny - 2;
-    const int fbA = (cxyA & 0xffff) + (cy0A + g.ly_shift) * nxk, fbB = (cxyB & 0xffff) + (cy0B + g.ly_shift) * nxk;
-    // one shared walk if the two windows overlap almost completely (same row, at most a cell apart); else one pass each
-    const bool paired = intA && intB && cy0A == cy0B && fbB >= fbA && fbB - fbA <= K;
-    const uint32_t row2 = (uint32_t)__cvta_generic_to_shared(tab) + 8u * (uint32_t)tid;
-    FastParticleLife32x2 v(P, row2);
-    const float2 park = make_float2(kParked, kParked);
-    const float2 nA = make_float2(-meA.x, -meA.y), nB = make_float2(-meB.x, -meB.y);
-    const int chunk_cap = 3 * (cap + kStagePad) - kStagePad;
-    // pass 0: A (together with B if paired); pass 1: B alone (unpaired only, rare)
-    const bool live0 = intA, live1 = intB && !paired;
-    const int hi0 = paired ? fbB : fbA;
-    const float2 nB0 = paired ? nB : park;
-    int s0[3], e0[3], s1[3], e1[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        s0[r] = live0 ? __ldg(cell_end + fbA + (r - 1) * nxk - K - 1) : 0;
-        e0[r] = live0 ? __ldg(cell_end + hi0 + (r - 1) * nxk + K) : 0;
-        s1[r] = live1 ? __ldg(cell_end + fbB + (r - 1) * nxk - K - 1) : 0;
-        e1[r] = live1 ? __ldg(cell_end + fbB + (r - 1) * nxk + K) : 0;
-    }
-    if (staged_ok) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + s0[r] - s_start[r]) * 16u;
-            walk_span2(a, a + (uint32_t)(e0[r] - s0[r]) * 16u, nA, nB0, v);
-        }
-        if (live1) {
-#pragma unroll 1
-            for (int r = 0; r < 3; ++r) {
-                const int sr = r == 0 ? s1[0] : (r == 1 ? s1[1] : s1[2]), er = r == 0 ? e1[0] : (r == 1 ? e1[1] : e1[2]);
-                const uint32_t a = stage_addr + (uint32_t)(r * (cap + kStagePad) + sr - s_start[r]) * 16u;
-                walk_span2(a, a + (uint32_t)(er - sr) * 16u, park, nB, v);
-            }
-        }
-    } else { // dense cluster: the row ranges stream through the staging area in chunks (CTA-uniform loops, two barriers each)
-#pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
-            const int row_lo = s_start[r], row_hi = row_lo + s_len[r];
-            const int sr0 = r == 0 ? s0[0] : (r == 1 ? s0[1] : s0[2]), er0 = r == 0 ? e0[0] : (r == 1 ? e0[1] : e0[2]);
-            const int sr1 = r == 0 ? s1[0] : (r == 1 ? s1[1] : s1[2]), er1 = r == 0 ? e1[0] : (r == 1 ? e1[1] : e1[2]);
-#pragma unroll 1
-            for (int c0 = row_lo; c0 < row_hi; c0 += chunk_cap) {
-                const int clen = min(chunk_cap, row_hi - c0);
-                __syncthreads(); // the previous chunk has been consumed
-                const float4 *src = io.pt + c0;
-                for (int k = tid; k < clen + kStagePad; k += kForceThreads2)
-                    stage[k] = k < clen ? __ldg(src + k) : make_float4(1.0e9f, 1.0e9f, 0.f, 0.f);
-                __syncthreads();
-                int a0 = max(sr0, c0), a1 = min(er0, c0 + clen);
-                if (a0 < a1) walk_span2(stage_addr + (uint32_t)(a0 - c0) * 16u, stage_addr + (uint32_t)(a1 - c0) * 16u, nA, nB0, v);
-                a0 = max(sr1, c0), a1 = min(er1, c0 + clen);
-                if (a0 < a1) walk_span2(stage_addr + (uint32_t)(a0 - c0) * 16u, stage_addr + (uint32_t)(a1 - c0) * 16u, park, nB, v);
-            }
-        }
-    }
-    // seam targets: the literal 9-cell walk over global memory, one target at a time
-    float axA = v.acc0.x, ayA = v.acc0.y, axB = v.acc1.x, ayB = v.acc1.y;
-    if ((validA && !intA) || (validB && !intB)) {
-        MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, 0, 1.0f, 0u, 0u};
-        if (validA && !intA) {
-            M.row = row2;
-            FastParticleLife32<kMatLaneTab> v1(P, M);
-            traverse_global32(io, cell_end, g, P.wrap, P.first + iA, meA.x, meA.y, cx0A, cy0A, v1);
-            axA = v1.ax();
-            ayA = v1.ay();
-        }
-        if (validB && !intB) {
-            M.row = row2 + 4u;
-            FastParticleLife32<kMatLaneTab> v1(P, M);
-            traverse_global32(io, cell_end, g, P.wrap, P.first + iA + 1, meB.x, meB.y, cx0B, cy0B, v1);
-            axB = v1.ax();
-            ayB = v1.ay();
-        }
-    }
-    auto finish = [&](int i, const float4 &me, int type, int cxy, float vx, float vy, float ax, float ay) {
-        const float nvx = fmaf(P.fast_k, ax, vx * P.mu); // friction first (:401-402), then the summed acceleration
-        const float nvy = fmaf(P.fast_k, ay, vy * P.mu);
-        float nx_ = fmaf(nvx, P.dt, me.x);
-        float ny_ = fmaf(nvy, P.dt, me.y);
-        if (P.wrap) {
-            nx_ = range_wrap(nx_);
-            ny_ = range_wrap(ny_);
-        } else {
-            nx_ = range_clamp(nx_);
-            ny_ = range_clamp(ny_);
-        }
-        const int o = io.out_slot(i, cxy, cell_end, g);
-        io.store(o, nx_, ny_, nvx, nvy, type, __float_as_uint(me.w));
-        nb.add(o, nx_, ny_, nvx, nvy, type, __float_as_uint(me.w), g);
-    };
-    if (validA) finish(iA, meA, typeA, cxyA, vxA, vyA, axA, ayA);
-    if (validB) finish(iA + 1, meB, typeB, cxyB, vxB, vyB, axB, ayB);
 }
 
 // ---- v4: candidates staged four wide ------------------------------------------------------------------------------------
@@ -1504,53 +1005,21 @@ __global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED4_MIN_BLOCKS)
     nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, g);
 }
 
-// variant: 4 = candidates staged four wide (default), 2 = two targets per lane (kind 0 only), 1 = bulk-copied 16-byte records
 inline cudaError_t dispatch_force_staged(const IOF32 &io, const int32_t *cell_end, const int32_t *cell_sorted,
                                          const ForceParams<float> &P, int nblocks, const float *gM, int kind, int cap, NextBin nbin,
-                                         cudaStream_t stream, int variant)
+                                         cudaStream_t stream)
 {
     if (nblocks <= 0) return cudaSuccess;
-    if (variant == 4) {
-        const int cap4 = ((cap + 3) & ~3) + kStageLead + kStageTail;
-        const size_t sbytes4 = (size_t)3 * cap4 * 12 + (size_t)P.m * kForceThreads * 4;
-#define PLIFE_LAUNCH_STAGED4(KIND, FAST)                                                                         \
-    do {                                                                                                         \
-        auto kfn = force_kernel_staged4<KIND, FAST>;                                                             \
-        if (sbytes4 > 48 * 1024) {                                                                               \
-            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes4); \
-            if (e != cudaSuccess) return e;                                                                      \
-        }                                                                                                        \
-        kfn<<<nblocks, kForceThreads, sbytes4, stream>>>(io, cell_end, cell_sorted, P, gM, cap4, nbin);          \
-    } while (0)
-        switch (kind) {
-        case PLIFE_ACC_PARTICLE_LIFE: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PARTICLE_LIFE, true); break;
-        case PLIFE_ACC_PARTICLE_LIFE_R: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PARTICLE_LIFE_R, false); break;
-        case PLIFE_ACC_PARTICLE_LIFE_R2: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PARTICLE_LIFE_R2, false); break;
-        case PLIFE_ACC_ROTATOR_90: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_ROTATOR_90, false); break;
-        case PLIFE_ACC_ROTATOR_ATTR: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_ROTATOR_ATTR, false); break;
-        case PLIFE_ACC_PLANETS: PLIFE_LAUNCH_STAGED4(PLIFE_ACC_PLANETS, false); break;
-        default: return cudaErrorInvalidValue;
-        }
-#undef PLIFE_LAUNCH_STAGED4
-        return cudaGetLastError();
-    }
-    const size_t sbytes = (size_t)3 * (cap + kStagePad) * 16 + (size_t)P.m * kForceThreads * 4;
-    if (variant == 2 && kind == PLIFE_ACC_PARTICLE_LIFE) {
-        if (sbytes > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(force_kernel_staged2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
-            if (e != cudaSuccess) return e;
-        }
-        force_kernel_staged2<<<nblocks, kForceThreads2, sbytes, stream>>>(io, cell_end, cell_sorted, P, gM, cap, nbin);
-        return cudaGetLastError();
-    }
+    const int cap4 = ((cap + 3) & ~3) + kStageLead + kStageTail; // candidate slots per staging row
+    const size_t sbytes = (size_t)3 * cap4 * 12 + (size_t)P.m * kForceThreads * 4;
 #define PLIFE_LAUNCH_STAGED(KIND, FAST)                                                                          \
     do {                                                                                                         \
-        auto kfn = force_kernel_staged<KIND, FAST>;                                                              \
+        auto kfn = force_kernel_staged4<KIND, FAST>;                                                             \
         if (sbytes > 48 * 1024) {                                                                                \
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);  \
             if (e != cudaSuccess) return e;                                                                      \
         }                                                                                                        \
-        kfn<<<nblocks, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, P, gM, cap, nbin);            \
+        kfn<<<nblocks, kForceThreads, sbytes, stream>>>(io, cell_end, cell_sorted, P, gM, cap4, nbin);           \
     } while (0)
     switch (kind) {
     case PLIFE_ACC_PARTICLE_LIFE: PLIFE_LAUNCH_STAGED(PLIFE_ACC_PARTICLE_LIFE, true); break;
@@ -1581,7 +1050,7 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel_cells(IOF32 io, co
                                                                    const int32_t *__restrict__ cell_sorted, ForceParams<float> P,
                                                                    const float *__restrict__ gMt, int capw, int wpc, NextBin nb)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kWarps = kForceThreads / 32;
     float4 *buf = reinterpret_cast<float4 *>(smem_raw) + (size_t)(threadIdx.x >> 5) * capw; // this warp's candidates
     float *sM = reinterpret_cast<float *>(smem_raw + (size_t)kWarps * capw * 16);

@@ -18,7 +18,7 @@ import numpy as np
 from . import _native as N
 from . import synth
 from ._native import (ACC_PARTICLE_LIFE, ACC_PARTICLE_LIFE_R, ACC_PARTICLE_LIFE_R2, ACC_PLANETS,
-                      ACC_ROTATOR_90, ACC_ROTATOR_ATTR, F32, F64, FLAG_FORCE_V1, FLAG_NO_FUSED_BIN, FLAG_ONE_TARGET, FLAG_SCAN3, FLAG_NO_CELLS,
+                      ACC_ROTATOR_90, ACC_ROTATOR_ATTR, F32, F64, FLAG_FORCE_V1, FLAG_NO_FUSED_BIN, FLAG_SCAN3, FLAG_NO_CELLS,
                       FLAG_UNSTABLE_SORT, KERNEL_NAMES, PlifeError)
 
 __all__ = ["Physics", "PhysicsSettings", "NativePhysics", "Particles", "PlifeError",

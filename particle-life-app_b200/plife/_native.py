@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("PLIFE_LIB") or os.path.join(_HERE, "libplife.so")  # 
 OK = 0
 ERR_INVALID, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_STOPPED = -1, -2, -3, -4, -5, -6
 F32, F64 = 0, 1
-FLAG_UNSTABLE_SORT, FLAG_NO_GRAPH, FLAG_FORCE_V1, FLAG_NO_FUSED_BIN, FLAG_ONE_TARGET, FLAG_SCAN3, FLAG_NO_CELLS = 1, 2, 4, 8, 16, 32, 64
+FLAG_UNSTABLE_SORT, FLAG_NO_GRAPH, FLAG_FORCE_V1, FLAG_NO_FUSED_BIN, FLAG_SCAN3, FLAG_NO_CELLS = 1, 2, 4, 8, 32, 64
 (ACC_PARTICLE_LIFE, ACC_PARTICLE_LIFE_R, ACC_PARTICLE_LIFE_R2, ACC_ROTATOR_90, ACC_ROTATOR_ATTR,
  ACC_PLANETS) = range(6)
 K_BIN, K_SCAN, K_SCATTER, K_GATHER, K_FORCE, K_COUNT = 0, 1, 2, 3, 4, 5
