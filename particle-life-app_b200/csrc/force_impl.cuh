@@ -897,6 +897,19 @@ __global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED4_MIN_BLOCKS)
         cxy = __ldg(cell_sorted + i);
         io.self_vel(i, vx, vy);
     }
+    // the six bounds of this lane's candidate ranges depend on the bin word only: fetched now, in the shadow of the staging
+    const int cx0 = (cxy & 0xffff) >> g.ks, cy0 = scan_row(cxy >> 16, g);
+    const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
+    const int fb = (cxy & 0xffff) + (cy0 + g.ly_shift) * nxk; // own bin (interior lanes: no clamp needed)
+    int s[3] = {0, 0, 0}, e[3] = {0, 0, 0};
+    if (interior) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int base = fb + (r - 1) * nxk;
+            s[r] = __ldg(cell_end + base - K - 1);
+            e[r] = __ldg(cell_end + base + K);
+        }
+    }
     { // this lane's matrix row -> tab[other][tid] (bank = lane: conflict-free lookups)
         const float mscale = FAST ? P.fast_a_scale : 1.0f;
         const float *rowp = gM + self.type * P.m;
@@ -922,28 +935,22 @@ __global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED4_MIN_BLOCKS)
             stage_in4(smem_raw + (size_t)r * row_bytes, io.pt, j0, ((s_start[r] - j0 + s_len[r] + 3) & ~3) + kStageTail, s_start[r],
                       s_start[r] + s_len[r]);
         }
+    }
+    // the slot of the result in the reference's order is a rank over the pre-sort indices of the cell: global loads that need
+    // nothing from the force pass, issued while the staging stores drain
+    int o = 0;
+    if (valid) o = io.out_slot(i, cxy, cell_end, g);
+    if (staged_ok) {
         __syncthreads();
         if (!valid) return; // (in chunked mode every thread is needed at the barriers)
     }
 
-    const int cx0 = (cxy & 0xffff) >> g.ks, cy0 = scan_row(cxy >> 16, g);
-    const bool interior = valid && g.nx >= 4 && cx0 >= 1 && cx0 <= g.nx - 2 && cy0 >= 1 && cy0 <= g.ny - 2;
-    const int fb = (cxy & 0xffff) + (cy0 + g.ly_shift) * nxk; // own bin (interior lanes: no clamp needed)
     MatrixView<float, kMatLaneTab> M{nullptr, tab, P.m, self.type, 1.0f, 0u, 0u};
     M.init();
     const float2 nself = make_float2(-self.x, -self.y);
     float nvx, nvy;
     // walk(v, masked_row): `masked_row(rb, s_rel, e_rel)` is how this visitor walks one row with masks
     auto walk = [&](auto &v, auto masked_row) {
-        int s[3] = {0, 0, 0}, e[3] = {0, 0, 0};
-        if (interior) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int base = fb + (r - 1) * nxk;
-                s[r] = __ldg(cell_end + base - K - 1);
-                e[r] = __ldg(cell_end + base + K);
-            }
-        }
         if (staged_ok && s_clean && FAST) {
             if (interior) {
 #pragma unroll
@@ -1000,7 +1007,6 @@ __global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED4_MIN_BLOCKS)
         nx_ = range_clamp(nx_);
         ny_ = range_clamp(ny_);
     }
-    const int o = io.out_slot(i, cxy, cell_end, g);
     io.store(o, nx_, ny_, nvx, nvy, self.type, self.id);
     nb.add(o, nx_, ny_, nvx, nvy, self.type, self.id, g);
 }
