@@ -426,7 +426,7 @@ constexpr int kGatherUnroll = 2; // measured: 1 -> 0.186 ms, 2 -> 0.166 ms, 4 ->
 // the pre-sort slots of its CELL, which the force pass computes from src_sorted (reference_slot, plife_internal.h).
 // Bins nest in cells, so both slots lie in the cell's own index range; with ks = 0 they coincide.
 // The record's type field is stored shifted (kTypeShift): it is the byte offset of a row of the force kernel's per-lane
-// matrix table, so staging candidates in shared memory is a plain bulk copy.
+// matrix table, so the staged key is the table offset itself.
 // Block 0 also prepares the slab step (tr: target ranges of the two force launches; mig0/mig1: migration cursors).
 template <bool STABLE>
 __global__ void __launch_bounds__(kThreads) gather_f32(const float4 *__restrict__ pt_in, float4 *__restrict__ pt_out, DevInt n_, Grid g,

@@ -951,7 +951,7 @@ __global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED4_MIN_BLOCKS)
     float nvx, nvy;
     // walk(v, masked_row): `masked_row(rb, s_rel, e_rel)` is how this visitor walks one row with masks
     auto walk = [&](auto &v, auto masked_row) {
-        if (staged_ok && s_clean && FAST) {
+        if (staged_ok && s_clean) {
             if (interior) {
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
