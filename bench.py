@@ -687,6 +687,29 @@ def run_ours(args):
         q.close()
         secondary["C5_rotator"] = s
 
+        # BASELINE config 1 (the app's own default scale; the reference's CPU-runnable case): 10 000 particles at rmax 0.04
+        # and at the snapshot default rmax 0.02, replayed as a CUDA graph
+        for nm, label in (("C1", "C1: 10000 particles, 6 types, rmax=0.04 (nx=25, 16 particles/cell): launch-latency regime, CUDA-graph replay"),
+                          ("C1d", "C1 at the reference's default rmax=0.02 (nx=50, 4 particles/cell)")):
+            q, s = single_gpu_secondary(torch, plife, stream, local_rank, nm, plife.F32, 2000, label, hbm_peak, traffic)
+            s["graph_steps"] = q.step_stats().get("graph_steps")
+            q.close()
+            secondary[nm] = s
+        if not args.no_cpu:
+            # the CPU arm at C1 (both rmax) and C2 as well, all host threads and the reference's default 12
+            threads = os.cpu_count() or 1
+            for nm, steps in (("C1", 100), ("C1d", 100), ("C2", 10)):
+                c = workload(nm)
+                c["n_per_gpu"] = c["n"]
+                arm = CpuArm(c)
+                r = arm.run(steps, 3, threads, probed=0)
+                entry = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
+                if threads != REF_THREADS:
+                    r12 = arm.run(steps, 1, REF_THREADS, probed=0)
+                    entry["reference_default_threads"] = {"value": r12["value"], "unit": UNIT, "cores": REF_THREADS, "ms_per_step": r12["ms_per_step"]}
+                secondary[nm]["cpu_baseline"] = entry
+                del arm
+
     if rank != 0:
         return 0
 
