@@ -691,7 +691,7 @@ def run_ours(args):
         # and at the snapshot default rmax 0.02, replayed as a CUDA graph
         for nm, label in (("C1", "C1: 10000 particles, 6 types, rmax=0.04 (nx=25, 16 particles/cell): launch-latency regime, CUDA-graph replay"),
                           ("C1d", "C1 at the reference's default rmax=0.02 (nx=50, 4 particles/cell)")):
-            q, s = single_gpu_secondary(torch, plife, stream, local_rank, nm, plife.F32, 2000, label, hbm_peak, traffic)
+            q, s = single_gpu_secondary(torch, plife, stream, local_rank, nm, plife.F32, 100, label, hbm_peak, traffic)  # (100 steps: still the uniform state)
             s["graph_steps"] = q.step_stats().get("graph_steps")
             q.close()
             secondary[nm] = s
