@@ -153,6 +153,8 @@ int plife_snapshot_async(plife_handle *h, float *pos_xy, float *vel_xy, int32_t 
 /* The same with the types as one byte each (the app allows at most 256 types, A/Main.java:745): 17 instead of
  * 20 bytes per particle over PCIe; a GL renderer binds it as an unsigned-byte integer attribute. */
 int plife_snapshot_async_u8(plife_handle *h, float *pos_xy, float *vel_xy, uint8_t *type_u8);
+/* Waits for the OLDEST snapshot requested and not yet waited for.  Up to two requests may be in flight: request snapshot
+ * k + 1 before waiting for snapshot k and the copy engine never idles (a third request first waits for the oldest). */
 int plife_snapshot_wait(plife_handle *h);
 
 /* Headless generators with the distributions of the reference's default setters

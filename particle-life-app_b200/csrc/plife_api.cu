@@ -980,11 +980,17 @@ static int snapshot_async_impl(plife_handle *h, float *pos_xy, float *vel_xy, in
             h->d_snap_async[k] = nullptr;
         }
         h->snap_async_cap = 0;
+        h->snap_awaited = h->snap_issued; // (both streams are idle: nothing is in flight any more)
         for (int k = 0; k < 2; k++) CU(h, cudaMalloc(&h->d_snap_async[k], (size_t)want * 20));
         h->snap_async_cap = want;
     }
-    const int k = h->snap_k;
-    h->snap_k ^= 1;
+    // two snapshots may be in flight (one being copied while the next one is taken); a third waits for the oldest
+    while (h->snap_issued - h->snap_awaited >= 2) {
+        CU(h, cudaEventSynchronize(h->snap_done[h->snap_awaited & 1]));
+        h->snap_awaited++;
+    }
+    const int k = (int)(h->snap_issued & 1);
+    h->snap_issued++;
     float2 *dp = (float2 *)h->d_snap_async[k];
     float2 *dv = dp + h->snap_async_cap;
     int32_t *dt = (int32_t *)(dv + h->snap_async_cap);
@@ -1016,7 +1022,12 @@ int plife_snapshot_async_u8(plife_handle *h, float *pos_xy, float *vel_xy, uint8
 int plife_snapshot_wait(plife_handle *h)
 {
     CHECK_HANDLE(h);
-    if (h->snap_init) CU(h, cudaStreamSynchronize(h->copy_stream));
+    // the OLDEST snapshot not yet handed over: with two requests in flight the caller gets the earlier one while the
+    // later one is still crossing PCIe (true double buffering; one request in flight: the old behaviour)
+    if (h->snap_init && h->snap_awaited < h->snap_issued) {
+        CU(h, cudaEventSynchronize(h->snap_done[h->snap_awaited & 1]));
+        h->snap_awaited++;
+    }
     return PLIFE_OK;
 }
 

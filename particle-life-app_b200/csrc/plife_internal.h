@@ -329,7 +329,7 @@ struct plife_handle {
     int64_t snap_async_cap = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t snap_ready[2]{}, snap_done[2]{};
-    int snap_k = 0;
+    int64_t snap_issued = 0, snap_awaited = 0; // asynchronous snapshots requested / handed over by plife_snapshot_wait
     bool snap_init = false;
 
     int32_t *d_count = nullptr;   // per-cell histogram, zero between steps

@@ -140,6 +140,7 @@ class NativePhysics:
         self._check(fn(self.h, addr(pos), addr(vel), addr(types)))
 
     def snapshot_wait(self):
+        """Completes the OLDEST snapshot requested and not yet waited for (up to two may be in flight)."""
         self._check(self.L.plife_snapshot_wait(self.h))
 
     def init_uniform(self, n, seed):

@@ -341,6 +341,31 @@ def test_fp32_kernel_variants_match_oracle(native_lib, flags, bins, case):
 
 
 @pytest.mark.gpu
+def test_two_snapshots_in_flight(native_lib):
+    """plife_snapshot_wait hands over the OLDEST outstanding snapshot: request k + 1 before waiting for k (the bench's
+    end-to-end loop), a third request first completes the oldest; every snapshot equals the state it was taken from."""
+    pos, vel, types, matrix = make_state(50_000, 4, seed=33, vel_scale=0.05, f32=True)
+    p = plife.NativePhysics()
+    p.set_settings(0.02, 0.85, 1.0, True)
+    p.set_matrix(matrix)
+    p.upload(pos, vel, types)
+    n = p.count
+    bufs = [[np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)] for _ in range(3)]
+    refs = []
+    for k in range(3):  # three requests, no wait in between
+        p.step(DT, 2)
+        refs.append(p.download())
+        p.snapshot_async(*bufs[k], types_u8=True)
+    for k in range(3):
+        p.snapshot_wait()
+    p.snapshot_wait()  # nothing outstanding: returns at once
+    for k in range(3):
+        assert np.array_equal(bufs[k][0], refs[k].position.astype(np.float32))
+        assert np.array_equal(bufs[k][1], refs[k].velocity.astype(np.float32))
+        assert np.array_equal(bufs[k][2], refs[k].type.astype(np.uint8))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("bins", [1, 4, 8])
 def test_staged_kernel_rows_with_empty_ends(native_lib, bins):
     """Grid rows whose left and right ends are empty: in the sorted order the records next to a lane's candidate range then
