@@ -615,11 +615,15 @@ def run_ours(args):
         e2e_drain()
         barrier()
         t0 = time.perf_counter()
+        marks = []
         for _ in range(e2e_steps):
             e2e_step()
+            marks.append(time.perf_counter() - t0)
         e2e_drain()
         barrier()
         e2e_s = time.perf_counter() - t0
+        if args.verbose:
+            log("e2e iteration ends (ms): " + " ".join(f"{m * 1e3:.2f}" for m in marks) + f" | drained {e2e_s * 1e3:.2f}")
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
