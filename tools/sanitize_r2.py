@@ -1,4 +1,4 @@
-"""Driver for compute-sanitizer over the code paths added in round 2 (fine bins, bulk-copy staging, reference-slot rank,
+"""Driver for compute-sanitizer over the code paths added in round 2 (fine bins, four-wide staging with masked and unmasked walks, reference-slot rank,
 one-launch scan, small_sort, warp-per-cell kernel, graph replay, plife_rebuild, host-free slab step with the side stream):
 compute-sanitizer --tool memcheck python tools/sanitize_r2.py"""
 import sys, os
@@ -12,8 +12,11 @@ from helpers import make_state
 rng = np.random.default_rng(7)
 
 
-def run(n, m, rmax, wrap, flags=0, bins=0, steps=3, accel=(0, (0.3,)), precision=plife.F32, borders=True):
+def run(n, m, rmax, wrap, flags=0, bins=0, steps=3, accel=(0, (0.3,)), precision=plife.F32, borders=True, band=False):
     pos, vel, types, matrix = make_state(n, m, seed=n + m, vel_scale=0.2, f32=True)
+    if band:  # grid rows with empty ends: the CTAs straddle rows, the staged kernel walks with masks
+        pos[:, 0] = 0.41 + 0.05 * pos[:, 0]
+        pos = pos.astype(np.float32).astype(np.float64)
     if borders:
         pos[:10, 0] = 1.0
         pos[10:20, 1] = 1.0
@@ -37,6 +40,8 @@ for wrap in (True, False):
     run(70000, 5, 0.012, wrap, bins=8)                             # one-launch scan (several tiles), staged kernel, reference slots
     run(70000, 5, 0.012, wrap, bins=2, flags=plife.FLAG_SCAN3)
     run(70000, 5, 0.04, wrap)                                      # 112 particles per cell: chunked staging with fine bins
+    run(30000, 5, 0.02, wrap, flags=plife.FLAG_NO_CELLS, bins=8, band=True, borders=False)  # masked walk (rows with empty ends)
+    run(30000, 4, 0.02, wrap, flags=plife.FLAG_NO_CELLS, bins=4, accel=(3, ()))              # literal visitor in the staged kernel
     run(70000, 5, 0.004, wrap)                                     # one particle per cell: v1 kernel
     run(20000, 4, 0.03, wrap, precision=plife.F64)
 # plife_rebuild
