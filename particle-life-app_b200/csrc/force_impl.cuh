@@ -989,6 +989,13 @@ __global__ void __launch_bounds__(kForceThreads, PLIFE_STAGED4_MIN_BLOCKS)
     };
     if constexpr (FAST) {
         FastParticleLife32<kMatLaneTab> v(P, M);
+        { // {-b, -rmax} through a volatile shared-memory round trip of the thread's own slot: ptxas cannot rematerialise them
+          // from the constant bank inside the loop any more (two of 54 instructions per group)
+            __shared__ float2 s_c1[kForceThreads];
+            s_c1[tid] = v.c1;
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&s_c1[tid]);
+            asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.c1.x), "=f"(v.c1.y) : "r"(a) : "memory");
+        }
         walk(v, [&](uint32_t rb, int s_rel, int e_rel) { v.acc = walk_row4_call<kMatLaneTab>(rb, s_rel, e_rel, nself, v.acc, v.c1, M.row); });
         nvx = fmaf(P.fast_k, v.ax(), vx * P.mu);
         nvy = fmaf(P.fast_k, v.ay(), vy * P.mu);
