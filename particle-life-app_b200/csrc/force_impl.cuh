@@ -798,14 +798,20 @@ __device__ __forceinline__ uint32_t slot_x(uint32_t k) { return (k >> 2) * (uint
 // (LDG.128 -> 3 x STS.32, conflict-free); slots outside [lo, hi) become sentinels (far away, matrix key 0)
 __device__ __forceinline__ void stage_in4(unsigned char *base, const float4 *__restrict__ pt, int j0, int n_slots, int lo, int hi)
 {
+    // thread t owns the slots t, t + 128, ...: slot k lives at (k / 4) * 48 + (k % 4) * 4, i.e. a fixed 32 groups further per trip
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(base) + slot_x(threadIdx.x);
+    const float4 *src = pt + j0 + threadIdx.x;
+    const uint32_t len = (uint32_t)(hi - lo);
+    uint32_t rel = (uint32_t)(j0 + (int)threadIdx.x - lo); // record index relative to the range: in range <=> rel < len (unsigned)
     for (int k = threadIdx.x; k < n_slots; k += kForceThreads) {
-        const int j = j0 + k;
         float4 q = make_float4(kFar, kFar, 0.f, 0.f);
-        if (j >= lo && j < hi) q = __ldg(pt + j);
-        float *px = reinterpret_cast<float *>(base + slot_x((uint32_t)k));
-        px[0] = q.x;
-        px[4] = q.y;
-        px[8] = q.z;
+        if (rel < len) q = __ldg(src);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(q.x) : "memory");
+        asm volatile("st.shared.f32 [%0+16], %1;" ::"r"(dst), "f"(q.y) : "memory");
+        asm volatile("st.shared.f32 [%0+32], %1;" ::"r"(dst), "f"(q.z) : "memory");
+        dst += (kForceThreads / 4) * (uint32_t)kGroupBytes;
+        src += kForceThreads;
+        rel += kForceThreads;
     }
 }
 
