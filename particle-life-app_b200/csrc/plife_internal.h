@@ -198,16 +198,18 @@ __device__ __forceinline__ int reference_slot(int i, int cxy, const int32_t *__r
     if (g.ks == 0) return i;
     const int c0 = (container_of(cxy, g) >> g.ks) << g.ks; // first bin of the cell (bins per row is a multiple of K)
     const int cs = __ldg(cell_end + c0 - 1), ce = __ldg(cell_end + c0 + (1 << g.ks) - 1);
-    if (!key.cnt) { // one GPU: the raw pre-sort indices are the keys, no arrivals to look out for (stable_rank tracks their maximum)
+    if (!key.cnt) { // one GPU: no arrivals, the raw pre-sort indices are the keys and there is no maximum to track (stable_rank
+                    // does, to notice arrivals; a slab cannot skip it even for its interior rows: a fast particle may land there)
+        const int32_t *__restrict__ pp = src_sorted - first; // pp + k is 16-byte aligned where (k - first) % 4 == 0
         const int src = __ldg(src_sorted + i);
         int rank = 0, k = cs;
-        for (; k < ce && (k & 3); ++k) rank += (__ldg(src_sorted + k) < src) ? 1 : 0;
+        for (; k < ce && ((k - first) & 3); ++k) rank += (__ldg(pp + k) < src) ? 1 : 0;
         for (; k + 4 <= ce; k += 4) {
-            const int4 q = __ldg(reinterpret_cast<const int4 *>(src_sorted + k));
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(pp + k));
             rank += ((q.x < src) ? 1 : 0) + ((q.y < src) ? 1 : 0) + ((q.z < src) ? 1 : 0) + ((q.w < src) ? 1 : 0);
         }
-        for (; k < ce; ++k) rank += (__ldg(src_sorted + k) < src) ? 1 : 0;
-        return cs + rank;
+        for (; k < ce; ++k) rank += (__ldg(pp + k) < src) ? 1 : 0;
+        return cs - first + rank;
     }
     return cs - first + stable_rank(src_sorted - first, cs, ce, __ldg(src_sorted + i), first, key);
 }
