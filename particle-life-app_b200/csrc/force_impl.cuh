@@ -770,25 +770,24 @@ __device__ __forceinline__ void traverse_global32_plain(const IOF32 &io, const i
     }
 }
 
-// ---- v4: candidates staged four wide ------------------------------------------------------------------------------------
-// What binds force_kernel_staged at 16 particles per cell is the SM's shared-memory data pipe (ncu: l1tex data-pipe
-// wavefronts 95 % of peak, issue slots 71 %; profiles/r2_force_kernel.md): with fine bins the lanes of a warp read up to
-// 16 different 16-byte records per LDS.128, spread over a window of 32+ records - 4.5 wavefronts per candidate, plus one
-// for the matrix lookup.  Here the staging area holds the candidates in groups of four, {x0..x3 | y0..y3 | key0..key3}
-// (48 bytes), aligned to the global sorted index: a lane fetches a group with three LDS.128, and the 32 lanes of a warp
-// together touch some nine CONSECUTIVE groups per load (their range starts lie within ~32 records of each other), whose
-// 16-byte parts fall into different bank groups (the group stride of 3 x 16 bytes is coprime to 8): about two wavefronts
-// per load, 1.5 per candidate instead of 4.5.  The arithmetic per pair is the same, operation for operation, as in the
-// kernel above (bit-identical results); dx, dy, d2, {r, p} and the weight are formed for two candidates per packed
-// instruction.  The price: the ranges can no longer be bulk-copied (the records are transposed on the way in: LDG.128 ->
-// 3 x STS.32, conflict-free), and a lane's walk starts at the group boundary below its range (1.5 extra candidates per
-// row on average; they sit in bins left of the lane's window, beyond rmax in x: exact zeros like the padding at the end).
+// ---- the staged kernel: candidates four wide -------------------------------------------------------------------------------
+// At 16 particles per cell the pass is bound by the SM's ONE shared-memory data pipe (a 128-byte wavefront per cycle for all
+// four schedulers) and by its issue slots, not by HBM.  The predecessor of this kernel staged plain 16-byte records (bulk
+// copies) and read one per LDS.128: with fine bins the lanes of a warp then fetch up to 16 different records per load -
+// 4.5 wavefronts per candidate plus one for the matrix lookup, the pipe 95 % busy (ncu: l1tex__data_pipe_lsu_wavefronts),
+// the issue slots 71 % (profiles/r2_force_kernel.md).  Here the staging area holds the candidates in groups of four,
+// {x0..x3 | y0..y3 | key0..key3} (48 bytes), aligned to the global sorted index, and a lane fetches a group with three
+// LDS.128: 3.3 wavefronts per candidate (an LDS.128 costs the four quarter-warp phases whatever the addresses; the group
+// stride of 3 x 16 bytes is coprime to the 8 bank groups, so nothing is added: 1 % excessive wavefronts).  dx, dy, d2,
+// {r, p} and the weight are formed for two candidates per packed instruction (FADD2 / FFMA2): 52 instructions per group.
+// The price: the ranges are not bulk-copied any more (the records are transposed on the way in: LDG.128 -> 3 x STS.32,
+// conflict-free), and a lane's walk covers whole groups - the records next to its range come along (see walk_row4).
 #ifndef PLIFE_STAGED4_MIN_BLOCKS
 #define PLIFE_STAGED4_MIN_BLOCKS 10 // 48 registers: four candidates in flight per lane
 #endif
 constexpr int kGroupBytes = 48;
 constexpr int kStageLead = 4; // room for the groups' alignment below a range start
-constexpr int kStageTail = 4; // spare
+constexpr int kStageTail = 4; // sentinels after a range: the unmasked walk reads its last group in full
 constexpr float kFar = 1.0e9f; // x of a masked / sentinel candidate
 
 // smem byte offset of candidate slot k of a row (slots are group-aligned: 4 per 48-byte group)
